@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — K-hop propagation throughput on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload products]
+
+A "step" is one pass of the hot path over the synthetic graph: adjacency normalisation + K hops.
+  value        : K * nnz(A^) * F / t_step (edge*feat/s), raw CSR and features resident in HBM.
+  e2e          : the same through SymLaplacianGraphOp.propagate (host buffers in, host tensors out).
+  roofline     : the SpMM hop kernel, algorithmic gather-model bytes / CUDA-event time / measured HBM peak.
+  cpu_baseline : the reference's own matmul.c (oracle/_ref) on this box's host cores, one hop.
+`--impl reference` times the reference CPU implementation alone (same metric / unit / config).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, nnz of the symmetric adjacency without self loops, F, K)
+    "cora": (2708, 10556, 1433, 3),
+    "pubmed": (19717, 88648, 500, 5),
+    "arxiv": (169343, 1166243, 128, 3),
+    "products": (2449029, 61859140, 100, 3),
+}
+METRIC = "K-hop SpMM propagation throughput (normalisation + K hops)"
+UNIT = "edge*feat/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def synth_graph(n, nnz, seed=0):
+    from scalable_roubust_gnn_b200 import synth
+    return synth.uniform_graph(n, nnz, seed)
+
+
+def synth_features(n, f, seed=1):
+    from scalable_roubust_gnn_b200 import synth
+    return synth.features(n, f, seed)
+
+
+def gather_bytes(n, nnz_hat, f):
+    """CSR once, one F-vector per edge, output once."""
+    return nnz_hat * 8 + (n + 1) * 4 + nnz_hat * f * 4 + n * f * 4
+
+
+def comp_bytes(n, nnz_hat, f):
+    return nnz_hat * 8 + (n + 1) * 4 + 2 * n * f * 4
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_hop(adj_norm, x, reps=1):
+    """One hop of the reference's CPU path on this host: utils.py:38-47 marshalling + matmul.c."""
+    import oracle
+    kind = "reference" if oracle.have_ref() else "port"
+    lib = "ref" if kind == "reference" else "oracle"
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle.spmm_hop(adj_norm, x, lib=lib)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best, kind
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation (its matmul.c compiled in place), all
+    host threads, one hop of the workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    n, nnz, f, k = WORKLOADS[args.workload]
+    n, nnz = int(n * args.scale), int(nnz * args.scale)
+    a = synth_graph(n, nnz)
+    x = synth_features(n, f)
+    t0 = time.perf_counter()
+    adj_norm = oracle.sym_norm(a, 0.5)
+    t_norm = time.perf_counter() - t0
+    nnz_hat = adj_norm.nnz
+    kind = "reference" if oracle.have_ref() else "port"
+    lib = "ref" if kind == "reference" else "oracle"
+    for _ in range(args.warmup):
+        oracle.spmm_hop(adj_norm, x, lib=lib)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.spmm_hop(adj_norm, x, lib=lib)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = nnz_hat * f / dt
+    cores = os.cpu_count()
+    sample = f"one hop (utils.py:38-47 marshalling + matmul.c FloatCSRMulDenseOMP) over the full {args.workload}-shaped graph per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, n, nnz_hat, f, k),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "scipy_normalisation_s": t_norm},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n, nnz_hat, f, k):
+    return {"workload": f"{args.workload}-shaped synthetic uniform graph", "N": n, "nnz_hat": int(nnz_hat), "F": f,
+            "K": k, "r": 0.5, "scale": args.scale, "l2": "inputs (X, CSR) exceed L2; no flush needed" if n * f * 4 > 126e6
+            else "flushed between steps"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from scalable_roubust_gnn_b200 import _lib, device as dev
+    from scalable_roubust_gnn_b200.operators import SymLaplacianGraphOp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from scalable_roubust_gnn_b200 import dist_bench
+        return dist_bench.run(args, WORKLOADS, METRIC, UNIT)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    lib = _lib.load()
+
+    n, nnz, f, k = WORKLOADS[args.workload]
+    n, nnz = int(n * args.scale), int(nnz * args.scale)
+    t0 = time.perf_counter()
+    a = synth_graph(n, nnz)
+    x = synth_features(n, f)
+    log(f"[bench] graph N={n} nnz={a.nnz} F={f} K={k} generated in {time.perf_counter() - t0:.1f}s")
+
+    # ---- device-resident arm ---------------------------------------------------------------
+    a_dev = dev.upload_csr(a)                    # raw adjacency with its float64 ones, as scipy holds it
+    x_dev = dev.pack_features(torch.from_numpy(x).cuda())
+    ld = x_dev.shape[1]
+    hops = [x_dev] + [torch.empty_like(x_dev) for _ in range(k)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda") if n * f * 4 <= 126e6 else None
+
+    def step(ev=None):
+        norm, flags, _ = dev.sym_norm(a_dev, 0.5)
+        if ev is not None:
+            ev[0].record()
+        for i in range(1, k + 1):
+            dev.spmm(norm, hops[i - 1], f, out=hops[i])
+            if ev is not None:
+                ev[i].record()
+        return norm, flags
+
+    for _ in range(args.warmup):
+        norm, flags = step()
+    torch.cuda.synchronize()
+    assert int(flags.item()) == 0, f"normalisation flags {int(flags.item())}"
+    nnz_hat = int(norm.indptr[-1].item())
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(k + 2)] for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for s in range(args.steps):
+        if flush is not None:
+            flush.zero_()
+        evs[s][k + 1].record()          # step start
+        step(evs[s])
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+    step_ms = [evs[s][k + 1].elapsed_time(evs[s][k]) for s in range(args.steps)]
+    norm_ms = [evs[s][k + 1].elapsed_time(evs[s][0]) for s in range(args.steps)]
+    hop_ms = [evs[s][i - 1].elapsed_time(evs[s][i]) for s in range(args.steps) for i in range(1, k + 1)]
+    t_step = float(np.mean(step_ms)) * 1e-3
+    value = k * nnz_hat * f / t_step
+    peak, peak_src = measured_peak()
+    hop_avg = float(np.mean(hop_ms)) * 1e-3
+    bg = gather_bytes(n, nnz_hat, f)
+    achieved = bg / hop_avg / 1e9
+    roofline = {"bound": "hbm", "kernel": "spmm_group_kernel<float4,32,8> (one hop)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_launch": bg, "compulsory_bytes_per_launch": comp_bytes(n, nnz_hat, f),
+                "hop_ms_avg": hop_avg * 1e3, "hop_ms_min": float(np.min(hop_ms)), "frac_of_8TBps_nominal": achieved / 8000.0}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(args.workload)
+        except Exception:
+            pass
+
+    # ---- end to end through the public operator API (host buffers) ----------------------------
+    x_pin = torch.from_numpy(x).pin_memory()
+    a_pin = sp.csr_matrix((torch.from_numpy(a.data).pin_memory().numpy(), torch.from_numpy(a.indices).pin_memory().numpy(),
+                           torch.from_numpy(a.indptr).pin_memory().numpy()), shape=a.shape, copy=False)
+    op = SymLaplacianGraphOp(k, r=0.5)
+    e2e_steps = max(1, min(args.steps, 10))
+    for _ in range(2):
+        out = op.propagate(a_pin, x_pin.numpy())
+    del out
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = op.propagate(a_pin, x_pin.numpy())
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    checksum = float(out[-1][:: max(1, n // 1000)].double().sum())
+    h2d = a.indptr.nbytes + a.indices.nbytes + a.data.nbytes + x.nbytes
+    d2h = k * x.nbytes
+    e2e = {"value": k * nnz_hat * f / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": t_e2e * 1e3, "api": "SymLaplacianGraphOp(K).propagate(scipy_csr, float32 ndarray) -> K+1 CPU tensors",
+           "checksum": checksum}
+
+    # ---- CPU baseline on this host (bounded: one hop) -------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        import oracle
+        m = int(norm.indptr[-1].item())
+        adj_norm = sp.csr_matrix((norm.data[:m].cpu().numpy().astype(np.float64), norm.indices[:m].cpu().numpy(),
+                                  norm.indptr.cpu().numpy()), shape=(n, n))
+        dt, kind = cpu_reference_hop(adj_norm, x)
+        cpu = {"value": nnz_hat * f / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+               "sample": f"one hop of the full {args.workload}-shaped graph through the reference's matmul.c "
+                         f"(FloatCSRMulDenseOMP, OpenMP, all host threads) incl. its numpy marshalling", "hop_s": dt}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, n, nnz_hat, f, k),
+            "norm_ms": float(np.mean(norm_ms)), "hop_ms": float(np.mean(hop_ms)),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="products", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink N and nnz (smoke runs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,165 @@
+/*
+ * srgnn_b200.h — C ABI of libsrgnn_b200.so, the B200 (sm_100a) implementation of the
+ * K-hop feature-propagation path of yyysyyy/Scalable-Roubust-GNN.
+ *
+ * Reference interfaces replaced (paths relative to "Scalable Spectral Robust GNN/" = SSRG/):
+ *   - SSRG/operators/csrc/matmul.h:5        void FloatCSRMulDenseOMP(...)   (the CPU SpMM that runs today)
+ *   - SSRG/operators/csrc/cudamatmul.c:28   int  FloatCSRMulDense(...)      (dead cuSPARSE sibling)
+ *   - SSRG/operators/utils.py:17-47         csr_sparse_dense_matmul         (ctypes marshalling around the former)
+ *   - SSRG/operators/utils.py:81-93         adj_to_symmetric_norm           (scipy fp64 normalisation)
+ *   - SSRG/operators/base_operator.py:19-36 GraphOp.propagate               (K-hop loop)
+ *   - wavelet/src/utils.py:89-104,125-138   WaveletSparsifier               (Chebyshev heat filter + threshold)
+ *   - SSRG/data_process.py:35-67, SSRG/data_augument.py:28,99-102           (mask application / edge gather)
+ *
+ * Conventions
+ *   - plain C linkage, plain pointers and sizes; no torch / C++ types cross this boundary.
+ *   - every entry point returns 0 on success or a negative errno-style code; srg_last_error()
+ *     returns a thread-local human readable message for the last failure.
+ *   - "device" entry points take DEVICE pointers and a cudaStream_t passed as void* (NULL = legacy
+ *     default stream); they never synchronise the device and never allocate unless stated.
+ *   - "host" entry points take HOST pointers (pinned or pageable), do H2D / kernels / D2H
+ *     themselves on library-owned streams, and return after the results are in host memory.
+ *   - feature matrices are row-major fp32 with an explicit leading dimension (in floats).
+ *     The fast path needs ld % 4 == 0 and 16-byte aligned base pointers (128-bit loads);
+ *     anything else takes the scalar kernels.
+ *   - CSR: int32 indptr (n+1) and int32 indices, exactly what scipy hands the reference.
+ *     Products n*ld are formed in 64 bit (the reference's int offsets overflow at N*F >= 2^31,
+ *     SSRG/operators/csrc/matmul.c:29,33).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     SRG_ERR_NODEV.
+ */
+#ifndef SRGNN_B200_H
+#define SRGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRG_ABI_VERSION 1
+
+#define SRG_OK 0
+#define SRG_ERR_INVALID (-22) /* EINVAL: bad argument                     */
+#define SRG_ERR_NOMEM (-12)   /* ENOMEM: device / pinned allocation failed */
+#define SRG_ERR_CUDA (-5)     /* EIO:    CUDA runtime / kernel failure     */
+#define SRG_ERR_NODEV (-19)   /* ENODEV: no CUDA device                    */
+#define SRG_ERR_RANGE (-34)   /* ERANGE: size exceeds an int32 CSR limit   */
+#define SRG_ERR_UNSUPPORTED (-95) /* ENOTSUP: input needs a path not built yet (see message) */
+
+/* dtype tags for the adjacency value array */
+#define SRG_VAL_ONES 0 /* data == NULL, every stored entry is 1.0 (unweighted graph) */
+#define SRG_VAL_F32 1
+#define SRG_VAL_F64 2
+
+/* bits reported in the int32 flags word written by the normalisation entry points */
+#define SRG_FLAG_UNSORTED 1       /* input rows not strictly increasing (duplicates / unsorted)      */
+#define SRG_FLAG_ASYMMETRIC 2     /* pattern of (A+I) not symmetric: general transpose path required */
+#define SRG_FLAG_ZERO_PRODUCT 4   /* a normalised value is exactly 0: scipy would drop the entry     */
+#define SRG_FLAG_BAD_INDEX 8      /* a column index is outside [0, n)                                */
+
+/* ---- library / diagnostics ------------------------------------------------------------- */
+int srg_abi_version(void);
+const char *srg_last_error(void);
+/* number of visible CUDA devices (0 when there is none; never fails) */
+int srg_device_count(void);
+/* counts kernels launched by this library in the calling process (bench "gpu_launches") */
+int64_t srg_launch_count(void);
+
+/* ---- a3: adjacency normalisation  (SSRG/operators/utils.py:81-93) ------------------------ */
+/*
+ * Stage 1.  Structure of A~ = A + I over a canonical CSR (sorted rows, no duplicates).
+ *   out_indptr[n+1] : row pointer of A~ (explicit zeros and entries cancelled by +I are dropped,
+ *                     as scipy's csr_plus_csr does)
+ *   out_count[n]    : nullable; entries per row of A~ (= integer degree incl. the self loop for
+ *                     an unweighted graph)
+ *   out_flags       : device int32, OR of SRG_FLAG_* (caller zeroes it)
+ * Allocates scan scratch with cudaMallocAsync on `stream`.
+ */
+int srg_degree_selfloop_csr(const int32_t *indptr, const int32_t *indices, const void *data,
+                            int val_dtype, int64_t n, int32_t *out_indptr, int32_t *out_count,
+                            int32_t *out_flags, void *stream);
+
+/*
+ * Stage 2.  R = D^(r-1) A~^T D^(-r)   (R[a,b] = (A~[b,a] * d_a^(r-1)) * d_b^(-r), fp64, this
+ * multiply order) and optionally the PPR blend (1-alpha)*R + alpha*I
+ * (SSRG/operators/graph_operator/symmetrical_simgraph_ppr_operator.py:19-20) when ppr_alpha >= 0.
+ *   nnz                        : stored entries of A (capacity of the outputs is nnz + n)
+ *   out_indices[out_indptr[n]] : column indices of R, sorted per row
+ *   out_degree[n]              : nullable; d = A~.sum(1) in fp64, summed in numpy's add.reduceat
+ *                                order (first element + 8-lane pairwise sum of the rest)
+ *   out_val_f64 / out_val_f32  : either may be NULL; f32 = round-to-nearest of the fp64 value,
+ *                                i.e. the `adj.data.astype(np.float32)` of utils.py:39
+ * Symmetric-pattern path: sets SRG_FLAG_ASYMMETRIC (outputs then undefined) when A~ has an entry
+ * (a,b) without (b,a); SRG_FLAG_ZERO_PRODUCT when a value is exactly 0 (scipy drops those).
+ * Allocates scratch with cudaMallocAsync on `stream`.
+ */
+int srg_sym_norm_csr(const int32_t *indptr, const int32_t *indices, const void *data,
+                     int val_dtype, int64_t n, int64_t nnz, const int32_t *out_indptr, double r,
+                     double ppr_alpha, int32_t *out_indices, double *out_degree,
+                     double *out_val_f64, float *out_val_f32, int32_t *out_flags, void *stream);
+
+/* ---- a5/a6: one propagation hop  (SSRG/operators/csrc/matmul.c:23-40) --------------------- */
+/*
+ * Y[i, 0:F] = sum_j vals[j] * X[indices[j], 0:F]  for j in indptr[i]..indptr[i+1], evaluated
+ * per output element as a sequential fp32 FMA chain in CSR order starting from 0.0f, which is
+ * the arithmetic of the reference's vfmadd loop, so results are bit-identical to it.
+ * Y is overwritten (the reference accumulates into a pre-zeroed buffer).
+ * n_rows rows of the CSR are processed; column indices address rows of X (global ids).
+ */
+int srg_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
+                     int64_t n_rows, const float *X, int64_t ldx, float *Y, int64_t ldy,
+                     int32_t F, void *stream);
+
+/* ---- a1: K hops, device resident  (SSRG/operators/base_operator.py:31-35) ------------------ */
+/* hops[0] = input features, hops[k] = A^ * hops[k-1], k = 1..K; all n x ld fp32 device buffers. */
+int srg_propagate_khop_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
+                           int64_t n, float *const *hops, int64_t ld, int32_t F, int32_t K,
+                           void *stream);
+
+/* layout helpers: host layout (ld == F) <-> padded device layout (ld % 8 == 0, pad = 0).
+ * mask (optional, int32 n x F, SSRG/data_process.py:38-39) is applied as x * mask
+ * (SSRG/data_augument.py:28) while repacking. */
+int srg_pack_features_f32(const float *src, int64_t ld_src, float *dst, int64_t ld_dst,
+                          int64_t n, int32_t F, const int32_t *mask, void *stream);
+int srg_unpack_features_f32(const float *src, int64_t ld_src, float *dst, int64_t ld_dst,
+                            int64_t n, int32_t F, void *stream);
+
+/* ---- a1..a7 in one call, host buffers  (GraphOp.propagate) ---------------------------------- */
+/*
+ * Host CSR of the RAW adjacency + host features -> K host output matrices (hop 1..K), each
+ * n x F fp32 C-contiguous.  Does normalisation (r, ppr_alpha as above) and the hops on
+ * `device`; out_norm_* (all nullable) receive the normalised CSR (scipy layout: int32 indptr
+ * n+1, int32 indices, fp64 data; capacity nnz + n entries); *out_nnz receives its nnz.
+ * feature_mask: optional host int32 n x F.
+ */
+int srg_propagate_host(const int32_t *indptr, const int32_t *indices, const void *data,
+                       int val_dtype, int64_t n, int64_t nnz, const float *features, int32_t F,
+                       const int32_t *feature_mask, int32_t K, double r, double ppr_alpha,
+                       float *const *out_hops, int32_t *out_norm_indptr,
+                       int32_t *out_norm_indices, double *out_norm_data, int64_t *out_nnz,
+                       int device);
+
+/* construct_adj alone on host buffers (same outputs as above; capacity nnz + n). */
+int srg_construct_adj_host(const int32_t *indptr, const int32_t *indices, const void *data,
+                           int val_dtype, int64_t n, int64_t nnz, double r, double ppr_alpha,
+                           int32_t *out_indptr, int32_t *out_indices, double *out_data,
+                           int64_t *out_nnz, int device);
+
+/* release cached device workspaces / pinned staging owned by the host entry points */
+int srg_release_workspace(void);
+
+/* ---- literal ABI shims: same symbol names and signatures as the reference's libraries, so
+ * SSRG/operators/utils.py can load this library in place of ./csrc/libmatmul.so or
+ * ./csrc/libcudamatmul.so unmodified.  Host pointers; answer is accumulated into
+ * (answer += A*mat) exactly as matmul.c does. ------------------------------------------------ */
+void FloatCSRMulDenseOMP(float answer[], float data[], int indices[], int indptr[], float mat[],
+                         int mat_row, int mat_col);
+int FloatCSRMulDense(float answer[], int data_nnz, float data[], int indices[], int indptr[],
+                     float mat[], int mat_row, int mat_col);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRGNN_B200_H */

@@ -1,0 +1,258 @@
+"""oracle — CPU restatement of the reference's propagation path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import this package, and only as the checker or the timed CPU baseline.  The product
+(``scalable_roubust_gnn_b200``) never imports it and has no CPU fallback.
+
+What it restates (file:line in /root/reference, SSRG = "Scalable Spectral Robust GNN"):
+  sym_norm          SSRG/operators/utils.py:81-93  adj_to_symmetric_norm, driven as in
+                    SSRG/operators/graph_operator/symmetrical_simgraph_laplacian_operator.py:12-15
+                    and .../symmetrical_simgraph_ppr_operator.py:13-21
+  spmm_hop          SSRG/operators/utils.py:17-47 + SSRG/operators/csrc/matmul.c:23-40
+  propagate         SSRG/operators/base_operator.py:19-36
+  feature_mask / edge_mask / symmetrize_edges
+                    SSRG/data_process.py:35-41, :43-67, SSRG/data_augument.py:28, :99-102
+  cheby_*           pygsp 0.5.1 (PyPI "PyGSP", un-pinned and absent from /root/reference):
+                    call sites wavelet/src/utils.py:83,95,131-133 and
+                    SSRG/models/base_scalable/base_model.py:184-189,243  -- PARITY UNPINNED
+  row_partition     new functionality (no reference code): the bit-exact partition map
+
+Pinning: tests/test_oracle.py checks these against tests/golden/*.npz (outputs of the real
+reference package imported in the build container by tests/golden/make_golden.py) and against
+oracle/_ref/libmatmul_ref.so (the reference's matmul.c compiled in place by oracle/Makefile).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import scipy.sparse as sp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_SO = os.path.join(_HERE, "liboracle.so")
+_REF_SO = os.path.join(_HERE, "_ref", "libmatmul_ref.so")
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, ndim=1, flags="CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, ndim=1, flags="CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, ndim=1, flags="CONTIGUOUS")
+
+
+def build(ref: bool = True) -> None:
+    """Compile liboracle.so (and oracle/_ref when /root/reference is present)."""
+    subprocess.run(["make", "-C", _HERE] + ([] if ref else ["liboracle.so"]), check=True, capture_output=True)
+
+
+_oracle_lib = None
+_ref_lib = None
+
+
+def _lib():
+    global _oracle_lib
+    if _oracle_lib is None:
+        if not os.path.exists(_ORACLE_SO):
+            build(ref=False)
+        lib = C.CDLL(_ORACLE_SO)
+        lib.oracle_spmm_csr_f32.argtypes = [_f32p, C.c_int64, _f32p, _i32p, _i32p, _f32p, C.c_int64, C.c_int64, C.c_int32]
+        lib.oracle_spmm_csr_f32.restype = None
+        lib.oracle_spmm_csr_f64.argtypes = [_f64p, C.c_int64, _f64p, _i32p, _i32p, _f64p, C.c_int64, C.c_int64, C.c_int32]
+        lib.oracle_spmm_csr_f64.restype = None
+        _oracle_lib = lib
+    return _oracle_lib
+
+
+def have_ref() -> bool:
+    return os.path.exists(_REF_SO)
+
+
+def ref_lib():
+    """The reference's own matmul.c, compiled (oracle/Makefile).  None if it was never built."""
+    global _ref_lib
+    if _ref_lib is None and have_ref():
+        lib = C.CDLL(_REF_SO)
+        lib.FloatCSRMulDenseOMP.argtypes = [_f32p, _f32p, _i32p, _i32p, _f32p, C.c_int, C.c_int]
+        lib.FloatCSRMulDenseOMP.restype = None
+        _ref_lib = lib
+    return _ref_lib
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation
+# ------------------------------------------------------------------------------------------------
+def sym_norm(adj, r, ppr_alpha=None):
+    """R = D^(r-1) (A+I)^T D^(-r) as a canonical CSR (int32 indices, float64 data).
+
+    Restated entry-wise instead of as the reference's chain of diagonal products:
+        A~ = A + I (duplicates summed, exact zeros dropped);  d = row sums of A~ (fp64)
+        dl = d**(r-1), dr = d**(-r), inf -> 0
+        R[a, b] = (A~[b, a] * dl[a]) * dr[b]          (this multiply order, fp64)
+        exact zeros dropped (scipy's csr_matmat omits them)
+        PPR:  R <- (1 - alpha) * R;  R[a, a] += alpha
+    """
+    n = adj.shape[0]
+    a_tilde = (sp.csr_matrix(adj, dtype=np.float64) + sp.identity(n, dtype=np.float64, format="csr")).tocsr()
+    a_tilde.sum_duplicates()
+    d = np.asarray(a_tilde.sum(axis=1)).reshape(-1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dl = np.power(d, r - 1)
+        dr = np.power(d, -r)
+    dl[np.isinf(dl)] = 0.0
+    dr[np.isinf(dr)] = 0.0
+    t = a_tilde.transpose().tocsr()  # t[a, b] = A~[b, a]; structure-only operation
+    t.sort_indices()
+    rows = np.repeat(np.arange(n), np.diff(t.indptr))
+    vals = (t.data * dl[rows]) * dr[t.indices]
+    out = sp.csr_matrix((vals, t.indices.astype(np.int32), t.indptr.astype(np.int32)), shape=(n, n))
+    out.eliminate_zeros()
+    if ppr_alpha is not None:
+        out.data = (1 - ppr_alpha) * out.data
+        diag_pos = out.indices == np.repeat(np.arange(n), np.diff(out.indptr))
+        # A^ has a full diagonal whenever d > 0; rows whose diagonal vanished get a fresh entry
+        has_diag = np.zeros(n, dtype=bool)
+        has_diag[out.indices[diag_pos]] = True
+        out.data[diag_pos] = out.data[diag_pos] + ppr_alpha
+        if not has_diag.all():
+            missing = np.flatnonzero(~has_diag)
+            extra = sp.csr_matrix((np.full(len(missing), float(ppr_alpha)), (missing, missing)), shape=(n, n))
+            out = (out + extra).tocsr()
+        out.eliminate_zeros()
+        out.sort_indices()
+    out.indices = out.indices.astype(np.int32)
+    out.indptr = out.indptr.astype(np.int32)
+    return out
+
+
+def selfloop_structure(adj):
+    """(indptr, indices, degree) of A~ = A + I: the integer part of the normalisation."""
+    n = adj.shape[0]
+    a_tilde = (sp.csr_matrix(adj, dtype=np.float64) + sp.identity(n, dtype=np.float64, format="csr")).tocsr()
+    a_tilde.sum_duplicates()
+    a_tilde.sort_indices()
+    d = np.asarray(a_tilde.sum(axis=1)).reshape(-1)
+    return a_tilde.indptr.astype(np.int32), a_tilde.indices.astype(np.int32), d
+
+
+# ------------------------------------------------------------------------------------------------
+# propagation
+# ------------------------------------------------------------------------------------------------
+def spmm_hop(adj_norm, feature, lib="oracle"):
+    """One hop in the reference's fp32 arithmetic (utils.py:38-47 marshalling + matmul.c:23-40)."""
+    feature = np.ascontiguousarray(feature, dtype=np.float32)
+    n, f = feature.shape
+    data = adj_norm.data.astype(np.float32)
+    indices = np.ascontiguousarray(adj_norm.indices, dtype=np.int32)
+    indptr = np.ascontiguousarray(adj_norm.indptr, dtype=np.int32)
+    answer = np.zeros(n * f, dtype=np.float32)
+    mat = feature.reshape(-1)
+    if lib == "ref":
+        rl = ref_lib()
+        if rl is None:
+            raise RuntimeError("oracle/_ref/libmatmul_ref.so not built")
+        rl.FloatCSRMulDenseOMP(answer, data, indices, indptr, mat, n, f)
+    else:
+        _lib().oracle_spmm_csr_f32(answer, f, data, indices, indptr, mat, f, adj_norm.shape[0], f)
+    return answer.reshape(adj_norm.shape[0], f)
+
+
+def propagate(adj, feature, prop_steps, r=0.5, ppr_alpha=None, lib="oracle"):
+    """[X, A^X, ..., A^^K X] as float32 arrays (base_operator.py:31-36)."""
+    adj_norm = sym_norm(adj, r, ppr_alpha)
+    out = [np.ascontiguousarray(feature, dtype=np.float32)]
+    for _ in range(prop_steps):
+        out.append(spmm_hop(adj_norm, out[-1], lib=lib))
+    return out, adj_norm
+
+
+# ------------------------------------------------------------------------------------------------
+# sparsity masks (torch CPU RNG defines them)
+# ------------------------------------------------------------------------------------------------
+def feature_mask(shape, rate):
+    """`(torch.rand(shape) > r).int()` — data_process.py:38-39 (first RNG draw after seeding)."""
+    import torch
+    return (torch.rand(shape) > rate).int()
+
+
+def edge_mask(num_upper_edges, rate):
+    """`torch.randperm(E)[int(E*rate):]` — data_process.py:55,65."""
+    import torch
+    return torch.randperm(num_upper_edges)[int(num_upper_edges * rate):]
+
+
+def upper_edges(adj):
+    """canonical (row-major sorted) edges with col > row — data_process.py:48-53."""
+    coo = sp.coo_matrix(adj)
+    keep = coo.col > coo.row
+    return np.stack([coo.row[keep], coo.col[keep]]).astype(np.int64)
+
+
+def symmetrize_edges(edge_index, n):
+    """undirected, duplicate-free adjacency of an edge list (data_augument.py:99-102) as CSR of ones."""
+    e = np.asarray(edge_index, dtype=np.int64)
+    both = np.concatenate([e, e[::-1]], axis=1)
+    key = np.unique(both[0] * n + both[1])
+    row, col = key // n, key % n
+    return sp.csr_matrix((np.ones(len(key), dtype=np.float64), (row, col)), shape=(n, n))
+
+
+# ------------------------------------------------------------------------------------------------
+# Chebyshev heat filter — restated from pygsp 0.5.1 (parity unpinned, see module docstring)
+# ------------------------------------------------------------------------------------------------
+def combinatorial_laplacian(adj):
+    """L = D - W with W the symmetrised adjacency nx.Graph(adj) gives (max of the two directions
+    for an unweighted graph), pygsp Graph(W).L, lap_type='combinatorial'."""
+    w = sp.csr_matrix(adj, dtype=np.float64)
+    w = w.maximum(w.T).tocsr()
+    d = np.asarray(w.sum(axis=1)).reshape(-1)
+    lap = (sp.diags(d) - w).tocsr()
+    lap.sort_indices()
+    return lap
+
+
+def estimate_lmax(lap):
+    """pygsp Graph.estimate_lmax: 1.01 * largest eigenvalue by ARPACK (tol 5e-3, ncv=min(N,10))."""
+    from scipy.sparse.linalg import eigsh
+    n = lap.shape[0]
+    lmax = eigsh(lap, k=1, tol=5e-3, ncv=min(n, 10), return_eigenvectors=False)[0]
+    return float(lmax) * 1.01
+
+
+def cheby_coeff_heat(tau, lmax, order):
+    """compute_cheby_coeff(Heat(G, tau), m=order): N = order + 1 quadrature points."""
+    n_q = order + 1
+    a1 = a2 = lmax / 2.0
+    j = np.arange(n_q)
+    theta = np.pi * (j + 0.5) / n_q
+    g = np.exp(-tau * (a1 * np.cos(theta) + a2) / lmax)
+    return np.array([2.0 / n_q * np.sum(g * np.cos(np.pi * o * (j + 0.5) / n_q)) for o in range(order + 1)])
+
+
+def cheby_op(lap, coeffs, signal, lmax):
+    """pygsp cheby_op for a list of coefficient vectors sharing the T_k (fp64)."""
+    coeffs = np.atleast_2d(np.asarray(coeffs, dtype=np.float64))
+    a1 = a2 = lmax / 2.0
+    x = np.asarray(signal, dtype=np.float64)
+    t_old = x
+    t_cur = (lap.dot(x) - a2 * x) / a1
+    res = [0.5 * c[0] * t_old + c[1] * t_cur for c in coeffs]
+    for k in range(2, coeffs.shape[1]):
+        t_new = (2.0 / a1) * (lap.dot(t_cur) - a2 * t_cur) - t_old
+        res = [rs + c[k] * t_new for rs, c in zip(res, coeffs)]
+        t_old, t_cur = t_cur, t_new
+    return res
+
+
+def wavelet_threshold(coeffs, tol):
+    """`coeffs[coeffs < tol] = 0` then float32 CSR (wavelet/src/utils.py:98-103)."""
+    c = np.array(coeffs, dtype=np.float64, copy=True)
+    c[c < tol] = 0
+    return sp.csr_matrix(c, dtype=np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# row partition (new functionality; the oracle is its 3-line definition)
+# ------------------------------------------------------------------------------------------------
+def row_partition(n, world):
+    rows_per = -(-n // world)
+    starts = np.minimum(np.arange(world + 1, dtype=np.int64) * rows_per, n)
+    return rows_per, starts

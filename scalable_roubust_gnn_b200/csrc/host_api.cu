@@ -1,0 +1,441 @@
+// host_api.cu — library core (errors, counters) and the HOST-buffer entry points.
+//
+//   srg_propagate_host      = GraphOp.propagate           (SSRG/operators/base_operator.py:19-36)
+//   srg_construct_adj_host  = GraphOp.construct_adj        (SSRG/operators/graph_operator/*.py)
+//   FloatCSRMulDenseOMP     = literal ABI of SSRG/operators/csrc/matmul.h:5
+//   FloatCSRMulDense        = literal ABI of SSRG/operators/csrc/cudamatmul.c:28
+//
+// Pipeline of srg_propagate_host (three library-owned streams, no host threads):
+//   copy-in stream : H2D raw CSR, then H2D features (+ pack into the padded device layout)
+//   compute stream : normalisation kernels (overlap the feature upload), then K SpMM hops
+//   copy-out stream: after hop k: unpack to the host layout and D2H, overlapping hop k+1
+// Device memory comes from the stream-ordered pool (cudaMallocAsync) whose release threshold is
+// raised so repeated calls reuse the same blocks.
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace srg {
+
+std::atomic<long long> g_launches{0};
+
+char *err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+void set_err(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+}
+
+int require_device() {
+  static std::atomic<int> cached{-1};
+  int c = cached.load(std::memory_order_relaxed);
+  if (c < 0) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+      n = 0;
+      (void)cudaGetLastError();
+    }
+    cached.store(n, std::memory_order_relaxed);
+    c = n;
+  }
+  if (c <= 0) {
+    set_err("no CUDA device visible: libsrgnn_b200 has no CPU fallback");
+    return SRG_ERR_NODEV;
+  }
+  return SRG_OK;
+}
+
+int spmm_csr_f32_impl(const int32_t *indptr, const int32_t *indices, const float *vals,
+                      int64_t n_rows, const float *X, int64_t ldx, float *Y, int64_t ldy,
+                      int32_t F, bool accumulate, cudaStream_t s);
+
+// ---- per-device state of the host entry points -------------------------------------------------
+struct DeviceState {
+  bool init = false;
+  cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
+  cudaEvent_t ev_csr = nullptr, ev_x = nullptr, ev_norm = nullptr;
+  std::vector<cudaEvent_t> ev_hop;
+};
+static std::mutex g_state_mu;
+static DeviceState g_state[64];
+
+static int get_state(int device, DeviceState **out) {
+  SRG_REQUIRE(device >= 0 && device < 64, "bad device ordinal %d", device);
+  std::lock_guard<std::mutex> lk(g_state_mu);
+  DeviceState &st = g_state[device];
+  if (!st.init) {
+    SRG_CUDA(cudaStreamCreateWithFlags(&st.s_in, cudaStreamNonBlocking));
+    SRG_CUDA(cudaStreamCreateWithFlags(&st.s_compute, cudaStreamNonBlocking));
+    SRG_CUDA(cudaStreamCreateWithFlags(&st.s_out, cudaStreamNonBlocking));
+    SRG_CUDA(cudaEventCreateWithFlags(&st.ev_csr, cudaEventDisableTiming));
+    SRG_CUDA(cudaEventCreateWithFlags(&st.ev_x, cudaEventDisableTiming));
+    SRG_CUDA(cudaEventCreateWithFlags(&st.ev_norm, cudaEventDisableTiming));
+    cudaMemPool_t pool;
+    SRG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thresh = UINT64_MAX;
+    SRG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    st.init = true;
+  }
+  *out = &st;
+  return SRG_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// stream-ordered allocations released at scope exit
+struct PoolAllocs {
+  cudaStream_t s;
+  std::vector<void *> ptrs;
+  bool clean = false;  // set once every stream that touched the blocks has been synchronised
+  explicit PoolAllocs(cudaStream_t s_) : s(s_) {}
+  template <typename T> int alloc(T **p, int64_t count) {
+    *p = nullptr;
+    if (count <= 0) count = 1;
+    void *q = nullptr;
+    SRG_CUDA(cudaMallocAsync(&q, (size_t)count * sizeof(T), s));
+    ptrs.push_back(q);
+    *p = static_cast<T *>(q);
+    return SRG_OK;
+  }
+  ~PoolAllocs() {
+    if (!clean) cudaDeviceSynchronize();  // error path: other streams may still use the blocks
+    for (void *q : ptrs) cudaFreeAsync(q, s);
+  }
+};
+
+static inline size_t val_bytes(int dt) { return dt == SRG_VAL_F32 ? 4 : dt == SRG_VAL_F64 ? 8 : 0; }
+static inline int64_t pad8(int64_t f) { return (f + 7) / 8 * 8; }
+
+static int check_flags(int flags) {
+  if (flags & SRG_FLAG_BAD_INDEX) {
+    set_err("adjacency has a column index outside [0, n)");
+    return SRG_ERR_INVALID;
+  }
+  if (flags & SRG_FLAG_UNSORTED) {
+    set_err("adjacency CSR is not canonical (unsorted or duplicate column indices); canonicalise it first");
+    return SRG_ERR_UNSUPPORTED;
+  }
+  if (flags & SRG_FLAG_ASYMMETRIC) {
+    set_err("adjacency pattern is not symmetric; the general transpose path is required");
+    return SRG_ERR_UNSUPPORTED;
+  }
+  if (flags & SRG_FLAG_ZERO_PRODUCT) {
+    set_err("a normalised value is exactly 0 (scipy would drop the entry); compaction path required");
+    return SRG_ERR_UNSUPPORTED;
+  }
+  return SRG_OK;
+}
+
+// normalisation on the compute stream from device copies of the raw CSR
+struct NormOut {
+  int32_t *indptr = nullptr, *indices = nullptr;
+  double *val64 = nullptr;
+  float *val32 = nullptr;
+  int32_t *flags = nullptr;
+};
+
+static int run_norm(PoolAllocs &pa, const int32_t *d_indptr, const int32_t *d_indices,
+                    const void *d_data, int val_dtype, int64_t n, int64_t nnz, double r,
+                    double ppr_alpha, bool want64, bool want32, cudaStream_t s, NormOut *o) {
+  int rc;
+  if ((rc = pa.alloc(&o->indptr, n + 1))) return rc;
+  if ((rc = pa.alloc(&o->indices, nnz + n))) return rc;
+  if (want64 && (rc = pa.alloc(&o->val64, nnz + n))) return rc;
+  if (want32 && (rc = pa.alloc(&o->val32, nnz + n))) return rc;
+  if ((rc = pa.alloc(&o->flags, 1))) return rc;
+  SRG_CUDA(cudaMemsetAsync(o->flags, 0, sizeof(int32_t), s));
+  rc = srg_degree_selfloop_csr(d_indptr, d_indices, d_data, val_dtype, n, o->indptr, nullptr, o->flags, s);
+  if (rc) return rc;
+  return srg_sym_norm_csr(d_indptr, d_indices, d_data, val_dtype, n, nnz, o->indptr, r, ppr_alpha,
+                          o->indices, nullptr, o->val64, o->val32, o->flags, s);
+}
+
+}  // namespace srg
+
+using namespace srg;
+
+extern "C" int srg_abi_version(void) { return SRG_ABI_VERSION; }
+extern "C" const char *srg_last_error(void) { return err_buf(); }
+extern "C" int srg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+extern "C" int64_t srg_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int srg_release_workspace(void) {
+  std::lock_guard<std::mutex> lk(g_state_mu);
+  for (int d = 0; d < 64; ++d) {
+    DeviceState &st = g_state[d];
+    if (!st.init) continue;
+    DeviceGuard g(d);
+    cudaDeviceSynchronize();
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  }
+  return SRG_OK;
+}
+
+extern "C" int srg_construct_adj_host(const int32_t *indptr, const int32_t *indices,
+                                      const void *data, int val_dtype, int64_t n, int64_t nnz,
+                                      double r, double ppr_alpha, int32_t *out_indptr,
+                                      int32_t *out_indices, double *out_data, int64_t *out_nnz,
+                                      int device) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n >= 0 && nnz >= 0, "construct_adj: negative size");
+  SRG_REQUIRE(indptr && out_indptr && out_nnz, "construct_adj: NULL pointer");
+  SRG_REQUIRE(nnz == 0 || indices, "construct_adj: indices is NULL");
+  SRG_REQUIRE(val_dtype >= 0 && val_dtype <= 2, "construct_adj: bad val_dtype");
+  SRG_REQUIRE(val_dtype == SRG_VAL_ONES || nnz == 0 || data, "construct_adj: data is NULL");
+  SRG_REQUIRE(nnz + n <= 2147483647LL, "construct_adj: nnz + n exceeds the int32 CSR range");
+  DeviceGuard guard(device);
+  SRG_REQUIRE(guard.ok, "construct_adj: cannot select device %d", device);
+  DeviceState *st;
+  if ((rc = get_state(device, &st))) return rc;
+  cudaStream_t s = st->s_compute;
+  if (n == 0) {
+    out_indptr[0] = 0;
+    *out_nnz = 0;
+    return SRG_OK;
+  }
+  int flags = 0;
+  int32_t nnz_out = 0;
+  {
+    PoolAllocs pa(s);
+    int32_t *d_indptr, *d_indices;
+    char *d_data = nullptr;
+    if ((rc = pa.alloc(&d_indptr, n + 1))) return rc;
+    if ((rc = pa.alloc(&d_indices, nnz))) return rc;
+    SRG_CUDA(cudaMemcpyAsync(d_indptr, indptr, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
+    if (nnz) SRG_CUDA(cudaMemcpyAsync(d_indices, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
+    if (val_dtype != SRG_VAL_ONES) {
+      if ((rc = pa.alloc(&d_data, nnz * (int64_t)val_bytes(val_dtype)))) return rc;
+      if (nnz) SRG_CUDA(cudaMemcpyAsync(d_data, data, (size_t)nnz * val_bytes(val_dtype), cudaMemcpyHostToDevice, s));
+    }
+    NormOut no;
+    if ((rc = run_norm(pa, d_indptr, d_indices, d_data, val_dtype, n, nnz, r, ppr_alpha,
+                       out_data != nullptr, false, s, &no)))
+      return rc;
+    SRG_CUDA(cudaMemcpyAsync(&flags, no.flags, 4, cudaMemcpyDeviceToHost, s));
+    SRG_CUDA(cudaMemcpyAsync(out_indptr, no.indptr, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, s));
+    SRG_CUDA(cudaStreamSynchronize(s));
+    if ((rc = check_flags(flags))) return rc;
+    nnz_out = out_indptr[n];
+    if (out_indices) SRG_CUDA(cudaMemcpyAsync(out_indices, no.indices, (size_t)nnz_out * 4, cudaMemcpyDeviceToHost, s));
+    if (out_data) SRG_CUDA(cudaMemcpyAsync(out_data, no.val64, (size_t)nnz_out * 8, cudaMemcpyDeviceToHost, s));
+    SRG_CUDA(cudaStreamSynchronize(s));
+    pa.clean = true;
+  }
+  *out_nnz = nnz_out;
+  return SRG_OK;
+}
+
+extern "C" int srg_propagate_host(const int32_t *indptr, const int32_t *indices, const void *data,
+                                  int val_dtype, int64_t n, int64_t nnz, const float *features,
+                                  int32_t F, const int32_t *feature_mask, int32_t K, double r,
+                                  double ppr_alpha, float *const *out_hops,
+                                  int32_t *out_norm_indptr, int32_t *out_norm_indices,
+                                  double *out_norm_data, int64_t *out_nnz, int device) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n >= 0 && nnz >= 0 && F >= 0 && K >= 0, "propagate_host: negative size");
+  SRG_REQUIRE(indptr, "propagate_host: indptr is NULL");
+  SRG_REQUIRE(nnz == 0 || indices, "propagate_host: indices is NULL");
+  SRG_REQUIRE(val_dtype >= 0 && val_dtype <= 2, "propagate_host: bad val_dtype");
+  SRG_REQUIRE(val_dtype == SRG_VAL_ONES || nnz == 0 || data, "propagate_host: data is NULL");
+  SRG_REQUIRE(n * (int64_t)F == 0 || features, "propagate_host: features is NULL");
+  SRG_REQUIRE(K == 0 || out_hops, "propagate_host: out_hops is NULL");
+  SRG_REQUIRE(nnz + n <= 2147483647LL, "propagate_host: nnz + n exceeds the int32 CSR range");
+  for (int k = 0; k < K; ++k)
+    SRG_REQUIRE(n * (int64_t)F == 0 || out_hops[k], "propagate_host: out_hops[%d] is NULL", k);
+  if (out_nnz) *out_nnz = 0;
+  if (n == 0) {
+    if (out_norm_indptr) out_norm_indptr[0] = 0;
+    return SRG_OK;
+  }
+  DeviceGuard guard(device);
+  SRG_REQUIRE(guard.ok, "propagate_host: cannot select device %d", device);
+  DeviceState *st;
+  if ((rc = get_state(device, &st))) return rc;
+  while ((int)st->ev_hop.size() < K) {
+    cudaEvent_t e;
+    SRG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    st->ev_hop.push_back(e);
+  }
+  cudaStream_t s_in = st->s_in, s_c = st->s_compute, s_out = st->s_out;
+  const int64_t ld = pad8(F);
+  const bool padded = (ld != F);
+  int flags = 0;
+  int32_t nnz_out = 0;
+  {
+    // all allocations are made on the compute stream first; the copy streams are ordered
+    // behind an event recorded after the allocations.
+    PoolAllocs pa(s_c);
+    int32_t *d_indptr, *d_indices;
+    char *d_data = nullptr;
+    if ((rc = pa.alloc(&d_indptr, n + 1))) return rc;
+    if ((rc = pa.alloc(&d_indices, nnz))) return rc;
+    if (val_dtype != SRG_VAL_ONES && (rc = pa.alloc(&d_data, nnz * (int64_t)val_bytes(val_dtype)))) return rc;
+    std::vector<float *> hops(K + 1, nullptr);
+    const bool have_feat = (int64_t)F * n > 0;
+    if (have_feat)
+      for (int k = 0; k <= K; ++k)
+        if ((rc = pa.alloc(&hops[k], n * ld))) return rc;
+    float *d_flat_in = nullptr, *d_flat_out[2] = {nullptr, nullptr};
+    int32_t *d_mask = nullptr;
+    const bool need_pack = have_feat && (padded || feature_mask);
+    if (need_pack && (rc = pa.alloc(&d_flat_in, n * (int64_t)F))) return rc;
+    if (have_feat && feature_mask && (rc = pa.alloc(&d_mask, n * (int64_t)F))) return rc;
+    if (have_feat && padded && K > 0) {
+      if ((rc = pa.alloc(&d_flat_out[0], n * (int64_t)F))) return rc;
+      if (K > 1 && (rc = pa.alloc(&d_flat_out[1], n * (int64_t)F))) return rc;
+    }
+    SRG_CUDA(cudaEventRecord(st->ev_csr, s_c));
+    SRG_CUDA(cudaStreamWaitEvent(s_in, st->ev_csr, 0));
+    SRG_CUDA(cudaStreamWaitEvent(s_out, st->ev_csr, 0));
+
+    // copy-in: raw CSR first (normalisation can start), then features
+    SRG_CUDA(cudaMemcpyAsync(d_indptr, indptr, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s_in));
+    if (nnz) SRG_CUDA(cudaMemcpyAsync(d_indices, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, s_in));
+    if (d_data && nnz)
+      SRG_CUDA(cudaMemcpyAsync(d_data, data, (size_t)nnz * val_bytes(val_dtype), cudaMemcpyHostToDevice, s_in));
+    SRG_CUDA(cudaEventRecord(st->ev_csr, s_in));
+    // compute: normalisation (queued before the feature upload so it overlaps it even when the
+    // host buffers are pageable and cudaMemcpyAsync blocks the host while staging)
+    SRG_CUDA(cudaStreamWaitEvent(s_c, st->ev_csr, 0));
+    NormOut no;
+    if ((rc = run_norm(pa, d_indptr, d_indices, d_data, val_dtype, n, nnz, r, ppr_alpha,
+                       out_norm_data != nullptr, true, s_c, &no)))
+      return rc;
+    SRG_CUDA(cudaEventRecord(st->ev_norm, s_c));
+
+    if (have_feat) {
+      float *dst = need_pack ? d_flat_in : hops[0];
+      SRG_CUDA(cudaMemcpyAsync(dst, features, (size_t)n * F * 4, cudaMemcpyHostToDevice, s_in));
+      if (feature_mask)
+        SRG_CUDA(cudaMemcpyAsync(d_mask, feature_mask, (size_t)n * F * 4, cudaMemcpyHostToDevice, s_in));
+      if (need_pack && (rc = srg_pack_features_f32(d_flat_in, F, hops[0], ld, n, F, d_mask, s_in))) return rc;
+      SRG_CUDA(cudaEventRecord(st->ev_x, s_in));
+    }
+
+    // hops + overlapped copy-out
+    if (have_feat) {
+      SRG_CUDA(cudaStreamWaitEvent(s_c, st->ev_x, 0));
+      for (int k = 1; k <= K; ++k) {
+        if ((rc = spmm_csr_f32_impl(no.indptr, no.indices, no.val32, n, hops[k - 1], ld, hops[k], ld, F, false, s_c)))
+          return rc;
+        SRG_CUDA(cudaEventRecord(st->ev_hop[k - 1], s_c));
+        SRG_CUDA(cudaStreamWaitEvent(s_out, st->ev_hop[k - 1], 0));
+        const float *src = hops[k];
+        if (padded) {
+          float *flat = d_flat_out[(k - 1) & 1];
+          if ((rc = srg_unpack_features_f32(hops[k], ld, flat, F, n, F, s_out))) return rc;
+          src = flat;
+        }
+        SRG_CUDA(cudaMemcpyAsync(out_hops[k - 1], src, (size_t)n * F * 4, cudaMemcpyDeviceToHost, s_out));
+      }
+    }
+    // normalised CSR back to the host if requested (after the hop copies are queued)
+    SRG_CUDA(cudaStreamWaitEvent(s_in, st->ev_norm, 0));
+    SRG_CUDA(cudaMemcpyAsync(&flags, no.flags, 4, cudaMemcpyDeviceToHost, s_in));
+    int32_t h_nnz_out = 0;
+    SRG_CUDA(cudaMemcpyAsync(&h_nnz_out, no.indptr + n, 4, cudaMemcpyDeviceToHost, s_in));
+    if (out_norm_indptr)
+      SRG_CUDA(cudaMemcpyAsync(out_norm_indptr, no.indptr, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, s_in));
+    SRG_CUDA(cudaStreamSynchronize(s_in));
+    nnz_out = h_nnz_out;
+    int frc = check_flags(flags);
+    if (!frc) {
+      if (out_norm_indices)
+        SRG_CUDA(cudaMemcpyAsync(out_norm_indices, no.indices, (size_t)nnz_out * 4, cudaMemcpyDeviceToHost, s_in));
+      if (out_norm_data)
+        SRG_CUDA(cudaMemcpyAsync(out_norm_data, no.val64, (size_t)nnz_out * 8, cudaMemcpyDeviceToHost, s_in));
+    }
+    SRG_CUDA(cudaStreamSynchronize(s_in));
+    SRG_CUDA(cudaStreamSynchronize(s_out));
+    SRG_CUDA(cudaStreamSynchronize(s_c));
+    pa.clean = true;
+    if (frc) return frc;
+  }
+  if (out_nnz) *out_nnz = nnz_out;
+  return SRG_OK;
+}
+
+// ---- literal reference ABI ------------------------------------------------------------------------
+static int shim_spmm(float *answer, const float *data, const int *indices, const int *indptr,
+                     const float *mat, int mat_row, int mat_col) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(mat_row >= 0 && mat_col >= 0, "FloatCSRMulDense*: negative size");
+  if (mat_row == 0 || mat_col == 0) return SRG_OK;
+  SRG_REQUIRE(answer && indptr && mat, "FloatCSRMulDense*: NULL pointer");
+  int device = 0;
+  SRG_CUDA(cudaGetDevice(&device));
+  DeviceState *st;
+  if ((rc = get_state(device, &st))) return rc;
+  cudaStream_t s = st->s_compute;
+  const int64_t n = mat_row, F = mat_col, nnz = indptr[mat_row];
+  SRG_REQUIRE(nnz >= 0 && (nnz == 0 || (data && indices)), "FloatCSRMulDense*: bad CSR");
+  PoolAllocs pa(s);
+  int32_t *d_indptr, *d_indices;
+  float *d_vals, *d_x, *d_y;
+  if ((rc = pa.alloc(&d_indptr, n + 1))) return rc;
+  if ((rc = pa.alloc(&d_indices, nnz))) return rc;
+  if ((rc = pa.alloc(&d_vals, nnz))) return rc;
+  if ((rc = pa.alloc(&d_x, n * F))) return rc;
+  if ((rc = pa.alloc(&d_y, n * F))) return rc;
+  SRG_CUDA(cudaMemcpyAsync(d_indptr, indptr, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
+  if (nnz) {
+    SRG_CUDA(cudaMemcpyAsync(d_indices, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
+    SRG_CUDA(cudaMemcpyAsync(d_vals, data, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
+  }
+  SRG_CUDA(cudaMemcpyAsync(d_x, mat, (size_t)n * F * 4, cudaMemcpyHostToDevice, s));
+  // the reference accumulates into `answer` (matmul.c:37): start every chain from its content
+  SRG_CUDA(cudaMemcpyAsync(d_y, answer, (size_t)n * F * 4, cudaMemcpyHostToDevice, s));
+  if ((rc = spmm_csr_f32_impl(d_indptr, d_indices, d_vals, n, d_x, F, d_y, F, (int32_t)F, true, s))) return rc;
+  SRG_CUDA(cudaMemcpyAsync(answer, d_y, (size_t)n * F * 4, cudaMemcpyDeviceToHost, s));
+  SRG_CUDA(cudaStreamSynchronize(s));
+  pa.clean = true;
+  return SRG_OK;
+}
+
+extern "C" void FloatCSRMulDenseOMP(float answer[], float data[], int indices[], int indptr[],
+                                    float mat[], int mat_row, int mat_col) {
+  // the reference symbol has no error channel (matmul.h:5): failures are loud, never silent.
+  int rc = shim_spmm(answer, data, indices, indptr, mat, mat_row, mat_col);
+  if (rc) {
+    fprintf(stderr, "libsrgnn_b200: FloatCSRMulDenseOMP failed (%d): %s\n", rc, err_buf());
+    abort();
+  }
+}
+
+extern "C" int FloatCSRMulDense(float answer[], int data_nnz, float data[], int indices[],
+                                int indptr[], float mat[], int mat_row, int mat_col) {
+  (void)data_nnz;
+  int rc = shim_spmm(answer, data, indices, indptr, mat, mat_row, mat_col);
+  if (rc) {
+    printf("libsrgnn_b200: FloatCSRMulDense failed (%d): %s\n", rc, err_buf());  // cudamatmul.c:7-25 prints
+    return 1;  // EXIT_FAILURE
+  }
+  return 0;  // EXIT_SUCCESS
+}

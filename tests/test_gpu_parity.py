@@ -1,0 +1,210 @@
+"""GPU parity suite (-m gpu): every call goes through the C ABI of libsrgnn_b200.so and is
+compared with the oracle / the golden vectors of the real reference."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import oracle
+from helpers import assert_same_structure, golden_csr, sym_graph, ulp_diff32, ulp_diff64
+from scalable_roubust_gnn_b200 import _lib, device as dev
+from scalable_roubust_gnn_b200.operators import (PprGraphOp, SymLaplacianGraphOp, adj_to_symmetric_norm,
+                                                 csr_sparse_dense_matmul)
+
+pytestmark = pytest.mark.gpu
+
+GRAPHS = ["cora", "rand_unw", "rand_w", "loop_iso"]
+RS = [0.5, 0.0, 0.3, 1.0]
+# fp64 weights: the exponents 0, +-0.5, +-1 are correctly rounded on the device while the golden
+# values carry the build host's np.power rounding (<= 1 ulp); CUDA pow is <= 2 ulp elsewhere.
+ULP64 = 4
+
+
+# ---- a3: normalisation -----------------------------------------------------------------------
+@pytest.mark.parametrize("name", GRAPHS)
+@pytest.mark.parametrize("r", RS)
+def test_construct_adj_vs_reference_golden(golden_prop, name, r):
+    adj = golden_csr(golden_prop, f"{name}_adj")
+    want = golden_csr(golden_prop, f"{name}_r{r}_norm")
+    got = SymLaplacianGraphOp(3, r=r).construct_adj(adj)
+    assert isinstance(got, sp.csr_matrix) and got.indices.dtype == np.int32 and got.data.dtype == np.float64
+    assert_same_structure(got, want)
+    assert ulp_diff64(got.data, want.data).max() <= ULP64
+    # the fp32 weights the hops use (utils.py:39) agree except where fp64 sat on a rounding tie
+    assert (ulp_diff32(got.data.astype(np.float32), want.data.astype(np.float32)) > 1).sum() == 0
+
+
+@pytest.mark.parametrize("name", GRAPHS)
+def test_ppr_construct_adj_vs_reference_golden(golden_prop, name):
+    adj = golden_csr(golden_prop, f"{name}_adj")
+    want = golden_csr(golden_prop, f"{name}_ppr_norm")
+    got = PprGraphOp(2, r=0.5, alpha=0.15).construct_adj(adj)
+    assert_same_structure(got, want)
+    assert ulp_diff64(got.data, want.data).max() <= ULP64
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_construct_adj_vs_oracle_random(dtype, weighted):
+    adj = sym_graph(3000, 40000, 21, weighted=weighted, dtype=dtype)
+    want = oracle.sym_norm(adj, 0.5)
+    got = adj_to_symmetric_norm(adj, 0.5)
+    assert_same_structure(got, want)
+    assert ulp_diff64(got.data, want.data).max() <= ULP64
+
+
+def test_degrees_bit_exact_weighted():
+    """Degree = numpy add.reduceat order (first + pairwise of the rest), incl. rows > 128 entries."""
+    n = 600
+    adj = sym_graph(n, 60000, 5, weighted=True)          # ~170 entries per row: pairwise recursion
+    a = dev.upload_csr(adj)
+    _, flags, ex = dev.sym_norm(a, 0.5, want_degree=True)
+    indptr, indices, d = oracle.selfloop_structure(adj)
+    assert int(flags.item()) == 0
+    np.testing.assert_array_equal(ex["degree"].cpu().numpy(), d)
+    np.testing.assert_array_equal(ex["count"].cpu().numpy(), np.diff(indptr))
+
+
+def test_non_canonical_input_is_canonicalised():
+    rows = np.array([0, 0, 1, 1, 2, 2, 0, 1]); cols = np.array([2, 1, 0, 2, 1, 0, 1, 0])
+    adj = sp.csr_matrix((np.ones(8), (rows, cols)), shape=(3, 3))   # scipy sums the duplicates
+    raw = sp.csr_matrix((np.ones(8), cols, np.array([0, 3, 6, 8])), shape=(3, 3))  # unsorted + dup
+    want = oracle.sym_norm(raw, 0.5)
+    got = adj_to_symmetric_norm(raw, 0.5)
+    assert_same_structure(got, want)
+    assert ulp_diff64(got.data, want.data).max() <= ULP64
+
+
+# ---- a5/a6: one hop ------------------------------------------------------------------------------
+@pytest.mark.parametrize("f", [1, 2, 3, 4, 7, 8, 24, 31, 32, 33, 64, 100, 128, 129, 257, 500, 1433])
+def test_spmm_bit_exact_all_widths(f):
+    """Every group width / chunk count of the kernel against the C oracle, bit for bit."""
+    n = 700
+    adj = oracle.sym_norm(sym_graph(n, 6000, f), 0.5)
+    x = np.random.default_rng(f).standard_normal((n, f)).astype(np.float32)
+    want = oracle.spmm_hop(adj, x)
+    got = csr_sparse_dense_matmul(adj, x)                       # reference-ABI shim, host buffers
+    assert got.dtype == np.float32 and got.shape == x.shape
+    np.testing.assert_array_equal(got, want)
+    # device entry point on the padded layout
+    a = dev.upload_csr(adj.astype(np.float32))
+    xp = dev.pack_features(torch.from_numpy(x).cuda())
+    y = dev.unpack_features(dev.spmm(a, xp, f), f).cpu().numpy()
+    np.testing.assert_array_equal(y, want)
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_spmm_bit_exact_vs_compiled_reference():
+    adj = oracle.sym_norm(sym_graph(5000, 60000, 3), 0.5)
+    x = np.random.default_rng(0).random((5000, 100), dtype=np.float32)
+    np.testing.assert_array_equal(csr_sparse_dense_matmul(adj, x), oracle.spmm_hop(adj, x, lib="ref"))
+
+
+def test_spmm_edge_cases():
+    # empty rows, a hub row longer than several index tiles, negative / tiny weights
+    n, f = 300, 20
+    rng = np.random.default_rng(9)
+    dense = np.zeros((n, n))
+    dense[7, :] = rng.standard_normal(n)            # hub: 300 entries
+    dense[:, 7] += rng.standard_normal(n) * 1e-20
+    dense[50:60, 100:140] = rng.standard_normal((10, 40))
+    adj = sp.csr_matrix(dense)
+    x = rng.standard_normal((n, f)).astype(np.float32)
+    np.testing.assert_array_equal(csr_sparse_dense_matmul(adj, x), oracle.spmm_hop(adj, x))
+    # shim accumulates into a non-zero answer exactly like matmul.c:37
+    lib = _lib.load()
+    ans = rng.standard_normal(n * f).astype(np.float32)
+    want = ans.copy()
+    oracle._lib().oracle_spmm_csr_f32(want, f, adj.data.astype(np.float32), adj.indices.astype(np.int32),
+                                      adj.indptr.astype(np.int32), x.reshape(-1), f, n, f)
+    d32, ii, ip = adj.data.astype(np.float32), adj.indices.astype(np.int32), adj.indptr.astype(np.int32)
+    lib.FloatCSRMulDenseOMP(ans.ctypes.data, d32.ctypes.data, ii.ctypes.data, ip.ctypes.data, x.ctypes.data, n, f)
+    np.testing.assert_array_equal(ans, want)
+    # empty matrix / zero features
+    e = sp.csr_matrix((5, 5))
+    np.testing.assert_array_equal(csr_sparse_dense_matmul(e, np.ones((5, 3), np.float32)), np.zeros((5, 3), np.float32))
+
+
+# ---- a1: propagate ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", GRAPHS)
+@pytest.mark.parametrize("r", RS)
+def test_propagate_vs_reference_golden(golden_prop, name, r):
+    adj = golden_csr(golden_prop, f"{name}_adj")
+    x = golden_prop[f"{name}_x"]
+    op = SymLaplacianGraphOp(3, r=r)
+    hops = op.propagate(adj, x)
+    assert len(hops) == 4 and all(isinstance(h, torch.Tensor) and h.dtype == torch.float32 and not h.is_cuda for h in hops)
+    np.testing.assert_array_equal(hops[0].numpy(), x)
+    np.testing.assert_allclose(hops[1].numpy(), golden_prop[f"{name}_r{r}_hop1"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(hops[3].numpy(), golden_prop[f"{name}_r{r}_hop3"], rtol=1e-5, atol=1e-6)
+    # lazily materialised op.adj is the reference's normalised matrix
+    assert_same_structure(op.adj, golden_csr(golden_prop, f"{name}_r{r}_norm"))
+
+
+@pytest.mark.parametrize("name", GRAPHS)
+def test_ppr_propagate_vs_reference_golden(golden_prop, name):
+    adj = golden_csr(golden_prop, f"{name}_adj")
+    hops = PprGraphOp(2, r=0.5, alpha=0.15).propagate(adj, golden_prop[f"{name}_x"])
+    np.testing.assert_allclose(hops[2].numpy(), golden_prop[f"{name}_ppr_hop2"], rtol=1e-5, atol=1e-6)
+
+
+def test_propagate_inputs_tensor_and_fortran_order():
+    adj = sym_graph(500, 3000, 2)
+    x = np.asfortranarray(np.random.default_rng(0).random((500, 12), dtype=np.float32))
+    want, _ = oracle.propagate(adj, x, 2)
+    for feat in (x, torch.from_numpy(np.ascontiguousarray(x))):
+        got = SymLaplacianGraphOp(2).propagate(adj, feat)
+        for g, w in zip(got, want):
+            np.testing.assert_allclose(g.numpy(), w, rtol=1e-5, atol=1e-6)
+
+
+def test_propagate_cora_shape_config1(golden_prop):
+    """BASELINE config 1: Cora topology (real bundled edges), F = 1433, K = 3, r = 0.5."""
+    adj = golden_csr(golden_prop, "cora_adj")
+    x = np.random.default_rng(1).random((2708, 1433), dtype=np.float32)
+    want, norm = oracle.propagate(adj, x, 3)
+    op = SymLaplacianGraphOp(3)
+    got = op.propagate(adj, x)
+    for g, w in zip(got, want):
+        np.testing.assert_allclose(g.numpy(), w, rtol=1e-5, atol=1e-6)
+    # from identical fp32 weights the hops are bit-exact
+    a32 = dev.upload_csr(norm.astype(np.float32))
+    hops = dev.propagate(a32, dev.pack_features(torch.from_numpy(x).cuda()), 1433, 3)
+    for h, w in zip(hops, want):
+        np.testing.assert_array_equal(dev.unpack_features(h, 1433).cpu().numpy(), w)
+
+
+def test_propagate_pubmed_shape_config2_with_masks(golden_masks):
+    """BASELINE config 2: PubMed topology, feature mask 0.6 / edge drop 0.6 (seed 2023), K = 5."""
+    n, f = 19717, 500
+    up = golden_masks["pubmed_0p6_0p6_edge_index"].astype(np.int64)     # bundled, already gathered
+    adj = oracle.symmetrize_edges(up, n)
+    torch.manual_seed(2023)
+    fmask = oracle.feature_mask((n, f), 0.6)
+    x = np.random.default_rng(1).random((n, f), dtype=np.float32)
+    want, _ = oracle.propagate(adj, x * fmask.numpy(), 5)
+    from scalable_roubust_gnn_b200.operators.utils import propagate_host
+    hops, _ = propagate_host(adj, x, 5, 0.5, feature_mask=fmask)
+    for g, w in zip(hops, want[1:]):
+        np.testing.assert_allclose(g.numpy(), w, rtol=1e-5, atol=1e-6)
+
+
+# ---- properties at larger size (oracle too slow / not needed) --------------------------------------
+def test_large_graph_properties():
+    """Linearity and row-stochasticity at 1M nodes: A^(r=1) rows sum to 1, so constant features
+    are a fixed point; a hop is linear in X (exactly, for power-of-two scalings)."""
+    n, f = 1_000_000, 16
+    adj = sym_graph(n, 8_000_000, 1)
+    a = dev.upload_csr(adj, ones_as_null=True)
+    norm, flags, _ = dev.sym_norm(a, 1.0)          # D^0 A~^T D^-1 ... row sums of D^-1-scaled columns
+    assert int(flags.item()) == 0
+    x = torch.rand((n, f), device="cuda")
+    xp = dev.pack_features(x)
+    y1 = dev.spmm(norm, xp, f)
+    y2 = dev.spmm(norm, xp * 4.0, f)
+    assert torch.equal(y2, y1 * 4.0)
+    # r = 0: A^ = D^-1 A~^T -> rows sum to one for a symmetric graph
+    norm0, _, _ = dev.sym_norm(a, 0.0)
+    ones = dev.pack_features(torch.ones((n, f), device="cuda"))
+    y = dev.spmm(norm0, ones, f)[:, :f]
+    assert torch.allclose(y, torch.ones_like(y), rtol=1e-5, atol=1e-6)

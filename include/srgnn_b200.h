@@ -67,6 +67,11 @@ int srg_device_count(void);
 /* counts kernels launched by this library in the calling process (bench "gpu_launches") */
 int64_t srg_launch_count(void);
 
+/* tuning / experiment knobs (profiles/ records which values the defaults come from):
+ *   "spmm_variant" 0 group kernel | 1 stream kernel;  "stream_cfg" ring shape;  "stream_rows" rows
+ *   per warp task;  "group_unroll";  "l2_fetch_granularity" 32|64|128 (cudaLimitMaxL2FetchGranularity) */
+int srg_set_tuning(const char *key, int64_t value);
+
 /* ---- a3: adjacency normalisation  (SSRG/operators/utils.py:81-93) ------------------------ */
 /*
  * Stage 1.  Structure of A~ = A + I over a canonical CSR (sorted rows, no duplicates).

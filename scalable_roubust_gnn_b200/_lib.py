@@ -48,6 +48,7 @@ SIGNATURES = {
     "srg_last_error": (C.c_char_p, []),
     "srg_device_count": (C.c_int, []),
     "srg_launch_count": (_i64, []),
+    "srg_set_tuning": (C.c_int, [C.c_char_p, _i64]),
     "srg_degree_selfloop_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp]),
     "srg_sym_norm_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "srg_spmm_csr_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
@@ -123,3 +124,7 @@ def device_count() -> int:
 
 def launch_count() -> int:
     return int(load().srg_launch_count())
+
+
+def set_tuning(key: str, value: int) -> None:
+    check(load().srg_set_tuning(key.encode(), int(value)))

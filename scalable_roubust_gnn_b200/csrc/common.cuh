@@ -62,10 +62,11 @@ __device__ __forceinline__ float ld_stream_f32(const float *p) {
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
-// gathered feature rows: read-only path, 128-bit
+// gathered feature rows: read-only path, 128-bit, 64-byte DRAM fetch granule on an L2 miss
+// (the default fetches the whole 128-byte line: tools/micro/fetch_gran.cu)
 __device__ __forceinline__ float4 ld_gather_f4(const float4 *p) {
   float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
   return v;

@@ -15,6 +15,8 @@
 //     kernel is sized for occupancy and bytes in flight, not for tensor cores.
 //
 // Long rows: handled by the split kernels further down (fixed-order partial sums, deterministic).
+#include <string>
+
 #include "common.cuh"
 
 namespace srg {
@@ -93,10 +95,11 @@ spmm_group_kernel(const int *__restrict__ indptr, const int *__restrict__ indice
   if (active) Ops::store(Y + row * ldy + col, acc);
 }
 
-template <typename VT, int G, bool ACCUM>
+static int g_group_unroll = 4;  // tuning: gathers in flight per lane for the 32-lane group kernel
+
+template <typename VT, int G, bool ACCUM, int U = ((G >= 4) ? 4 : G)>
 static int launch_group(const int *indptr, const int *indices, const float *vals, int64_t n_rows,
                         const VT *X, int64_t ldx, VT *Y, int64_t ldy, int nvec, cudaStream_t s) {
-  constexpr int U = (G >= 8) ? 8 : G;
   constexpr int GROUPS = kSpmmThreads / G;
   const int chunks = (nvec + G - 1) / G;
   const int64_t items = n_rows * (int64_t)chunks;
@@ -123,8 +126,195 @@ static int dispatch_group(const int *indptr, const int *indices, const float *va
   if (nvec <= 4) SRG_CASE(4);
   if (nvec <= 8) SRG_CASE(8);
   if (nvec <= 16) SRG_CASE(16);
+  if (g_group_unroll == 8)
+    return launch_group<VT, 32, ACCUM, 8>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
   SRG_CASE(32);
 #undef SRG_CASE
+}
+
+
+// ---- stream kernel: deep asynchronous gather pipeline through shared memory ---------------------
+// One warp owns R consecutive rows and treats their neighbours as ONE stream of positions
+// [indptr[r0], indptr[r0+R)).  A producer cursor issues, for every position, one 16-byte
+// cp.async (LDGSTS, L2 -> shared, no register staging) per lane into a per-warp ring of S row
+// slots; a consumer cursor S positions behind applies the FMAs in CSR order and flushes a row of
+// Y whenever it crosses a row end.  The in-flight depth is S rows (S*16 B per lane) independent
+// of the register budget, the index/value chunks are prefetched one chunk ahead, and nothing
+// stalls at row boundaries, so the warp keeps the memory system busy across short rows.
+// Each lane reads back only the 16 bytes it copied itself: no barrier is needed for the ring.
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+// same, fetching 64-byte granules from DRAM on an L2 miss instead of the default full 128-byte
+// line (measured: tools/micro/fetch_gran.cu, profiles/fetch_granularity.md)
+__device__ __forceinline__ void cp_async_16_l2_64(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int kStreamWarps = 8;
+
+template <int S, int B, bool L2_64>
+__global__ void __launch_bounds__(kStreamWarps * 32)
+spmm_stream_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
+                   const float *__restrict__ vals, long long n_rows, const float4 *__restrict__ X,
+                   long long ldx, float4 *__restrict__ Y, long long ldy, int nvec, int chunks,
+                   int R, int stride) {
+  static_assert(S % B == 0 && (S & (S - 1)) == 0, "ring must be a power of two multiple of B");
+  constexpr int NB = S / B;
+  extern __shared__ float4 smem4[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 *ring = smem4 + (size_t)w * S * stride;  // slot = `stride` float4 (active lanes only)
+  float *vring = reinterpret_cast<float *>(smem4 + (size_t)kStreamWarps * S * stride) + w * S;
+
+  const long long task = (long long)blockIdx.x * kStreamWarps + w;
+  const long long rblock = task / chunks;
+  const int chunk = (int)(task - rblock * chunks);
+  const long long r0 = rblock * R;
+  if (r0 >= n_rows) return;
+  const int nr = (int)min((long long)R, n_rows - r0);
+  const int col = chunk * 32 + lane;
+  const bool active = col < nvec;
+
+  const int my_end = (lane < nr) ? __ldg(indptr + r0 + lane + 1) : 0;
+  const int e0 = __ldg(indptr + r0);
+  const int e1 = __shfl_sync(0xffffffffu, my_end, nr - 1);
+
+  int p = e0, q = e0;
+  // index / value chunks: lane l holds position cbase + l; the next chunk is always in flight
+  int cbase = e0;
+  int my_c = 0, nx_c = 0;
+  float my_v = 0.f, nx_v = 0.f;
+  if (cbase + lane < e1) {
+    my_c = ld_stream_i32(indices + cbase + lane);
+    my_v = ld_stream_f32(vals + cbase + lane);
+  }
+  if (cbase + 32 + lane < e1) {
+    nx_c = ld_stream_i32(indices + cbase + 32 + lane);
+    nx_v = ld_stream_f32(vals + cbase + 32 + lane);
+  }
+
+  const float4 *Xc = X + col;
+  float4 *Yc = Y + r0 * ldy + col;
+  int cr = 0;
+  int cur_end = __shfl_sync(0xffffffffu, my_end, 0);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto flush_rows = [&]() {
+    while (cr < nr && q == cur_end) {  // also walks over empty rows
+      if (active) Yc[(long long)cr * ldy] = acc;
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      ++cr;
+      cur_end = __shfl_sync(0xffffffffu, my_end, min(cr, 31));
+    }
+  };
+  auto issue_batch = [&]() {
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      if (p < e1) {
+        if (p == cbase + 32) {
+          cbase += 32;
+          my_c = nx_c;
+          my_v = nx_v;
+          if (cbase + 32 + lane < e1) {
+            nx_c = ld_stream_i32(indices + cbase + 32 + lane);
+            nx_v = ld_stream_f32(vals + cbase + 32 + lane);
+          }
+        }
+        const int c = __shfl_sync(0xffffffffu, my_c, p - cbase);
+        const float v = __shfl_sync(0xffffffffu, my_v, p - cbase);
+        const int slot = p & (S - 1);
+        if (lane == 0) vring[slot] = v;
+        if (active) {
+          if (L2_64)
+            cp_async_16_l2_64(ring + slot * stride + lane, Xc + (long long)c * ldx);
+          else
+            cp_async_16(ring + slot * stride + lane, Xc + (long long)c * ldx);
+        }
+        ++p;
+      }
+    }
+    cp_async_commit();
+  };
+  auto consume_batch = [&]() {
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      if (q < e1) {
+        const int slot = q & (S - 1);
+        const float v = vring[slot];
+        if (active) {
+          const float4 x = ring[slot * stride + lane];
+          acc.x = fmaf(v, x.x, acc.x);
+          acc.y = fmaf(v, x.y, acc.y);
+          acc.z = fmaf(v, x.z, acc.z);
+          acc.w = fmaf(v, x.w, acc.w);
+        }
+        ++q;
+        flush_rows();
+      }
+    }
+    __syncwarp();
+  };
+
+  flush_rows();  // leading empty rows
+  const int nbatches = (e1 - e0 + B - 1) / B;
+#pragma unroll
+  for (int i = 0; i < NB - 1; ++i) issue_batch();
+  for (int it = 0; it < nbatches; ++it) {
+    issue_batch();
+    cp_async_wait<NB - 1>();
+    consume_batch();
+  }
+  cp_async_wait<0>();
+}
+
+// tuning knobs (srg_set_tuning): which kernel serves 16 < nvec and its shape
+static int g_spmm_variant = 1;     // 0 = group kernel, 1 = stream kernel
+static int g_stream_rows = 4;      // rows per warp task
+static int g_stream_cfg = 0;       // 0: S8/B4, 1: S8/B2, 2: S4/B2, 3: S4/B4, 4: S16/B4, 5: S16/B8, 6: S8/B1
+static int g_stream_compact = 0;   // ring slot = nvec float4 instead of 32
+static int g_gather_l2_64 = 1;     // gathers fetch 64-byte DRAM granules instead of 128-byte lines
+
+template <int S, int B, bool L2_64>
+static int launch_stream(const int *indptr, const int *indices, const float *vals, int64_t n_rows,
+                         const float4 *X, int64_t ldx, float4 *Y, int64_t ldy, int nvec,
+                         cudaStream_t s) {
+  const int R = g_stream_rows < 1 ? 1 : (g_stream_rows > 32 ? 32 : g_stream_rows);
+  const int chunks = (nvec + 31) / 32;
+  const int stride = (g_stream_compact && nvec < 32) ? nvec : 32;
+  const int64_t tasks = ceil_div64(n_rows, R) * chunks;
+  const int64_t blocks = ceil_div64(tasks, kStreamWarps);
+  if (blocks > 2147483647LL) {
+    set_err("spmm: grid too large (%lld blocks)", (long long)blocks);
+    return SRG_ERR_RANGE;
+  }
+  const size_t smem = (size_t)kStreamWarps * S * stride * sizeof(float4) + (size_t)kStreamWarps * S * sizeof(float);
+  SRG_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<S, B, L2_64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  spmm_stream_kernel<S, B, L2_64><<<(unsigned)blocks, kStreamWarps * 32, smem, s>>>(
+      indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, chunks, R, stride);
+  SRG_LAUNCHED();
+  return SRG_OK;
+}
+
+template <bool L2_64>
+static int dispatch_stream(const int *indptr, const int *indices, const float *vals, int64_t n_rows,
+                           const float4 *X, int64_t ldx, float4 *Y, int64_t ldy, int nvec,
+                           cudaStream_t s) {
+  switch (g_stream_cfg) {
+    case 1: return launch_stream<8, 2, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
+    case 2: return launch_stream<4, 2, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
+    case 3: return launch_stream<4, 4, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
+    case 4: return launch_stream<16, 4, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
+    case 5: return launch_stream<16, 8, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
+    case 6: return launch_stream<8, 1, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
+    default: return launch_stream<8, 4, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
+  }
 }
 
 int spmm_csr_f32_impl(const int32_t *indptr, const int32_t *indices, const float *vals,
@@ -142,6 +332,10 @@ int spmm_csr_f32_impl(const int32_t *indptr, const int32_t *indices, const float
     const int nvec = (F + 3) / 4;
     const float4 *X4 = reinterpret_cast<const float4 *>(X);
     float4 *Y4 = reinterpret_cast<float4 *>(Y);
+    if (!accumulate && g_spmm_variant == 1 && nvec > 16) {
+      return g_gather_l2_64 ? dispatch_stream<true>(indptr, indices, vals, n_rows, X4, ldx / 4, Y4, ldy / 4, nvec, s)
+                            : dispatch_stream<false>(indptr, indices, vals, n_rows, X4, ldx / 4, Y4, ldy / 4, nvec, s);
+    }
     return accumulate
                ? dispatch_group<float4, true>(indptr, indices, vals, n_rows, X4, ldx / 4, Y4, ldy / 4, nvec, s)
                : dispatch_group<float4, false>(indptr, indices, vals, n_rows, X4, ldx / 4, Y4, ldy / 4, nvec, s);
@@ -183,6 +377,26 @@ unpack_features_kernel(const float *__restrict__ src, long long ld_src, float *_
 }  // namespace srg
 
 using namespace srg;
+
+extern "C" int srg_set_tuning(const char *key, int64_t value) {
+  SRG_REQUIRE(key != nullptr, "set_tuning: NULL key");
+  const std::string k(key);
+  if (k == "spmm_variant") g_spmm_variant = (int)value;
+  else if (k == "stream_rows") g_stream_rows = (int)value;
+  else if (k == "group_unroll") g_group_unroll = (int)value;
+  else if (k == "gather_l2_64") g_gather_l2_64 = (int)value;
+  else if (k == "stream_compact") g_stream_compact = (int)value;
+  else if (k == "stream_cfg") g_stream_cfg = (int)value;
+  else if (k == "l2_fetch_granularity") {
+    int rc = require_device();
+    if (rc) return rc;
+    SRG_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+  } else {
+    set_err("set_tuning: unknown key '%s'", key);
+    return SRG_ERR_INVALID;
+  }
+  return SRG_OK;
+}
 
 extern "C" int srg_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
                                 int64_t n_rows, const float *X, int64_t ldx, float *Y, int64_t ldy,

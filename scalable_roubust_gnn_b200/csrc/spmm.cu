@@ -274,10 +274,153 @@ spmm_stream_kernel(const int *__restrict__ indptr, const int *__restrict__ indic
   cp_async_wait<0>();
 }
 
+// ---- stream kernel, unrolled form ------------------------------------------------------------------
+// Same pipeline as above with the bookkeeping taken out of the per-position path: the stream is
+// walked in chunks of 32 positions whose (index, value) live one per lane, the chunk body is fully
+// unrolled so every shuffle lane, ring slot and row-end test is a compile-time constant, row ends
+// are a 32-bit mask built once per chunk (REDUX), and the consumer lags the producer by exactly
+// one batch of B positions (ring of 2B slots), carrying the tail of a chunk into the next one.
+// ~13 issued instructions per gathered row instead of ~85: the kernel is DRAM-bound, not
+// issue-bound (profiles/spmm_stream.md).
+__device__ __forceinline__ void cp_async_16s(unsigned smem_addr, const void *g, bool l2_64) {
+  if (l2_64)
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+  else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(unsigned smem_addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr));
+  return v;
+}
+
+template <int B, bool L2_64>
+__global__ void __launch_bounds__(kStreamWarps * 32)
+spmm_stream2_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
+                    const float *__restrict__ vals, long long n_rows, const float4 *__restrict__ X,
+                    unsigned ldx, float4 *__restrict__ Y, long long ldy, int nvec, int chunks, int R) {
+  constexpr int S = 2 * B;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ float4 smem4[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned ring = (unsigned)__cvta_generic_to_shared(smem4 + (size_t)w * S * 32 + lane);
+
+  const long long task = (long long)blockIdx.x * kStreamWarps + w;
+  const long long rblock = task / chunks;
+  const int chunk = (int)(task - rblock * chunks);
+  const long long r0 = rblock * R;
+  if (r0 >= n_rows) return;
+  const int nr = (int)min((long long)R, n_rows - r0);
+  const int col = chunk * 32 + lane;
+  const bool active = col < nvec;
+  const float4 *Xc = X + col;
+  float4 *yrow = Y + r0 * ldy + col;
+
+  const int my_end = (lane < nr) ? __ldg(indptr + r0 + lane + 1) : 0;
+  const int e0 = __ldg(indptr + r0);
+  const int e1 = __shfl_sync(FULL, my_end, nr - 1);
+  int prev_end = __shfl_up_sync(FULL, my_end, 1);
+  if (lane == 0) prev_end = e0;
+
+  if (__any_sync(FULL, lane < nr && my_end == prev_end)) {
+    // an empty row in this task (never happens for A^, which has a full diagonal): plain loop
+    for (int r = 0; r < nr; ++r) {
+      const int st = __shfl_sync(FULL, prev_end, r), ed = __shfl_sync(FULL, my_end, r);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = st; j < ed; ++j) {
+        const int c = __ldg(indices + j);
+        const float v = __ldg(vals + j);
+        if (active) {
+          const float4 x = ld_gather_f4(Xc + (unsigned long long)(unsigned)c * ldx);
+          acc.x = fmaf(v, x.x, acc.x);
+          acc.y = fmaf(v, x.y, acc.y);
+          acc.z = fmaf(v, x.z, acc.z);
+          acc.w = fmaf(v, x.w, acc.w);
+        }
+      }
+      if (active) yrow[(long long)r * ldy] = acc;
+    }
+    return;
+  }
+
+  int cbase = e0;
+  int my_c = 0, nx_c = 0;
+  float my_v = 0.f, nx_v = 0.f, pv_v = 0.f;
+  if (cbase + lane < e1) {
+    my_c = ld_stream_i32(indices + cbase + lane);
+    my_v = ld_stream_f32(vals + cbase + lane);
+  }
+  if (cbase + 32 + lane < e1) {
+    nx_c = ld_stream_i32(indices + cbase + 32 + lane);
+    nx_v = ld_stream_f32(vals + cbase + 32 + lane);
+  }
+  int prev_cnt = 0;
+  unsigned prev_mask = 0;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (;;) {
+    const int cnt = max(0, min(32, e1 - cbase));
+    unsigned bit = 0;
+    {
+      const int d = my_end - cbase - 1;
+      if (lane < nr && d >= 0 && d < 32) bit = 1u << d;
+    }
+    const unsigned endmask = __reduce_or_sync(FULL, bit);
+#pragma unroll
+    for (int b = 0; b < 32 / B; ++b) {
+      if (b * B < cnt) {
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+          const int i = b * B + u;
+          const int c = __shfl_sync(FULL, my_c, i);
+          if (i < cnt && active)
+            cp_async_16s(ring + ((i & (S - 1)) << 9), Xc + (unsigned long long)(unsigned)c * ldx, L2_64);
+        }
+      }
+      cp_async_commit();
+      cp_async_wait<1>();
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        const int j = (b - 1) * B + u;  // position consumed now (one batch behind)
+        const int jj = j & 31;          // lane / bit inside its own chunk
+        const bool valid = (j < 0) ? (jj < prev_cnt) : (j < cnt);
+        if (valid) {
+          const float v = __shfl_sync(FULL, (j < 0) ? pv_v : my_v, jj);
+          if (active) {
+            const float4 x = lds_f4(ring + ((jj & (S - 1)) << 9));
+            acc.x = fmaf(v, x.x, acc.x);
+            acc.y = fmaf(v, x.y, acc.y);
+            acc.z = fmaf(v, x.z, acc.z);
+            acc.w = fmaf(v, x.w, acc.w);
+          }
+          if ((((j < 0) ? prev_mask : endmask) >> jj) & 1u) {
+            if (active) *yrow = acc;
+            yrow += ldy;
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      if (b * B >= cnt) break;  // nothing was issued in this round: the chunk is drained
+    }
+    if (cnt <= 32 - B) break;   // everything issued in this chunk has been consumed
+    prev_cnt = cnt;
+    prev_mask = endmask;
+    pv_v = my_v;
+    my_c = nx_c;
+    my_v = nx_v;
+    cbase += 32;
+    if (cbase + 32 + lane < e1) {
+      nx_c = ld_stream_i32(indices + cbase + 32 + lane);
+      nx_v = ld_stream_f32(vals + cbase + 32 + lane);
+    }
+  }
+  cp_async_wait<0>();
+}
+
 // tuning knobs (srg_set_tuning): which kernel serves 16 < nvec and its shape
 static int g_spmm_variant = 1;     // 0 = group kernel, 1 = stream kernel
 static int g_stream_rows = 4;      // rows per warp task
-static int g_stream_cfg = 0;       // 0: S8/B4, 1: S8/B2, 2: S4/B2, 3: S4/B4, 4: S16/B4, 5: S16/B8, 6: S8/B1
+static int g_stream_cfg = 10;      // 10/11/12: unrolled stream kernel B4/B8/B2; 0: S8/B4, 1: S8/B2, 2: S4/B2, 3: S4/B4, 4: S16/B4, 5: S16/B8, 6: S8/B1
 static int g_stream_compact = 0;   // ring slot = nvec float4 instead of 32
 static int g_gather_l2_64 = 1;     // gathers fetch 64-byte DRAM granules instead of 128-byte lines
 
@@ -302,11 +445,34 @@ static int launch_stream(const int *indptr, const int *indices, const float *val
   return SRG_OK;
 }
 
+template <int B, bool L2_64>
+static int launch_stream2(const int *indptr, const int *indices, const float *vals, int64_t n_rows,
+                          const float4 *X, int64_t ldx, float4 *Y, int64_t ldy, int nvec,
+                          cudaStream_t s) {
+  const int R = g_stream_rows < 1 ? 1 : (g_stream_rows > 32 ? 32 : g_stream_rows);
+  const int chunks = (nvec + 31) / 32;
+  const int64_t tasks = ceil_div64(n_rows, R) * chunks;
+  const int64_t blocks = ceil_div64(tasks, kStreamWarps);
+  if (blocks > 2147483647LL || ldx > 0xffffffffLL) {
+    set_err("spmm: problem too large for the stream kernel (%lld blocks, ldx %lld)", (long long)blocks, (long long)ldx);
+    return SRG_ERR_RANGE;
+  }
+  const size_t smem = (size_t)kStreamWarps * (2 * B) * 32 * sizeof(float4);
+  SRG_CUDA(cudaFuncSetAttribute(spmm_stream2_kernel<B, L2_64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  spmm_stream2_kernel<B, L2_64><<<(unsigned)blocks, kStreamWarps * 32, smem, s>>>(
+      indptr, indices, vals, n_rows, X, (unsigned)ldx, Y, ldy, nvec, chunks, R);
+  SRG_LAUNCHED();
+  return SRG_OK;
+}
+
 template <bool L2_64>
 static int dispatch_stream(const int *indptr, const int *indices, const float *vals, int64_t n_rows,
                            const float4 *X, int64_t ldx, float4 *Y, int64_t ldy, int nvec,
                            cudaStream_t s) {
   switch (g_stream_cfg) {
+    case 10: return launch_stream2<4, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
+    case 11: return launch_stream2<8, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
+    case 12: return launch_stream2<2, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
     case 1: return launch_stream<8, 2, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
     case 2: return launch_stream<4, 2, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
     case 3: return launch_stream<4, 4, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);

@@ -62,9 +62,12 @@ ld0 = dev.pad_ld(f)
 run("group U8 (v0)", ld0, spmm_variant=0, group_unroll=8)
 run("group U4", ld0, spmm_variant=0, group_unroll=4)
 names = {0: "S8/B4", 1: "S8/B2", 2: "S4/B2", 3: "S4/B4", 4: "S16/B4", 5: "S16/B8", 6: "S8/B1"}
-for l2, compact in itertools.product((1, 0), (0, 1)):
-    for cfg, rows in itertools.product([0, 1, 4], [4, 8, 16, 32]):
-        run(f"stream {names[cfg]} R{rows} l2_64={l2} compact={compact}", ld0, spmm_variant=1, stream_cfg=cfg, stream_rows=rows, gather_l2_64=l2, stream_compact=compact)
+run("stream S8/B4 R4 (old)", ld0, spmm_variant=1, stream_cfg=0, stream_rows=4, gather_l2_64=1, stream_compact=0)
+names2 = {10: "B4", 11: "B8", 12: "B2"}
+for l2 in (1, 0):
+    for cfg, rows in itertools.product([10, 11, 12], [4, 8, 16, 32]):
+        run(f"stream2 {names2[cfg]} R{rows} l2_64={l2}", ld0, spmm_variant=1, stream_cfg=cfg, stream_rows=rows, gather_l2_64=l2, stream_compact=0)
+run("stream S8/B4 R4 (old, again)", ld0, spmm_variant=1, stream_cfg=0, stream_rows=4, gather_l2_64=1, stream_compact=0)
 best = min((r for r in results if r.get("spmm_variant") == 1), key=lambda r: r["ms_avg"])
 print("best stream:", best, flush=True)
 kw = {kk: best[kk] for kk in ("spmm_variant", "stream_cfg", "stream_rows", "gather_l2_64", "stream_compact")}

@@ -105,6 +105,43 @@ int srg_sym_norm_csr(const int32_t *indptr, const int32_t *indices, const void *
                      double ppr_alpha, int32_t *out_indices, double *out_degree,
                      double *out_val_f64, float *out_val_f32, int32_t *out_flags, void *stream);
 
+/*
+ * General path of stage 2 for a NON-symmetric pattern (directed input): explicit transpose by a
+ * stable key sort.  Same outputs as srg_sym_norm_csr plus out_indptr (the row pointer of R, which
+ * differs from that of A~); at_indptr is the stage-1 row pointer of A~.  Synchronises `stream`
+ * once (4-byte readback of the entry count).
+ */
+int srg_sym_norm_csr_general(const int32_t *indptr, const int32_t *indices, const void *data,
+                             int val_dtype, int64_t n, int64_t nnz, const int32_t *at_indptr,
+                             double r, double ppr_alpha, int32_t *out_indptr, int32_t *out_indices,
+                             double *out_degree, double *out_val_f64, float *out_val_f32,
+                             int32_t *out_flags, void *stream);
+
+/*
+ * Canonical form of a CSR with unsorted rows and/or duplicate entries (what scipy's
+ * `adj.tocoo() + eye` does first, SSRG/operators/utils.py:82): rows sorted by column, duplicates
+ * summed in stored order.  Outputs have capacity nnz; *out_nnz_dev (device int32) = entries kept.
+ */
+int srg_csr_canonicalize(const int32_t *indptr, const int32_t *indices, const void *data,
+                         int val_dtype, int64_t n, int64_t nnz, int32_t *out_indptr,
+                         int32_t *out_indices, double *out_vals, int32_t *out_nnz_dev,
+                         int32_t *out_flags, void *stream);
+
+/* ---- a8: sparsity masks (SSRG/data_process.py:35-67, SSRG/data_augument.py:28,99-102) -------- */
+/* out[:, i] = edge_index[:, keep[i]]  (int64 2 x E row-major in, 2 x E_keep out): data_process.py:66 */
+int srg_edge_gather_i64(const int64_t *edge_index, int64_t E, const int64_t *keep, int64_t E_keep,
+                        int64_t *out, int32_t *out_flags, void *stream);
+/* undirected duplicate-free adjacency (pattern CSR, every value 1.0) of an edge list:
+ * data_augument.py:99-102 (cat both directions, unique).  out_indices capacity 2E;
+ * *out_nnz_dev (device int32) = stored entries. */
+int srg_edges_to_sym_csr(const int64_t *edge_index, int64_t E, int64_t n, int32_t *out_indptr,
+                         int32_t *out_indices, int32_t *out_nnz_dev, int32_t *out_flags,
+                         void *stream);
+/* x * feature_mask (data_augument.py:28) into a (possibly padded) device layout; alias of
+ * srg_pack_features_f32 with a non-NULL mask */
+int srg_apply_feature_mask_f32(const float *x, int64_t ld_x, const int32_t *mask, float *out,
+                               int64_t ld_out, int64_t n, int32_t F, void *stream);
+
 /* ---- a5/a6: one propagation hop  (SSRG/operators/csrc/matmul.c:23-40) --------------------- */
 /*
  * Y[i, 0:F] = sum_j vals[j] * X[indices[j], 0:F]  for j in indptr[i]..indptr[i+1], evaluated
@@ -122,6 +159,32 @@ int srg_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float 
 int srg_propagate_khop_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
                            int64_t n, float *const *hops, int64_t ld, int32_t F, int32_t K,
                            void *stream);
+
+/* ---- a9: Chebyshev heat-wavelet filter  (wavelet/src/utils.py:89-104,125-138; pygsp cheby_op) --- */
+/*
+ * Combinatorial Laplacian L = diag(W 1) - W of a canonical CSR W (what pygsp.graphs.Graph(W).L is
+ * for lap_type='combinatorial').  out_indptr n+1, out_indices / out_vals capacity nnz + n; exact
+ * zeros dropped; degree (nullable) = W.sum(1) in numpy's summation order.
+ */
+int srg_laplacian_csr(const int32_t *indptr, const int32_t *indices, const void *data,
+                      int val_dtype, int64_t n, int32_t *out_indptr, int32_t *out_indices,
+                      double *out_vals, double *out_degree, int32_t *out_flags, void *stream);
+
+/*
+ * r_s = sum_k c[s][k] T_k(L~) X for n_scales (<= 4) coefficient vectors sharing the T_k, fp64:
+ *   T0 = X, T1 = (L X - a X)/a, T_k = (2/a)(L T_{k-1} - a T_{k-1}) - T_{k-2},  a = lmax/2,
+ *   r_s = 0.5 c[s][0] T0 + sum_{k>=1} c[s][k] T_k      (coeffs: HOST array [n_scales][order+1])
+ * The recurrence and the accumulation are the epilogue of the SpMM of each order (one launch per
+ * order).  tol: values < tol are zeroed in the last step (wavelet/src/utils.py:98); pass NaN for no
+ * threshold.  out_r[s]: device n x ld fp64; out_r32 (nullable array, nullable entries): float32
+ * copy of the thresholded result (leading dimension ld32).  work0/work1: n x ld fp64 scratch.
+ * ld (in doubles) must be even, pointers 16-byte aligned.
+ */
+int srg_cheby_filter_f64(const int32_t *lap_indptr, const int32_t *lap_indices,
+                         const double *lap_vals, int64_t n, const double *X, int64_t ld, int32_t B,
+                         double lmax, const double *coeffs, int32_t n_scales, int32_t order,
+                         double tol, double *const *out_r, float *const *out_r32, int64_t ld32,
+                         double *work0, double *work1, void *stream);
 
 /* layout helpers: host layout (ld == F) <-> padded device layout (ld % 8 == 0, pad = 0).
  * mask (optional, int32 n x F, SSRG/data_process.py:38-39) is applied as x * mask

@@ -51,8 +51,16 @@ SIGNATURES = {
     "srg_set_tuning": (C.c_int, [C.c_char_p, _i64]),
     "srg_degree_selfloop_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp]),
     "srg_sym_norm_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "srg_sym_norm_csr_general": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "srg_csr_canonicalize": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "srg_edge_gather_i64": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "srg_edges_to_sym_csr": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "srg_apply_feature_mask_f32": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
     "srg_spmm_csr_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
     "srg_propagate_khop_f32": (C.c_int, [_vp, _vp, _vp, _i64, C.POINTER(_vp), _i64, _i32, _i32, _vp]),
+    "srg_laplacian_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "srg_cheby_filter_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i32, _f64, C.POINTER(_f64), _i32, _i32, _f64,
+                                       C.POINTER(_vp), C.POINTER(_vp), _i64, _vp, _vp, _vp]),
     "srg_pack_features_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp]),
     "srg_unpack_features_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),
     "srg_propagate_host": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _i32, _vp, _i32, _f64, _f64,

@@ -1,0 +1,361 @@
+// coo.cu — edge-list / COO stages around the propagation path (integer work, bit-exact):
+//
+//   srg_edge_gather_i64      edge_index[:, keep]                      SSRG/data_process.py:65-66
+//   srg_edges_to_sym_csr     symmetrise + unique -> CSR of ones       SSRG/data_augument.py:99-102
+//   srg_csr_canonicalize     sort rows + sum duplicates               what scipy's `adj.tocoo() + eye`
+//                                                                     does to non-canonical input
+//                                                                     (SSRG/operators/utils.py:82)
+//   srg_sym_norm_csr_general R = D^(r-1) A~^T D^(-r) when the pattern of A~ is NOT symmetric: the
+//                            explicit transpose of SSRG/operators/utils.py:92
+//
+// All four are "sort (row, col) keys, then segment" problems.  The key sort is the one place the
+// library calls a CUDA-toolkit primitive (cub::DeviceRadixSort, stable LSD radix sort); everything
+// else (key construction, duplicate segmentation, row pointer search, value arithmetic) is local
+// kernels.  None of this is on the per-hop path.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace srg {
+
+static int bits_for(int64_t n) {
+  int b = 1;
+  while (b < 63 && (1LL << b) < n) ++b;
+  return b;
+}
+
+// stable sort of 64-bit keys (optionally carrying a payload) on `s`
+template <typename V>
+static int sort_pairs(uint64_t *keys_in, uint64_t *keys_out, V *vals_in, V *vals_out, int64_t m,
+                      int end_bit, cudaStream_t s) {
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, m, 0, end_bit, s);
+  void *tmp = nullptr;
+  SRG_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, s));
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, m, 0, end_bit, s);
+  g_launches.fetch_add(1);
+  cudaFreeAsync(tmp, s);
+  if (e != cudaSuccess) return cuda_fail(e, "cub::DeviceRadixSort::SortPairs", __FILE__, __LINE__);
+  return SRG_OK;
+}
+static int sort_keys(uint64_t *keys_in, uint64_t *keys_out, int64_t m, int end_bit, cudaStream_t s) {
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys_in, keys_out, m, 0, end_bit, s);
+  void *tmp = nullptr;
+  SRG_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, s));
+  cudaError_t e = cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys_in, keys_out, m, 0, end_bit, s);
+  g_launches.fetch_add(1);
+  cudaFreeAsync(tmp, s);
+  if (e != cudaSuccess) return cuda_fail(e, "cub::DeviceRadixSort::SortKeys", __FILE__, __LINE__);
+  return SRG_OK;
+}
+
+__global__ void edge_gather_kernel(const long long *__restrict__ ei, long long E,
+                                   const long long *__restrict__ keep, long long Ek,
+                                   long long *__restrict__ out, int *__restrict__ flags) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Ek) return;
+  const long long k = keep[i];
+  if (k < 0 || k >= E) {
+    atomicOr(flags, SRG_FLAG_BAD_INDEX);
+    return;
+  }
+  out[i] = ei[k];
+  out[Ek + i] = ei[E + k];
+}
+
+// keys of both directions of every edge: (u<<32|v) and (v<<32|u)
+__global__ void sym_keys_kernel(const long long *__restrict__ ei, long long E, long long n,
+                                uint64_t *__restrict__ keys, int *__restrict__ flags) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E) return;
+  const long long u = ei[i], v = ei[E + i];
+  if (u < 0 || u >= n || v < 0 || v >= n) {
+    atomicOr(flags, SRG_FLAG_BAD_INDEX);
+    keys[2 * i] = keys[2 * i + 1] = 0;
+    return;
+  }
+  keys[2 * i] = ((uint64_t)u << 32) | (uint64_t)v;
+  keys[2 * i + 1] = ((uint64_t)v << 32) | (uint64_t)u;
+}
+
+__global__ void head_flags_kernel(const uint64_t *__restrict__ keys, long long m, int *__restrict__ head) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+// compact unique keys: out_col[seg] = low 32 bits; optionally sum the values of a segment in
+// stored order (first + rest, sequential)
+template <bool WITH_VALS>
+__global__ void compact_unique_kernel(const uint64_t *__restrict__ keys, const int *__restrict__ head,
+                                      const int *__restrict__ seg, long long m,
+                                      const double *__restrict__ vals, int *__restrict__ out_col,
+                                      uint64_t *__restrict__ out_key, double *__restrict__ out_val) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m || !head[i]) return;
+  const int sidx = seg[i];
+  out_col[sidx] = (int)(keys[i] & 0xffffffffu);
+  if (out_key) out_key[sidx] = keys[i];
+  if (WITH_VALS) {
+    double acc = vals[i];
+    for (long long j = i + 1; j < m && !head[j]; ++j) acc = __dadd_rn(acc, vals[j]);
+    out_val[sidx] = acc;
+  }
+}
+
+// indptr[r] = first position whose row (key >> 32) is >= r, over `cnt` sorted unique keys
+__global__ void row_lower_bound_kernel(const uint64_t *__restrict__ keys, const int *__restrict__ total,
+                                       long long n, int *__restrict__ indptr) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n) return;
+  const int cnt = *total;
+  int lo = 0, hi = cnt;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((long long)(keys[mid] >> 32) < r) lo = mid + 1; else hi = mid;
+  }
+  indptr[r] = lo;
+}
+
+// (row, col, val) keys of a CSR (row-major expansion)
+template <typename T>
+__global__ void csr_keys_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
+                                const T *__restrict__ data, long long n, uint64_t *__restrict__ keys,
+                                double *__restrict__ vals, int *__restrict__ flags, bool transpose) {
+  const long long a = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (a >= n) return;
+  const int lane = threadIdx.x & 31;
+  for (int j = indptr[a] + lane; j < indptr[a + 1]; j += 32) {
+    const int b = indices[j];
+    if (b < 0 || b >= n) {
+      atomicOr(flags, SRG_FLAG_BAD_INDEX);
+      keys[j] = 0;
+      vals[j] = 0.0;
+      continue;
+    }
+    keys[j] = transpose ? (((uint64_t)b << 32) | (uint64_t)a) : (((uint64_t)a << 32) | (uint64_t)b);
+    vals[j] = data ? (double)data[j] : 1.0;
+  }
+}
+
+// general path values: entry (a, b) of A~ lands at R[b, a] = (A~[a,b] * dl[b]) * dr[a]
+__global__ void general_norm_vals_kernel(const int *__restrict__ at_indptr, const int *__restrict__ at_indices,
+                                         const double *__restrict__ at_val, const double *__restrict__ degree,
+                                         long long n, const double *__restrict__ dl, const double *__restrict__ dr,
+                                         uint64_t *__restrict__ keys, double *__restrict__ vals, int ones) {
+  const long long a = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (a >= n) return;
+  const int lane = threadIdx.x & 31;
+  const int p0 = at_indptr[a], p1 = at_indptr[a + 1];
+  for (int p = p0 + lane; p < p1; p += 32) {
+    const int b = at_indices[p];
+    double v;
+    if (ones) v = (b == (int)a) ? degree[a] - (double)(p1 - p0 - 1) : 1.0;
+    else v = at_val[p];
+    keys[p] = ((uint64_t)b << 32) | (uint64_t)a;
+    vals[p] = __dmul_rn(__dmul_rn(v, dl[b]), dr[a]);
+  }
+}
+
+__global__ void finalize_general_kernel(const uint64_t *__restrict__ keys, const double *__restrict__ vals,
+                                        const int *__restrict__ total, double one_minus_alpha, double alpha,
+                                        int use_ppr, int *__restrict__ out_indices, double *__restrict__ v64,
+                                        float *__restrict__ v32, int *__restrict__ flags) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *total) return;
+  const uint64_t k = keys[i];
+  const int row = (int)(k >> 32), col = (int)(k & 0xffffffffu);
+  double v = vals[i];
+  if (use_ppr) {
+    v = __dmul_rn(one_minus_alpha, v);
+    if (row == col) v = __dadd_rn(v, alpha);
+  }
+  if (v == 0.0) atomicOr(flags, SRG_FLAG_ZERO_PRODUCT);
+  out_indices[i] = col;
+  if (v64) v64[i] = v;
+  if (v32) v32[i] = __double2float_rn(v);
+}
+
+__global__ void set_int_kernel(int *p, const int *src) { *p = *src; }
+
+}  // namespace srg
+
+using namespace srg;
+
+extern "C" int srg_edge_gather_i64(const int64_t *edge_index, int64_t E, const int64_t *keep,
+                                   int64_t E_keep, int64_t *out, int32_t *out_flags, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(E >= 0 && E_keep >= 0, "edge_gather: negative size");
+  if (E_keep == 0) return SRG_OK;
+  SRG_REQUIRE(edge_index && keep && out && out_flags, "edge_gather: NULL pointer");
+  const int64_t blocks = ceil_div64(E_keep, 256);
+  SRG_REQUIRE(blocks <= 2147483647LL, "edge_gather: too many edges");
+  edge_gather_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const long long *>(edge_index), E, reinterpret_cast<const long long *>(keep), E_keep,
+      reinterpret_cast<long long *>(out), out_flags);
+  SRG_LAUNCHED();
+  return SRG_OK;
+}
+
+// sorted keys (m of them, possibly with duplicates) -> unique CSR.  vals may be NULL.
+static int keys_to_csr(uint64_t *sorted_keys, double *sorted_vals, int64_t m, int64_t n, int32_t *out_indptr,
+                       int32_t *out_indices, double *out_vals, int32_t *out_nnz_dev, cudaStream_t s) {
+  int *head = nullptr;
+  const int64_t ints = 2 * (m + 1) + scan_scratch_ints(m);
+  SRG_CUDA(cudaMallocAsync(&head, (size_t)ints * sizeof(int), s));
+  int *seg = head + (m + 1);
+  int *scratch = seg + (m + 1);
+  uint64_t *ukeys = nullptr;
+  SRG_CUDA(cudaMallocAsync(&ukeys, (size_t)(m > 0 ? m : 1) * sizeof(uint64_t), s));
+  const unsigned blocks = (unsigned)ceil_div64(m, 256);
+  int rc = SRG_OK;
+  if (m > 0) {
+    head_flags_kernel<<<blocks, 256, 0, s>>>(sorted_keys, m, head);
+    SRG_LAUNCHED();
+  }
+  rc = exclusive_scan_i32(head, m, seg, scratch, s);  // seg[m] = number of unique keys
+  if (!rc && m > 0) {
+    if (sorted_vals)
+      compact_unique_kernel<true><<<blocks, 256, 0, s>>>(sorted_keys, head, seg, m, sorted_vals, out_indices, ukeys, out_vals);
+    else
+      compact_unique_kernel<false><<<blocks, 256, 0, s>>>(sorted_keys, head, seg, m, nullptr, out_indices, ukeys, nullptr);
+    SRG_LAUNCHED();
+  }
+  if (!rc) {
+    row_lower_bound_kernel<<<(unsigned)ceil_div64(n + 1, 256), 256, 0, s>>>(ukeys, seg + m, n, out_indptr);
+    SRG_LAUNCHED();
+    if (out_nnz_dev) {
+      set_int_kernel<<<1, 1, 0, s>>>(out_nnz_dev, seg + m);
+      SRG_LAUNCHED();
+    }
+  }
+  cudaFreeAsync(ukeys, s);
+  cudaFreeAsync(head, s);
+  return rc;
+}
+
+extern "C" int srg_edges_to_sym_csr(const int64_t *edge_index, int64_t E, int64_t n,
+                                    int32_t *out_indptr, int32_t *out_indices, int32_t *out_nnz_dev,
+                                    int32_t *out_flags, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(E >= 0 && n >= 0, "edges_to_sym_csr: negative size");
+  SRG_REQUIRE(out_indptr && out_flags, "edges_to_sym_csr: NULL pointer");
+  SRG_REQUIRE(2 * E <= 2147483647LL && n <= 2147483647LL, "edges_to_sym_csr: exceeds the int32 CSR range");
+  cudaStream_t s = as_stream(stream);
+  const int64_t m = 2 * E;
+  uint64_t *keys = nullptr;
+  SRG_CUDA(cudaMallocAsync(&keys, (size_t)(m > 0 ? 2 * m : 1) * sizeof(uint64_t), s));
+  if (m > 0) {
+    SRG_REQUIRE(edge_index && out_indices, "edges_to_sym_csr: NULL pointer");
+    sym_keys_kernel<<<(unsigned)ceil_div64(E, 256), 256, 0, s>>>(reinterpret_cast<const long long *>(edge_index), E, n, keys, out_flags);
+    SRG_LAUNCHED();
+    rc = sort_keys(keys, keys + m, m, 32 + bits_for(n), s);
+  }
+  if (!rc) rc = keys_to_csr(keys + m, nullptr, m, n, out_indptr, out_indices, nullptr, out_nnz_dev, s);
+  cudaFreeAsync(keys, s);
+  return rc;
+}
+
+extern "C" int srg_csr_canonicalize(const int32_t *indptr, const int32_t *indices, const void *data,
+                                    int val_dtype, int64_t n, int64_t nnz, int32_t *out_indptr,
+                                    int32_t *out_indices, double *out_vals, int32_t *out_nnz_dev,
+                                    int32_t *out_flags, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n >= 0 && nnz >= 0, "csr_canonicalize: negative size");
+  SRG_REQUIRE(indptr && out_indptr && out_flags, "csr_canonicalize: NULL pointer");
+  SRG_REQUIRE(val_dtype >= 0 && val_dtype <= 2, "csr_canonicalize: bad val_dtype");
+  cudaStream_t s = as_stream(stream);
+  uint64_t *keys = nullptr;
+  double *vals = nullptr;
+  const int64_t m = nnz;
+  SRG_CUDA(cudaMallocAsync(&keys, (size_t)(m > 0 ? 2 * m : 1) * sizeof(uint64_t), s));
+  SRG_CUDA(cudaMallocAsync(&vals, (size_t)(m > 0 ? 2 * m : 1) * sizeof(double), s));
+  if (m > 0) {
+    SRG_REQUIRE(indices && out_indices && out_vals, "csr_canonicalize: NULL pointer");
+    const unsigned wb = (unsigned)ceil_div64(n * 32, 256);
+    if (val_dtype == SRG_VAL_F32)
+      csr_keys_kernel<float><<<wb, 256, 0, s>>>(indptr, indices, static_cast<const float *>(data), n, keys, vals, out_flags, false);
+    else if (val_dtype == SRG_VAL_F64)
+      csr_keys_kernel<double><<<wb, 256, 0, s>>>(indptr, indices, static_cast<const double *>(data), n, keys, vals, out_flags, false);
+    else
+      csr_keys_kernel<double><<<wb, 256, 0, s>>>(indptr, indices, nullptr, n, keys, vals, out_flags, false);
+    SRG_LAUNCHED();
+    rc = sort_pairs<double>(keys, keys + m, vals, vals + m, m, 32 + bits_for(n), s);
+  }
+  if (!rc) rc = keys_to_csr(keys + m, vals + m, m, n, out_indptr, out_indices, out_vals, out_nnz_dev, s);
+  cudaFreeAsync(vals, s);
+  cudaFreeAsync(keys, s);
+  return rc;
+}
+
+namespace srg {
+// defined in norm.cu: fills A~ (pattern, values), degree and the power tables
+int selfloop_fill_dispatch(const int32_t *indptr, const int32_t *indices, const void *data, int val_dtype,
+                           int64_t n, const int32_t *at_indptr, int32_t *at_indices, double *at_val,
+                           double *degree, double *dl, double *dr, double r, cudaStream_t s);
+}  // namespace srg
+
+extern "C" int srg_sym_norm_csr_general(const int32_t *indptr, const int32_t *indices,
+                                        const void *data, int val_dtype, int64_t n, int64_t nnz,
+                                        const int32_t *at_indptr, double r, double ppr_alpha,
+                                        int32_t *out_indptr, int32_t *out_indices,
+                                        double *out_degree, double *out_val_f64, float *out_val_f32,
+                                        int32_t *out_flags, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n >= 0 && nnz >= 0, "sym_norm_general: negative size");
+  if (n == 0) return SRG_OK;
+  SRG_REQUIRE(indptr && indices && at_indptr && out_indptr && out_indices && out_flags, "sym_norm_general: NULL pointer");
+  SRG_REQUIRE(val_dtype >= 0 && val_dtype <= 2, "sym_norm_general: bad val_dtype");
+  SRG_REQUIRE(nnz + n <= 2147483647LL, "sym_norm_general: nnz + n exceeds the int32 CSR range");
+  cudaStream_t s = as_stream(stream);
+  const int64_t cap = nnz + n;
+  // scratch: A~ indices, A~ values, degree, dl, dr, keys x2, vals x2
+  int *at_indices = nullptr;
+  double *dscratch = nullptr;
+  uint64_t *keys = nullptr;
+  SRG_CUDA(cudaMallocAsync(&at_indices, (size_t)cap * sizeof(int), s));
+  SRG_CUDA(cudaMallocAsync(&dscratch, (size_t)(3 * n + 3 * cap) * sizeof(double), s));
+  SRG_CUDA(cudaMallocAsync(&keys, (size_t)(2 * cap) * sizeof(uint64_t), s));
+  double *deg = out_degree ? out_degree : dscratch;
+  double *dl = dscratch + n, *dr = dscratch + 2 * n;
+  double *at_val = dscratch + 3 * n, *vals = at_val + cap;
+  rc = selfloop_fill_dispatch(indptr, indices, data, val_dtype, n, at_indptr, at_indices, at_val, deg, dl, dr, r, s);
+  if (!rc) {
+    general_norm_vals_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, s>>>(
+        at_indptr, at_indices, at_val, deg, n, dl, dr, keys, vals, val_dtype == SRG_VAL_ONES ? 1 : 0);
+    SRG_LAUNCHED();
+  }
+  // The number of A~ entries is only known on the device (at_indptr[n]): this directed-graph path
+  // reads it back (one 4-byte synchronising copy) to size the sort.
+  int h_cnt = 0;
+  if (!rc) {
+    SRG_CUDA(cudaMemcpyAsync(&h_cnt, at_indptr + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SRG_CUDA(cudaStreamSynchronize(s));  // general (directed) path only: one small readback
+    rc = sort_pairs<double>(keys, keys + cap, vals, vals + cap, h_cnt, 32 + bits_for(n), s);
+  }
+  int *total = nullptr;
+  if (!rc) {
+    SRG_CUDA(cudaMallocAsync(&total, sizeof(int), s));
+    SRG_CUDA(cudaMemcpyAsync(total, &h_cnt, sizeof(int), cudaMemcpyHostToDevice, s));
+    row_lower_bound_kernel<<<(unsigned)ceil_div64(n + 1, 256), 256, 0, s>>>(keys + cap, total, n, out_indptr);
+    SRG_LAUNCHED();
+    if (h_cnt > 0) {
+      finalize_general_kernel<<<(unsigned)ceil_div64(h_cnt, 256), 256, 0, s>>>(
+          keys + cap, vals + cap, total, 1.0 - ppr_alpha, ppr_alpha, ppr_alpha >= 0.0 ? 1 : 0, out_indices,
+          out_val_f64, out_val_f32, out_flags);
+      SRG_LAUNCHED();
+    }
+    SRG_CUDA(cudaStreamSynchronize(s));  // h_cnt lives on this stack frame
+    cudaFreeAsync(total, s);
+  }
+  cudaFreeAsync(keys, s);
+  cudaFreeAsync(dscratch, s);
+  cudaFreeAsync(at_indices, s);
+  return rc;
+}

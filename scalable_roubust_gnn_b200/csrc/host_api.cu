@@ -127,13 +127,9 @@ static int check_flags(int flags) {
     set_err("adjacency has a column index outside [0, n)");
     return SRG_ERR_INVALID;
   }
-  if (flags & SRG_FLAG_UNSORTED) {
-    set_err("adjacency CSR is not canonical (unsorted or duplicate column indices); canonicalise it first");
-    return SRG_ERR_UNSUPPORTED;
-  }
-  if (flags & SRG_FLAG_ASYMMETRIC) {
-    set_err("adjacency pattern is not symmetric; the general transpose path is required");
-    return SRG_ERR_UNSUPPORTED;
+  if (flags & (SRG_FLAG_UNSORTED | SRG_FLAG_ASYMMETRIC)) {
+    set_err("internal: normalisation retry did not resolve flags 0x%x", flags);
+    return SRG_ERR_CUDA;
   }
   if (flags & SRG_FLAG_ZERO_PRODUCT) {
     set_err("a normalised value is exactly 0 (scipy would drop the entry); compaction path required");
@@ -152,18 +148,56 @@ struct NormOut {
 
 static int run_norm(PoolAllocs &pa, const int32_t *d_indptr, const int32_t *d_indices,
                     const void *d_data, int val_dtype, int64_t n, int64_t nnz, double r,
-                    double ppr_alpha, bool want64, bool want32, cudaStream_t s, NormOut *o) {
+                    double ppr_alpha, bool want64, bool want32, cudaStream_t s, bool canon,
+                    bool general, NormOut *o) {
   int rc;
-  if ((rc = pa.alloc(&o->indptr, n + 1))) return rc;
+  if ((rc = pa.alloc(&o->flags, 1))) return rc;
+  SRG_CUDA(cudaMemsetAsync(o->flags, 0, sizeof(int32_t), s));
+  if (canon) {
+    // unsorted rows / duplicate entries: sort + sum first (scipy's tocoo() + eye does the same)
+    int32_t *c_indptr, *c_indices, *c_nnz;
+    double *c_vals;
+    if ((rc = pa.alloc(&c_indptr, n + 1))) return rc;
+    if ((rc = pa.alloc(&c_indices, nnz))) return rc;
+    if ((rc = pa.alloc(&c_vals, nnz))) return rc;
+    if ((rc = pa.alloc(&c_nnz, 1))) return rc;
+    if ((rc = srg_csr_canonicalize(d_indptr, d_indices, d_data, val_dtype, n, nnz, c_indptr, c_indices, c_vals,
+                                   c_nnz, o->flags, s)))
+      return rc;
+    d_indptr = c_indptr;
+    d_indices = c_indices;
+    d_data = c_vals;
+    val_dtype = SRG_VAL_F64;
+  }
+  int32_t *at_indptr;
+  if ((rc = pa.alloc(&at_indptr, n + 1))) return rc;
   if ((rc = pa.alloc(&o->indices, nnz + n))) return rc;
   if (want64 && (rc = pa.alloc(&o->val64, nnz + n))) return rc;
   if (want32 && (rc = pa.alloc(&o->val32, nnz + n))) return rc;
-  if ((rc = pa.alloc(&o->flags, 1))) return rc;
-  SRG_CUDA(cudaMemsetAsync(o->flags, 0, sizeof(int32_t), s));
-  rc = srg_degree_selfloop_csr(d_indptr, d_indices, d_data, val_dtype, n, o->indptr, nullptr, o->flags, s);
+  rc = srg_degree_selfloop_csr(d_indptr, d_indices, d_data, val_dtype, n, at_indptr, nullptr, o->flags, s);
   if (rc) return rc;
-  return srg_sym_norm_csr(d_indptr, d_indices, d_data, val_dtype, n, nnz, o->indptr, r, ppr_alpha,
-                          o->indices, nullptr, o->val64, o->val32, o->flags, s);
+  if (!general) {
+    o->indptr = at_indptr;
+    return srg_sym_norm_csr(d_indptr, d_indices, d_data, val_dtype, n, nnz, at_indptr, r, ppr_alpha,
+                            o->indices, nullptr, o->val64, o->val32, o->flags, s);
+  }
+  if ((rc = pa.alloc(&o->indptr, n + 1))) return rc;
+  return srg_sym_norm_csr_general(d_indptr, d_indices, d_data, val_dtype, n, nnz, at_indptr, r, ppr_alpha,
+                                  o->indptr, o->indices, nullptr, o->val64, o->val32, o->flags, s);
+}
+
+// which retry the flags ask for: returns true when another attempt with (canon, general) makes sense
+static bool next_attempt(int flags, bool *canon, bool *general) {
+  if (flags & SRG_FLAG_BAD_INDEX) return false;
+  if ((flags & SRG_FLAG_UNSORTED) && !*canon) {
+    *canon = true;
+    return true;
+  }
+  if ((flags & SRG_FLAG_ASYMMETRIC) && !*general) {
+    *general = true;
+    return true;
+  }
+  return false;
 }
 
 }  // namespace srg
@@ -195,11 +229,10 @@ extern "C" int srg_release_workspace(void) {
   return SRG_OK;
 }
 
-extern "C" int srg_construct_adj_host(const int32_t *indptr, const int32_t *indices,
-                                      const void *data, int val_dtype, int64_t n, int64_t nnz,
-                                      double r, double ppr_alpha, int32_t *out_indptr,
-                                      int32_t *out_indices, double *out_data, int64_t *out_nnz,
-                                      int device) {
+static int construct_attempt(const int32_t *indptr, const int32_t *indices, const void *data,
+                             int val_dtype, int64_t n, int64_t nnz, double r, double ppr_alpha,
+                             int32_t *out_indptr, int32_t *out_indices, double *out_data,
+                             int64_t *out_nnz, int device, bool canon, bool general, int *flags_out) {
   int rc = require_device();
   if (rc) return rc;
   SRG_REQUIRE(n >= 0 && nnz >= 0, "construct_adj: negative size");
@@ -234,12 +267,16 @@ extern "C" int srg_construct_adj_host(const int32_t *indptr, const int32_t *indi
     }
     NormOut no;
     if ((rc = run_norm(pa, d_indptr, d_indices, d_data, val_dtype, n, nnz, r, ppr_alpha,
-                       out_data != nullptr, false, s, &no)))
+                       out_data != nullptr, false, s, canon, general, &no)))
       return rc;
     SRG_CUDA(cudaMemcpyAsync(&flags, no.flags, 4, cudaMemcpyDeviceToHost, s));
     SRG_CUDA(cudaMemcpyAsync(out_indptr, no.indptr, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, s));
     SRG_CUDA(cudaStreamSynchronize(s));
-    if ((rc = check_flags(flags))) return rc;
+    *flags_out = flags;
+    if (flags) {
+      pa.clean = true;
+      return SRG_OK;  // the caller decides between a retry and an error
+    }
     nnz_out = out_indptr[n];
     if (out_indices) SRG_CUDA(cudaMemcpyAsync(out_indices, no.indices, (size_t)nnz_out * 4, cudaMemcpyDeviceToHost, s));
     if (out_data) SRG_CUDA(cudaMemcpyAsync(out_data, no.val64, (size_t)nnz_out * 8, cudaMemcpyDeviceToHost, s));
@@ -250,12 +287,28 @@ extern "C" int srg_construct_adj_host(const int32_t *indptr, const int32_t *indi
   return SRG_OK;
 }
 
-extern "C" int srg_propagate_host(const int32_t *indptr, const int32_t *indices, const void *data,
-                                  int val_dtype, int64_t n, int64_t nnz, const float *features,
-                                  int32_t F, const int32_t *feature_mask, int32_t K, double r,
-                                  double ppr_alpha, float *const *out_hops,
-                                  int32_t *out_norm_indptr, int32_t *out_norm_indices,
-                                  double *out_norm_data, int64_t *out_nnz, int device) {
+extern "C" int srg_construct_adj_host(const int32_t *indptr, const int32_t *indices,
+                                      const void *data, int val_dtype, int64_t n, int64_t nnz,
+                                      double r, double ppr_alpha, int32_t *out_indptr,
+                                      int32_t *out_indices, double *out_data, int64_t *out_nnz,
+                                      int device) {
+  bool canon = false, general = false;
+  for (;;) {
+    int flags = 0;
+    int rc = construct_attempt(indptr, indices, data, val_dtype, n, nnz, r, ppr_alpha, out_indptr, out_indices,
+                               out_data, out_nnz, device, canon, general, &flags);
+    if (rc) return rc;
+    if (!flags) return SRG_OK;
+    if (!next_attempt(flags, &canon, &general)) return check_flags(flags);
+  }
+}
+
+static int propagate_attempt(const int32_t *indptr, const int32_t *indices, const void *data,
+                             int val_dtype, int64_t n, int64_t nnz, const float *features,
+                             int32_t F, const int32_t *feature_mask, int32_t K, double r,
+                             double ppr_alpha, float *const *out_hops, int32_t *out_norm_indptr,
+                             int32_t *out_norm_indices, double *out_norm_data, int64_t *out_nnz,
+                             int device, bool canon, bool general, int *flags_out) {
   int rc = require_device();
   if (rc) return rc;
   SRG_REQUIRE(n >= 0 && nnz >= 0 && F >= 0 && K >= 0, "propagate_host: negative size");
@@ -325,7 +378,7 @@ extern "C" int srg_propagate_host(const int32_t *indptr, const int32_t *indices,
     SRG_CUDA(cudaStreamWaitEvent(s_c, st->ev_csr, 0));
     NormOut no;
     if ((rc = run_norm(pa, d_indptr, d_indices, d_data, val_dtype, n, nnz, r, ppr_alpha,
-                       out_norm_data != nullptr, true, s_c, &no)))
+                       out_norm_data != nullptr, true, s_c, canon, general, &no)))
       return rc;
     SRG_CUDA(cudaEventRecord(st->ev_norm, s_c));
 
@@ -364,7 +417,8 @@ extern "C" int srg_propagate_host(const int32_t *indptr, const int32_t *indices,
       SRG_CUDA(cudaMemcpyAsync(out_norm_indptr, no.indptr, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, s_in));
     SRG_CUDA(cudaStreamSynchronize(s_in));
     nnz_out = h_nnz_out;
-    int frc = check_flags(flags);
+    *flags_out = flags;
+    const int frc = flags ? 1 : 0;  // flagged: results are discarded, the caller retries or fails
     if (!frc) {
       if (out_norm_indices)
         SRG_CUDA(cudaMemcpyAsync(out_norm_indices, no.indices, (size_t)nnz_out * 4, cudaMemcpyDeviceToHost, s_in));
@@ -375,10 +429,28 @@ extern "C" int srg_propagate_host(const int32_t *indptr, const int32_t *indices,
     SRG_CUDA(cudaStreamSynchronize(s_out));
     SRG_CUDA(cudaStreamSynchronize(s_c));
     pa.clean = true;
-    if (frc) return frc;
+    if (frc) return SRG_OK;
   }
   if (out_nnz) *out_nnz = nnz_out;
   return SRG_OK;
+}
+
+extern "C" int srg_propagate_host(const int32_t *indptr, const int32_t *indices, const void *data,
+                                  int val_dtype, int64_t n, int64_t nnz, const float *features,
+                                  int32_t F, const int32_t *feature_mask, int32_t K, double r,
+                                  double ppr_alpha, float *const *out_hops,
+                                  int32_t *out_norm_indptr, int32_t *out_norm_indices,
+                                  double *out_norm_data, int64_t *out_nnz, int device) {
+  bool canon = false, general = false;
+  for (;;) {
+    int flags = 0;
+    int rc = propagate_attempt(indptr, indices, data, val_dtype, n, nnz, features, F, feature_mask, K, r, ppr_alpha,
+                               out_hops, out_norm_indptr, out_norm_indices, out_norm_data, out_nnz, device, canon,
+                               general, &flags);
+    if (rc) return rc;
+    if (!flags) return SRG_OK;
+    if (!next_attempt(flags, &canon, &general)) return check_flags(flags);
+  }
 }
 
 // ---- literal reference ABI ------------------------------------------------------------------------

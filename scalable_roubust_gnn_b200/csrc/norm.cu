@@ -241,6 +241,21 @@ sym_norm_values_kernel(long long n, const int *__restrict__ out_indptr,
   if (fl) atomicOr(flags, fl);
 }
 
+// used by the general (transpose) path in coo.cu
+int selfloop_fill_dispatch(const int32_t *indptr, const int32_t *indices, const void *data, int val_dtype,
+                           int64_t n, const int32_t *at_indptr, int32_t *at_indices, double *at_val,
+                           double *degree, double *dl, double *dr, double r, cudaStream_t s) {
+  const unsigned blocks = (unsigned)ceil_div64(n, 256);
+  if (val_dtype == SRG_VAL_ONES)
+    selfloop_fill_kernel<SRG_VAL_ONES><<<blocks, 256, 0, s>>>(indptr, indices, data, n, at_indptr, at_indices, at_val, degree, dl, dr, r - 1.0, -r);
+  else if (val_dtype == SRG_VAL_F32)
+    selfloop_fill_kernel<SRG_VAL_F32><<<blocks, 256, 0, s>>>(indptr, indices, data, n, at_indptr, at_indices, at_val, degree, dl, dr, r - 1.0, -r);
+  else
+    selfloop_fill_kernel<SRG_VAL_F64><<<blocks, 256, 0, s>>>(indptr, indices, data, n, at_indptr, at_indices, at_val, degree, dl, dr, r - 1.0, -r);
+  SRG_LAUNCHED();
+  return SRG_OK;
+}
+
 }  // namespace srg
 
 using namespace srg;

@@ -40,7 +40,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int *total) {
   return excl;
 }
 
-__global__ void __launch_bounds__(kScanThreads)
+static __global__ void __launch_bounds__(kScanThreads)
 scan_tile_sums_kernel(const int *__restrict__ in, long long n, int *__restrict__ tile_sums) {
   const long long base = (long long)blockIdx.x * kScanTile;
   int s = 0;
@@ -55,7 +55,7 @@ scan_tile_sums_kernel(const int *__restrict__ in, long long n, int *__restrict__
 }
 
 // single block: in-place exclusive scan of tile_sums[0..nt), writes grand total to tile_sums[nt]
-__global__ void __launch_bounds__(1024) scan_tile_offsets_kernel(int *tile_sums, int nt) {
+static __global__ void __launch_bounds__(1024) scan_tile_offsets_kernel(int *tile_sums, int nt) {
   __shared__ int carry_s;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(1024) scan_tile_offsets_kernel(int *tile_sums,
   if (threadIdx.x == 0) tile_sums[nt] = carry_s;
 }
 
-__global__ void __launch_bounds__(kScanThreads)
+static __global__ void __launch_bounds__(kScanThreads)
 scan_apply_kernel(const int *__restrict__ in, long long n, const int *__restrict__ tile_sums,
                   int nt, int *__restrict__ out) {
   // thread t owns kScanItems consecutive elements so the tile is scanned in order

@@ -614,3 +614,9 @@ extern "C" int srg_unpack_features_f32(const float *src, int64_t ld_src, float *
   SRG_LAUNCHED();
   return SRG_OK;
 }
+
+extern "C" int srg_apply_feature_mask_f32(const float *x, int64_t ld_x, const int32_t *mask, float *out,
+                                          int64_t ld_out, int64_t n, int32_t F, void *stream) {
+  SRG_REQUIRE(mask != nullptr, "apply_feature_mask: mask is NULL");
+  return srg_pack_features_f32(x, ld_x, out, ld_out, n, F, mask, stream);
+}

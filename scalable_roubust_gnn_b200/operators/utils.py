@@ -57,14 +57,6 @@ def csr_host_parts(adj):
     return indptr, indices, data, vt, n, nnz
 
 
-def _canonical(adj):
-    """scipy's `adj.tocoo() + eye` sums duplicates and sorts; do the same for non-canonical
-    input (rare: every dataset of the reference is already canonical)."""
-    adj = adj.copy()
-    adj.sum_duplicates()
-    return adj
-
-
 def _empty(shape, dtype, pin):
     t = torch.empty(shape, dtype=dtype, pin_memory=bool(pin))
     return t
@@ -83,12 +75,7 @@ def adj_to_symmetric_norm(adj, r, ppr_alpha=None, device=0, pin=True):
     lib = _lib.load()
     if sp.issparse(adj) and not isinstance(adj, sp.csr_matrix):
         adj = adj.tocsr()
-    try:
-        return _construct(lib, adj, r, ppr_alpha, device, pin)
-    except _lib.SrgUnsupported as e:
-        if "not canonical" in e.message:
-            return _construct(lib, _canonical(adj), r, ppr_alpha, device, pin)
-        raise
+    return _construct(lib, adj, r, ppr_alpha, device, pin)
 
 
 def _construct(lib, adj, r, ppr_alpha, device, pin):
@@ -139,13 +126,7 @@ def propagate_host(adj, feature, prop_steps, r, ppr_alpha=None, feature_mask=Non
     when a GPU is present); ``adj_norm`` is the normalised scipy CSR when ``return_adj`` else None.
     """
     lib = _lib.load()
-    try:
-        return _propagate(lib, adj, feature, prop_steps, r, ppr_alpha, feature_mask, device, pin, return_adj)
-    except _lib.SrgUnsupported as e:
-        if "not canonical" in e.message:
-            return _propagate(lib, _canonical(adj), feature, prop_steps, r, ppr_alpha, feature_mask, device, pin,
-                              return_adj)
-        raise
+    return _propagate(lib, adj, feature, prop_steps, r, ppr_alpha, feature_mask, device, pin, return_adj)
 
 
 def _propagate(lib, adj, feature, K, r, ppr_alpha, feature_mask, device, pin, return_adj):

@@ -1,0 +1,149 @@
+"""Chebyshev heat-kernel wavelets on the GPU.
+
+Mirrors ``WaveletSparsifier`` (wavelet/src/utils.py:70-138) and the batched twin
+``SpectralModel.calculate_wavelet`` (SSRG/models/base_scalable/base_model.py:236-265).  In the
+reference the arithmetic lives in pygsp (absent, un-pinned: PARITY UNPINNED); the recurrence that
+``oracle.cheby_op`` restates runs here as fused SpMM + epilogue kernels in fp64
+(csrc/cheby.cu), both scales sharing every T_k.
+
+Host-side setup that stays on the host (scalars, a handful of flops): the m+1 Chebyshev
+coefficients of the heat kernel and lambda_max (ARPACK in pygsp; an input of the kernel).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _lib
+from .device import DeviceCSR, _p, _stream_ptr, upload_csr
+
+__all__ = ["laplacian", "heat_cheby_coeffs", "estimate_lmax", "cheby_filter", "WaveletSparsifier"]
+
+
+def laplacian(w: DeviceCSR):
+    """L = diag(W 1) - W on the device.  Returns (DeviceCSR with float64 data, degree, flags)."""
+    lib = _lib.load()
+    dev = w.indptr.device
+    n, nnz = w.n, w.nnz
+    cap = max(nnz + n, 1)
+    o_indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    o_indices = torch.empty(cap, dtype=torch.int32, device=dev)
+    o_vals = torch.empty(cap, dtype=torch.float64, device=dev)
+    o_deg = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(lib.srg_laplacian_csr(_p(w.indptr), _p(w.indices), _p(w.data), w.val_dtype, n, _p(o_indptr),
+                                     _p(o_indices), _p(o_vals), _p(o_deg), _p(flags), _stream_ptr(dev)))
+    return DeviceCSR(o_indptr, o_indices, o_vals, n, -1), o_deg, flags
+
+
+def heat_cheby_coeffs(tau: float, lmax: float, order: int) -> np.ndarray:
+    """pygsp compute_cheby_coeff(Heat(G, tau), m=order): order+1 quadrature points on [0, lmax]."""
+    n_q = order + 1
+    a = lmax / 2.0
+    j = np.arange(n_q)
+    theta = np.pi * (j + 0.5) / n_q
+    g = np.exp(-tau * (a * np.cos(theta) + a) / lmax)
+    return np.array([2.0 / n_q * np.sum(g * np.cos(np.pi * o * (j + 0.5) / n_q)) for o in range(order + 1)])
+
+
+def estimate_lmax(lap_host) -> float:
+    """pygsp Graph.estimate_lmax: 1.01 x ARPACK's largest eigenvalue (tol 5e-3, ncv = min(N, 10))."""
+    from scipy.sparse.linalg import eigsh
+    n = lap_host.shape[0]
+    return float(eigsh(lap_host, k=1, tol=5e-3, ncv=min(n, 10), return_eigenvectors=False)[0]) * 1.01
+
+
+def cheby_filter(lap: DeviceCSR, x: torch.Tensor, lmax: float, coeffs, tol: float | None = None, want_f32=False):
+    """r_s = sum_k coeffs[s][k] T_k(L~) x for every coefficient vector (fp64, device resident).
+
+    ``x``: float64 cuda tensor n x B with an even row stride.  Returns a list of float64 tensors
+    (and a list of float32 tensors when ``want_f32``).
+    """
+    lib = _lib.load()
+    coeffs = np.ascontiguousarray(np.atleast_2d(np.asarray(coeffs, dtype=np.float64)))
+    n_scales, m1 = coeffs.shape
+    order = m1 - 1
+    assert x.is_cuda and x.dtype == torch.float64 and x.stride(1) == 1 and x.stride(0) % 2 == 0
+    n, b = x.shape
+    ld = x.stride(0)
+    outs = [torch.empty((n, ld), dtype=torch.float64, device=x.device) for _ in range(n_scales)]
+    outs32 = [torch.empty((n, ld), dtype=torch.float32, device=x.device) for _ in range(n_scales)] if want_f32 else None
+    w0 = torch.empty((n, ld), dtype=torch.float64, device=x.device)
+    w1 = torch.empty((n, ld), dtype=torch.float64, device=x.device)
+    r_ptrs = (C.c_void_p * n_scales)(*[o.data_ptr() for o in outs])
+    q_ptrs = (C.c_void_p * n_scales)(*[o.data_ptr() for o in outs32]) if want_f32 else None
+    tol_v = float("nan") if tol is None else float(tol)
+    _lib.check(lib.srg_cheby_filter_f64(_p(lap.indptr), _p(lap.indices), _p(lap.data), n, _p(x), ld, b, float(lmax),
+                                        coeffs.ctypes.data_as(C.POINTER(C.c_double)), n_scales, order, tol_v, r_ptrs,
+                                        q_ptrs, ld, _p(w0), _p(w1), _stream_ptr(x.device)))
+    outs = [o[:, :b] for o in outs]
+    if want_f32:
+        return outs, [o[:, :b] for o in outs32]
+    return outs
+
+
+class WaveletSparsifier:
+    """Sparsified heat-kernel wavelets Psi(-s), Psi(+s) of a graph (wavelet/src/utils.py:70-138).
+
+    ``graph`` may be a scipy sparse adjacency or a networkx graph (the reference's argument); the
+    adjacency is symmetrised the way ``nx.Graph`` does.  Impulse columns are processed in blocks on
+    the device (the reference materialises the N x N identity, utils.py:94).
+    """
+
+    def __init__(self, graph, scale, approximation_order, tolerance, lmax=None, block=1024, device="cuda"):
+        if not sp.issparse(graph):
+            import networkx as nx  # only when the caller already uses it
+            graph = nx.adjacency_matrix(graph)
+        w = sp.csr_matrix(graph, dtype=np.float64)
+        w = w.maximum(w.T).tocsr()
+        w.sort_indices()
+        self.n = w.shape[0]
+        self.device = device
+        self.block = int(block)
+        self.scales = [-scale, scale]
+        self.approximation_order = approximation_order
+        self.tolerance = tolerance
+        self.phi_matrices = []
+        self._w_dev = upload_csr(w, device=device)
+        self.lap, self.degree, flags = laplacian(self._w_dev)
+        if lmax is None:
+            m = int(self.lap.indptr[-1].item())
+            lap_host = sp.csr_matrix((self.lap.data[:m].cpu().numpy(), self.lap.indices[:m].cpu().numpy(),
+                                      self.lap.indptr.cpu().numpy()), shape=(self.n, self.n))
+            lmax = estimate_lmax(lap_host)
+        self.lmax = float(lmax)
+
+    def chebyshev_coefficients(self):
+        return np.stack([heat_cheby_coeffs(s, self.lmax, self.approximation_order) for s in self.scales])
+
+    def calculate_all_wavelets(self, normalize=True):
+        coeffs = self.chebyshev_coefficients()
+        blocks = [[] for _ in self.scales]
+        for j0 in range(0, self.n, self.block):
+            b = min(self.block, self.n - j0)
+            ld = (b + 1) // 2 * 2
+            x = torch.zeros((self.n, ld), dtype=torch.float64, device=self.device)
+            idx = torch.arange(b, device=self.device)
+            x[j0 + idx, idx] = 1.0
+            _, r32 = cheby_filter(self.lap, x[:, :b] if ld == b else x.as_strided((self.n, b), (ld, 1)), self.lmax,
+                                  coeffs, tol=self.tolerance, want_f32=True)
+            for s, r in enumerate(r32):
+                blocks[s].append(sp.csr_matrix(r.cpu().numpy()))
+        self.phi_matrices = [sp.hstack(bl).tocsr() for bl in blocks]
+        if normalize:
+            self.normalize_matrices()
+        return self.phi_matrices
+
+    def normalize_matrices(self):
+        """L1 row normalisation (sklearn.preprocessing.normalize(norm='l1', axis=1), utils.py:106-112)."""
+        out = []
+        for phi in self.phi_matrices:
+            phi = phi.tocsr().astype(np.float32)
+            norms = np.abs(phi).sum(axis=1).A1
+            norms[norms == 0] = 1.0
+            phi.data = phi.data / np.repeat(norms, np.diff(phi.indptr)).astype(np.float32)
+            out.append(phi)
+        self.phi_matrices = out

@@ -58,6 +58,7 @@ extern "C" {
 #define SRG_FLAG_ASYMMETRIC 2     /* pattern of (A+I) not symmetric: general transpose path required */
 #define SRG_FLAG_ZERO_PRODUCT 4   /* a normalised value is exactly 0: scipy would drop the entry     */
 #define SRG_FLAG_BAD_INDEX 8      /* a column index is outside [0, n)                                */
+#define SRG_FLAG_WEIGHTED 16      /* informational: some stored value differs from 1.0              */
 
 /* ---- library / diagnostics ------------------------------------------------------------- */
 int srg_abi_version(void);
@@ -104,6 +105,33 @@ int srg_sym_norm_csr(const int32_t *indptr, const int32_t *indices, const void *
                      int val_dtype, int64_t n, int64_t nnz, const int32_t *out_indptr, double r,
                      double ppr_alpha, int32_t *out_indices, double *out_degree,
                      double *out_val_f64, float *out_val_f32, int32_t *out_flags, void *stream);
+
+/*
+ * The same two stages on a ROW SLICE [row0, row0 + n_rows) of an n_cols-column adjacency (column ids
+ * stay global): the building blocks of the row-partitioned multi-GPU normalisation.
+ *   srg_selfloop_rows_csr      stage 1 on the slice (diagonal = global row id)
+ *   srg_selfloop_fill_rows_csr pattern of A~ for the slice, its values (written only when the slice
+ *                              is weighted, see SRG_FLAG_WEIGHTED) and the slice's degrees
+ *   srg_pow_tables_f64         d^(r-1), d^(-r) with inf -> 0 over a (gathered) degree vector
+ *   srg_norm_values_rows_csr   R values of the slice from the GLOBAL power tables.  check_symmetry
+ *                              (row0 must be 0: every row local) verifies A~ == A~^T exactly (mirror
+ *                              lookup of every upper entry + upper/lower counts) and raises
+ *                              SRG_FLAG_ASYMMETRIC otherwise; without it symmetry is the caller's promise.
+ */
+int srg_selfloop_rows_csr(const int32_t *indptr, const int32_t *indices, const void *data,
+                          int val_dtype, int64_t n_rows, int64_t row0, int64_t n_cols,
+                          int32_t *out_indptr, int32_t *out_count, int32_t *out_flags, void *stream);
+int srg_selfloop_fill_rows_csr(const int32_t *indptr, const int32_t *indices, const void *data,
+                               int val_dtype, int64_t n_rows, int64_t row0, int64_t n_cols,
+                               const int32_t *at_indptr, int32_t *at_indices, double *at_val,
+                               double *out_degree, const int32_t *flags, void *stream);
+int srg_pow_tables_f64(const double *degree, int64_t n, double r, double *out_left,
+                       double *out_right, void *stream);
+int srg_norm_values_rows_csr(const int32_t *at_indptr, const int32_t *at_indices,
+                             const double *at_val, const double *degree_rows, int64_t n_rows,
+                             int64_t row0, const double *pow_left, const double *pow_right,
+                             double ppr_alpha, int check_symmetry, double *out_val_f64,
+                             float *out_val_f32, int32_t *flags, void *stream);
 
 /*
  * General path of stage 2 for a NON-symmetric pattern (directed input): explicit transpose by a
@@ -153,6 +181,24 @@ int srg_apply_feature_mask_f32(const float *x, int64_t ld_x, const int32_t *mask
 int srg_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
                      int64_t n_rows, const float *X, int64_t ldx, float *Y, int64_t ldy,
                      int32_t F, void *stream);
+
+/* ---- (e) row-partitioned multi-GPU hop ------------------------------------------------------- */
+/*
+ * One hop over this rank's row slice with the exchange fused into the epilogue: every finished row
+ * (global row dest_row0 + i) is stored into ALL n_dests (<= 8) next-hop buffers — this rank's own
+ * and its peers', mapped over NVLink through srg_ipc_open — so no separate all-gather runs.  `dests`
+ * is a HOST array of device pointers to the full (all rows) n_total x ldy buffers.  The caller
+ * orders hops across ranks (a stream-ordered collective / barrier between hops).
+ */
+int srg_spmm_csr_f32_push(const int32_t *indptr, const int32_t *indices, const float *vals,
+                          int64_t n_rows, const float *X, int64_t ldx, float *const *dests,
+                          int32_t n_dests, int64_t dest_row0, int64_t ldy, int32_t F, void *stream);
+/* peer-mappable device buffers: plain cudaMalloc + CUDA IPC handles (64 bytes) */
+int srg_ipc_alloc(void **ptr, int64_t bytes);
+int srg_ipc_free(void *ptr);
+int srg_ipc_get_handle(void *ptr, void *handle64);
+int srg_ipc_open(const void *handle64, void **ptr);
+int srg_ipc_close(void *ptr);
 
 /* ---- a1: K hops, device resident  (SSRG/operators/base_operator.py:31-35) ------------------ */
 /* hops[0] = input features, hops[k] = A^ * hops[k-1], k = 1..K; all n x ld fp32 device buffers. */

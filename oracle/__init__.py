@@ -143,12 +143,13 @@ def spmm_hop(adj_norm, feature, lib="oracle"):
     data = adj_norm.data.astype(np.float32)
     indices = np.ascontiguousarray(adj_norm.indices, dtype=np.int32)
     indptr = np.ascontiguousarray(adj_norm.indptr, dtype=np.int32)
-    answer = np.zeros(n * f, dtype=np.float32)
+    answer = np.zeros(adj_norm.shape[0] * f, dtype=np.float32)   # rectangular row slices allowed
     mat = feature.reshape(-1)
     if lib == "ref":
         rl = ref_lib()
         if rl is None:
             raise RuntimeError("oracle/_ref/libmatmul_ref.so not built")
+        assert adj_norm.shape[0] == n, "the reference's matmul.c assumes a square adjacency"
         rl.FloatCSRMulDenseOMP(answer, data, indices, indptr, mat, n, f)
     else:
         _lib().oracle_spmm_csr_f32(answer, f, data, indices, indptr, mat, f, adj_norm.shape[0], f)

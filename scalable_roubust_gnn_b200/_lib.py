@@ -24,7 +24,7 @@ SRG_ERR_RANGE = -34
 SRG_ERR_UNSUPPORTED = -95
 
 SRG_VAL_ONES, SRG_VAL_F32, SRG_VAL_F64 = 0, 1, 2
-SRG_FLAG_UNSORTED, SRG_FLAG_ASYMMETRIC, SRG_FLAG_ZERO_PRODUCT, SRG_FLAG_BAD_INDEX = 1, 2, 4, 8
+SRG_FLAG_UNSORTED, SRG_FLAG_ASYMMETRIC, SRG_FLAG_ZERO_PRODUCT, SRG_FLAG_BAD_INDEX, SRG_FLAG_WEIGHTED = 1, 2, 4, 8, 16
 
 
 class SrgError(RuntimeError):
@@ -51,12 +51,22 @@ SIGNATURES = {
     "srg_set_tuning": (C.c_int, [C.c_char_p, _i64]),
     "srg_degree_selfloop_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp]),
     "srg_sym_norm_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "srg_selfloop_rows_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "srg_selfloop_fill_rows_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "srg_pow_tables_f64": (C.c_int, [_vp, _i64, _f64, _vp, _vp, _vp]),
+    "srg_norm_values_rows_csr": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _f64, C.c_int, _vp, _vp, _vp, _vp]),
     "srg_sym_norm_csr_general": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "srg_csr_canonicalize": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "srg_edge_gather_i64": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "srg_edges_to_sym_csr": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "srg_apply_feature_mask_f32": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
     "srg_spmm_csr_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
+    "srg_spmm_csr_f32_push": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, C.POINTER(_vp), _i32, _i64, _i64, _i32, _vp]),
+    "srg_ipc_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
+    "srg_ipc_free": (C.c_int, [_vp]),
+    "srg_ipc_get_handle": (C.c_int, [_vp, _vp]),
+    "srg_ipc_open": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "srg_ipc_close": (C.c_int, [_vp]),
     "srg_propagate_khop_f32": (C.c_int, [_vp, _vp, _vp, _i64, C.POINTER(_vp), _i64, _i32, _i32, _vp]),
     "srg_laplacian_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "srg_cheby_filter_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i32, _f64, C.POINTER(_f64), _i32, _i32, _f64,

@@ -297,7 +297,8 @@ namespace srg {
 // defined in norm.cu: fills A~ (pattern, values), degree and the power tables
 int selfloop_fill_dispatch(const int32_t *indptr, const int32_t *indices, const void *data, int val_dtype,
                            int64_t n, const int32_t *at_indptr, int32_t *at_indices, double *at_val,
-                           double *degree, double *dl, double *dr, double r, cudaStream_t s);
+                           double *degree, double *dl, double *dr, double r, const int32_t *flags,
+                           cudaStream_t s);
 }  // namespace srg
 
 extern "C" int srg_sym_norm_csr_general(const int32_t *indptr, const int32_t *indices,
@@ -325,7 +326,7 @@ extern "C" int srg_sym_norm_csr_general(const int32_t *indptr, const int32_t *in
   double *deg = out_degree ? out_degree : dscratch;
   double *dl = dscratch + n, *dr = dscratch + 2 * n;
   double *at_val = dscratch + 3 * n, *vals = at_val + cap;
-  rc = selfloop_fill_dispatch(indptr, indices, data, val_dtype, n, at_indptr, at_indices, at_val, deg, dl, dr, r, s);
+  rc = selfloop_fill_dispatch(indptr, indices, data, val_dtype, n, at_indptr, at_indices, at_val, deg, dl, dr, r, out_flags, s);
   if (!rc) {
     general_norm_vals_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, s>>>(
         at_indptr, at_indices, at_val, deg, n, dl, dr, keys, vals, val_dtype == SRG_VAL_ONES ? 1 : 0);

@@ -34,24 +34,28 @@ template <> struct ValLoad<SRG_VAL_F64> {
   }
 };
 
-// ---- stage 1: row lengths of A~ --------------------------------------------------------------
+constexpr int kWeighted = SRG_FLAG_WEIGHTED;
+
+// ---- stage 1: row lengths of A~ for the rows [row0, row0 + n_rows) of an n_cols-column matrix --
 template <int DT>
 __global__ void __launch_bounds__(256)
-selfloop_rowlen_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
-                       const void *__restrict__ data, long long n, int *__restrict__ rowlen,
-                       int *__restrict__ flags) {
+rows_count_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
+                  const void *__restrict__ data, long long n_rows, long long row0, long long n_cols,
+                  int *__restrict__ rowlen, int *__restrict__ flags) {
   const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n) return;
+  if (a >= n_rows) return;
+  const int ag = (int)(a + row0);
   const int s = indptr[a], e = indptr[a + 1];
   int cnt = 0, prev = -1, fl = 0;
   double diag = 0.0;
   for (int j = s; j < e; ++j) {
     const int b = indices[j];
     if (b <= prev) fl |= SRG_FLAG_UNSORTED;
-    if (b < 0 || b >= n) fl |= SRG_FLAG_BAD_INDEX;
+    if (b < 0 || b >= n_cols) fl |= SRG_FLAG_BAD_INDEX;
     prev = b;
     const double v = ValLoad<DT>::at(data, j);
-    if (b == a)
+    if (DT != SRG_VAL_ONES && v != 1.0) fl |= kWeighted;
+    if (b == ag)
       diag = v;
     else if (v != 0.0)
       ++cnt;
@@ -120,138 +124,183 @@ __device__ double pow_tab(double x, double e) {
   return y;
 }
 
-// ---- stage 2a: write A~ (indices, values), degree and the two power tables ---------------------
+// ---- stage 2a: write A~ (indices, and values when the graph is weighted) and the row degree ------
 template <int DT>
 __global__ void __launch_bounds__(256)
-selfloop_fill_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
-                     const void *__restrict__ data, long long n, const int *__restrict__ out_indptr,
-                     int *__restrict__ out_indices, double *__restrict__ at_val,
-                     double *__restrict__ degree, double *__restrict__ dl, double *__restrict__ dr,
-                     double e_left, double e_right) {
+rows_fill_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
+                 const void *__restrict__ data, long long n_rows, long long row0,
+                 const int *__restrict__ at_indptr, int *__restrict__ at_indices,
+                 double *__restrict__ at_val, double *__restrict__ degree,
+                 const int *__restrict__ flags, int force_vals) {
   const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n) return;
+  if (a >= n_rows) return;
+  const bool weighted = (DT != SRG_VAL_ONES) && (force_vals || (*flags & kWeighted));
+  const int ag = (int)(a + row0);
   const int s = indptr[a], e = indptr[a + 1];
-  const int p0 = out_indptr[a];
+  const int p0 = at_indptr[a];
   int p = p0;
   bool placed = false;
-  double diag_add = 1.0;  // value contributed by I
-  // pass 1: find the diagonal value of A (rows are sorted, so this is a short scan)
   double diag_a = 0.0;
-  for (int j = s; j < e; ++j)
-    if (indices[j] == (int)a) diag_a = ValLoad<DT>::at(data, j);
-  const double diag = __dadd_rn(diag_a, diag_add);
+  if (DT != SRG_VAL_ONES || true) {
+    for (int j = s; j < e; ++j)
+      if (indices[j] == ag) diag_a = ValLoad<DT>::at(data, j);
+  }
+  const double diag = __dadd_rn(diag_a, 1.0);
   for (int j = s; j < e; ++j) {
     const int b = indices[j];
-    if (b == (int)a) continue;
-    if (!placed && b > (int)a) {
+    if (b == ag) continue;
+    if (!placed && b > ag) {
       placed = true;
       if (diag != 0.0) {
-        out_indices[p] = (int)a;
-        if (DT != SRG_VAL_ONES) at_val[p] = diag;
+        at_indices[p] = ag;
+        if (weighted) at_val[p] = diag;
         ++p;
       }
     }
     const double v = ValLoad<DT>::at(data, j);
     if (v != 0.0) {
-      out_indices[p] = b;
-      if (DT != SRG_VAL_ONES) at_val[p] = v;
+      at_indices[p] = b;
+      if (weighted) at_val[p] = v;
       ++p;
     }
   }
   if (!placed && diag != 0.0) {
-    out_indices[p] = (int)a;
-    if (DT != SRG_VAL_ONES) at_val[p] = diag;
+    at_indices[p] = ag;
+    if (weighted) at_val[p] = diag;
     ++p;
   }
   const int len = p - p0;
   double d;
-  if (DT == SRG_VAL_ONES) {
-    // all off-diagonal entries are 1.0, the diagonal is 1.0 or 2.0: exact in any order
-    d = (double)(len - 1) + diag;  // diag is 1.0 or 2.0, never dropped
+  if (!weighted) {
+    d = (double)(len - 1) + diag;  // entries are 1.0, the diagonal 1.0 or 2.0: exact in any order
   } else if (len == 0) {
     d = 0.0;
+  } else if (len == 1) {
+    d = at_val[p0];
   } else {
     d = __dadd_rn(at_val[p0], np_pairwise_sum(at_val + p0 + 1, len - 1));
-    if (len == 1) d = at_val[p0];
   }
   degree[a] = d;
-  dl[a] = pow_tab(d, e_left);
-  dr[a] = pow_tab(d, e_right);
 }
 
-// ---- stage 2b: R[a,b] = (A~[b,a] * dl[a]) * dr[b], symmetric-pattern path ---------------------
-// one warp per row; each lane owns entries p = p0+lane, p0+lane+32, ...
-template <int DT>
 __global__ void __launch_bounds__(256)
-sym_norm_values_kernel(long long n, const int *__restrict__ out_indptr,
-                       const int *__restrict__ out_indices, const double *__restrict__ at_val,
-                       const double *__restrict__ degree, const double *__restrict__ dl,
-                       const double *__restrict__ dr, double one_minus_alpha, double alpha,
-                       int use_ppr,
-                       double *__restrict__ val64, float *__restrict__ val32,
-                       int *__restrict__ flags) {
+pow_tables_kernel(const double *__restrict__ degree, long long n, double e_left, double e_right,
+                  double *__restrict__ dl, double *__restrict__ dr) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double d = degree[i];
+  dl[i] = pow_tab(d, e_left);
+  dr[i] = pow_tab(d, e_right);
+}
+
+__device__ __forceinline__ int ld_idx_64(const int *p) {
+  int v;
+  asm volatile("ld.global.nc.L2::64B.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// ---- stage 2b: R[a,b] = (A~[b,a] * dl[a]) * dr[b] on a symmetric A~ -------------------------------
+// For a symmetric matrix A~[b,a] = A~[a,b], so every value comes from the row itself.  Symmetry is
+// VERIFIED, not assumed (check_sym): every upper entry (b > a) must find its mirror (b,a) with the
+// same value (binary search in row b), and the number of upper and lower entries must agree; the
+// mirror map is injective, so together these prove pattern and value symmetry.  One warp per row.
+__global__ void __launch_bounds__(256)
+rows_values_kernel(long long n_rows, long long row0, const int *__restrict__ at_indptr,
+                   const int *__restrict__ at_indices, const double *__restrict__ at_val,
+                   const double *__restrict__ degree, const double *__restrict__ dl,
+                   const double *__restrict__ dr, double one_minus_alpha, double alpha, int use_ppr,
+                   int check_sym, double *__restrict__ val64, float *__restrict__ val32,
+                   int *__restrict__ flags, unsigned long long *__restrict__ tri_counts) {
   const long long a = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (a >= n) return;
+  if (a >= n_rows) return;
+  const bool weighted = (*flags & kWeighted) != 0;
   const int lane = threadIdx.x & 31;
-  const int p0 = out_indptr[a], p1 = out_indptr[a + 1];
-  const double dla = dl[a];
-  int fl = 0;
+  const int ag = (int)(a + row0);
+  const int p0 = at_indptr[a], p1 = at_indptr[a + 1];
+  const double dla = dl[ag];
+  const double diag_unw = weighted ? 0.0 : degree[a] - (double)(p1 - p0 - 1);
+  int fl = 0, n_up = 0, n_lo = 0;
   for (int p = p0 + lane; p < p1; p += 32) {
-    const int b = out_indices[p];
-    double vt;  // A~[b,a]
-    if (b == (int)a) {
-      vt = (DT == SRG_VAL_ONES) ? 0.0 : at_val[p];
-    } else {
-      // binary search for column a in row b
-      int lo = out_indptr[b], hi = out_indptr[b + 1];
-      int q = -1;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        const int c = out_indices[mid];
-        if (c == (int)a) {
-          q = mid;
-          break;
+    const int b = at_indices[p];
+    const double vt = weighted ? at_val[p] : (b == ag ? diag_unw : 1.0);
+    if (check_sym && b != ag) {
+      if (b > ag) {
+        ++n_up;
+        int lo = at_indptr[b], hi = at_indptr[b + 1];
+        int q = -1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          const int c = ld_idx_64(at_indices + mid);
+          if (c == ag) {
+            q = mid;
+            break;
+          }
+          if (c < ag)
+            lo = mid + 1;
+          else
+            hi = mid;
         }
-        if (c < (int)a)
-          lo = mid + 1;
-        else
-          hi = mid;
-      }
-      if (q < 0) {
-        fl |= SRG_FLAG_ASYMMETRIC;
-        vt = 0.0;
+        if (q < 0 || (weighted && at_val[q] != vt)) fl |= SRG_FLAG_ASYMMETRIC;
       } else {
-        vt = (DT == SRG_VAL_ONES) ? 1.0 : at_val[q];
+        ++n_lo;
       }
-    }
-    if (DT == SRG_VAL_ONES && b == (int)a) {
-      // diagonal of an unweighted graph: 1.0 from I, 2.0 when A already had the loop.
-      // degree = (#off-diagonal) + diag  =>  diag = degree - (len - 1), exact small integers.
-      vt = degree[a] - (double)(p1 - p0 - 1);
     }
     double v = __dmul_rn(__dmul_rn(vt, dla), dr[b]);
     if (use_ppr) {
       v = __dmul_rn(one_minus_alpha, v);
-      if (b == (int)a) v = __dadd_rn(v, alpha);
+      if (b == ag) v = __dadd_rn(v, alpha);
     }
     if (v == 0.0) fl |= SRG_FLAG_ZERO_PRODUCT;
     if (val64) val64[p] = v;
     if (val32) val32[p] = __double2float_rn(v);
   }
+  if (check_sym) {
+    n_up = __reduce_add_sync(0xffffffffu, n_up);
+    n_lo = __reduce_add_sync(0xffffffffu, n_lo);
+    if (lane == 0 && (n_up | n_lo)) {
+      if (n_up) atomicAdd(tri_counts, (unsigned long long)n_up);
+      if (n_lo) atomicAdd(tri_counts + 1, (unsigned long long)n_lo);
+    }
+  }
   if (fl) atomicOr(flags, fl);
 }
 
-// used by the general (transpose) path in coo.cu
+__global__ void tri_compare_kernel(const unsigned long long *tri_counts, int *flags) {
+  if (tri_counts[0] != tri_counts[1]) atomicOr(flags, SRG_FLAG_ASYMMETRIC);
+}
+
+#define SRG_DT_SWITCH(dt, CALL)                       \
+  switch (dt) {                                       \
+    case SRG_VAL_ONES: { constexpr int DTT = SRG_VAL_ONES; CALL; } break; \
+    case SRG_VAL_F32: { constexpr int DTT = SRG_VAL_F32; CALL; } break;   \
+    default: { constexpr int DTT = SRG_VAL_F64; CALL; } break;            \
+  }
+
+int rows_count_launch(const int32_t *indptr, const int32_t *indices, const void *data, int dt, int64_t n_rows,
+                      int64_t row0, int64_t n_cols, int32_t *rowlen, int32_t *flags, cudaStream_t s) {
+  const unsigned blocks = (unsigned)ceil_div64(n_rows, 256);
+  SRG_DT_SWITCH(dt, (rows_count_kernel<DTT><<<blocks, 256, 0, s>>>(indptr, indices, data, n_rows, row0, n_cols, rowlen, flags)));
+  SRG_LAUNCHED();
+  return SRG_OK;
+}
+
+int rows_fill_launch(const int32_t *indptr, const int32_t *indices, const void *data, int dt, int64_t n_rows,
+                     int64_t row0, const int32_t *at_indptr, int32_t *at_indices, double *at_val,
+                     double *degree, const int32_t *flags, int force_vals, cudaStream_t s) {
+  const unsigned blocks = (unsigned)ceil_div64(n_rows, 256);
+  SRG_DT_SWITCH(dt, (rows_fill_kernel<DTT><<<blocks, 256, 0, s>>>(indptr, indices, data, n_rows, row0, at_indptr, at_indices, at_val, degree, flags, force_vals)));
+  SRG_LAUNCHED();
+  return SRG_OK;
+}
+
+// used by the general (transpose) path in coo.cu: A~ with explicit values, degree, power tables
 int selfloop_fill_dispatch(const int32_t *indptr, const int32_t *indices, const void *data, int val_dtype,
                            int64_t n, const int32_t *at_indptr, int32_t *at_indices, double *at_val,
-                           double *degree, double *dl, double *dr, double r, cudaStream_t s) {
-  const unsigned blocks = (unsigned)ceil_div64(n, 256);
-  if (val_dtype == SRG_VAL_ONES)
-    selfloop_fill_kernel<SRG_VAL_ONES><<<blocks, 256, 0, s>>>(indptr, indices, data, n, at_indptr, at_indices, at_val, degree, dl, dr, r - 1.0, -r);
-  else if (val_dtype == SRG_VAL_F32)
-    selfloop_fill_kernel<SRG_VAL_F32><<<blocks, 256, 0, s>>>(indptr, indices, data, n, at_indptr, at_indices, at_val, degree, dl, dr, r - 1.0, -r);
-  else
-    selfloop_fill_kernel<SRG_VAL_F64><<<blocks, 256, 0, s>>>(indptr, indices, data, n, at_indptr, at_indices, at_val, degree, dl, dr, r - 1.0, -r);
+                           double *degree, double *dl, double *dr, double r, const int32_t *flags,
+                           cudaStream_t s) {
+  int rc = rows_fill_launch(indptr, indices, data, val_dtype, n, 0, at_indptr, at_indices, at_val, degree, flags, 1, s);
+  if (rc) return rc;
+  pow_tables_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(degree, n, r - 1.0, -r, dl, dr);
   SRG_LAUNCHED();
   return SRG_OK;
 }
@@ -260,71 +309,106 @@ int selfloop_fill_dispatch(const int32_t *indptr, const int32_t *indices, const 
 
 using namespace srg;
 
-extern "C" int srg_degree_selfloop_csr(const int32_t *indptr, const int32_t *indices,
-                                       const void *data, int val_dtype, int64_t n,
-                                       int32_t *out_indptr, int32_t *out_count,
-                                       int32_t *out_flags, void *stream) {
+static int check_rows_args(const char *who, const int32_t *indptr, const int32_t *indices, const void *data,
+                           int val_dtype, int64_t n_rows, int64_t row0, int64_t n_cols) {
+  SRG_REQUIRE(n_rows >= 0 && row0 >= 0 && n_cols >= 0 && row0 + n_rows <= n_cols,
+              "%s: bad row range (n_rows=%lld row0=%lld n_cols=%lld)", who, (long long)n_rows, (long long)row0, (long long)n_cols);
+  SRG_REQUIRE(n_cols <= 2147483647LL, "%s: more than 2^31-1 columns", who);
+  SRG_REQUIRE(val_dtype >= 0 && val_dtype <= 2, "%s: bad val_dtype %d", who, val_dtype);
+  SRG_REQUIRE(n_rows == 0 || indptr, "%s: indptr is NULL", who);
+  (void)indices; (void)data;
+  return SRG_OK;
+}
+
+extern "C" int srg_selfloop_rows_csr(const int32_t *indptr, const int32_t *indices, const void *data,
+                                     int val_dtype, int64_t n_rows, int64_t row0, int64_t n_cols,
+                                     int32_t *out_indptr, int32_t *out_count, int32_t *out_flags,
+                                     void *stream) {
   int rc = require_device();
   if (rc) return rc;
-  SRG_REQUIRE(n >= 0, "degree_selfloop: negative n");
-  SRG_REQUIRE(indptr && out_indptr && out_flags, "degree_selfloop: NULL pointer");
-  SRG_REQUIRE(val_dtype >= 0 && val_dtype <= 2, "degree_selfloop: bad val_dtype %d", val_dtype);
-  SRG_REQUIRE(val_dtype == SRG_VAL_ONES || data != nullptr,
-              "degree_selfloop: data is NULL but val_dtype says values");
+  if ((rc = check_rows_args("selfloop_rows", indptr, indices, data, val_dtype, n_rows, row0, n_cols))) return rc;
+  SRG_REQUIRE(out_indptr && out_flags, "selfloop_rows: NULL pointer");
   cudaStream_t s = as_stream(stream);
-  if (n == 0) {
+  if (n_rows == 0) {
     SRG_CUDA(cudaMemsetAsync(out_indptr, 0, sizeof(int), s));
     return SRG_OK;
   }
-  SRG_REQUIRE(indices != nullptr, "degree_selfloop: indices is NULL");
+  SRG_REQUIRE(indices != nullptr, "selfloop_rows: indices is NULL");
+  SRG_REQUIRE(val_dtype == SRG_VAL_ONES || data != nullptr, "selfloop_rows: data is NULL but val_dtype says values");
   int *scratch = nullptr;
-  const int64_t scratch_ints = (out_count ? 0 : n) + scan_scratch_ints(n);
+  const int64_t scratch_ints = (out_count ? 0 : n_rows) + scan_scratch_ints(n_rows);
   SRG_CUDA(cudaMallocAsync(&scratch, scratch_ints * sizeof(int), s));
-  int *rowlen = out_count ? out_count : scratch + scan_scratch_ints(n);
-  const int64_t blocks = ceil_div64(n, 256);
-  switch (val_dtype) {
-    case SRG_VAL_ONES:
-      selfloop_rowlen_kernel<SRG_VAL_ONES><<<(unsigned)blocks, 256, 0, s>>>(indptr, indices, data, n, rowlen, out_flags);
-      break;
-    case SRG_VAL_F32:
-      selfloop_rowlen_kernel<SRG_VAL_F32><<<(unsigned)blocks, 256, 0, s>>>(indptr, indices, data, n, rowlen, out_flags);
-      break;
-    default:
-      selfloop_rowlen_kernel<SRG_VAL_F64><<<(unsigned)blocks, 256, 0, s>>>(indptr, indices, data, n, rowlen, out_flags);
-      break;
-  }
-  SRG_LAUNCHED();
-  rc = exclusive_scan_i32(rowlen, n, out_indptr, scratch, s);
+  int *rowlen = out_count ? out_count : scratch + scan_scratch_ints(n_rows);
+  rc = rows_count_launch(indptr, indices, data, val_dtype, n_rows, row0, n_cols, rowlen, out_flags, s);
+  if (!rc) rc = exclusive_scan_i32(rowlen, n_rows, out_indptr, scratch, s);
   cudaFreeAsync(scratch, s);
   return rc;
 }
 
-template <int DT>
-static int sym_norm_typed(const int32_t *indptr, const int32_t *indices, const void *data, int64_t n,
-                          int64_t nnz, const int32_t *out_indptr, double r, double ppr_alpha,
-                          int32_t *out_indices, double *out_degree, double *out_val_f64,
-                          float *out_val_f32, int32_t *out_flags, cudaStream_t s) {
-  // scratch: dl, dr (n doubles each) [+ degree if the caller does not want it] [+ A~ values]
-  const int64_t cap = nnz + n;
-  const int64_t n_doubles = 2 * n + (out_degree ? 0 : n) + (DT == SRG_VAL_ONES ? 0 : cap);
-  double *scratch = nullptr;
-  SRG_CUDA(cudaMallocAsync(&scratch, (size_t)n_doubles * sizeof(double), s));
-  double *dl = scratch, *dr = scratch + n;
-  double *deg = out_degree ? out_degree : scratch + 2 * n;
-  double *at_val = (DT == SRG_VAL_ONES) ? nullptr : scratch + 2 * n + (out_degree ? 0 : n);
-  const int64_t blocks = ceil_div64(n, 256);
-  selfloop_fill_kernel<DT><<<(unsigned)blocks, 256, 0, s>>>(indptr, indices, data, n, out_indptr,
-                                                            out_indices, at_val, deg, dl, dr,
-                                                            r - 1.0, -r);
+extern "C" int srg_degree_selfloop_csr(const int32_t *indptr, const int32_t *indices,
+                                       const void *data, int val_dtype, int64_t n,
+                                       int32_t *out_indptr, int32_t *out_count,
+                                       int32_t *out_flags, void *stream) {
+  return srg_selfloop_rows_csr(indptr, indices, data, val_dtype, n, 0, n, out_indptr, out_count, out_flags, stream);
+}
+
+extern "C" int srg_selfloop_fill_rows_csr(const int32_t *indptr, const int32_t *indices,
+                                          const void *data, int val_dtype, int64_t n_rows,
+                                          int64_t row0, int64_t n_cols, const int32_t *at_indptr,
+                                          int32_t *at_indices, double *at_val, double *out_degree,
+                                          const int32_t *flags, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_rows_args("selfloop_fill_rows", indptr, indices, data, val_dtype, n_rows, row0, n_cols))) return rc;
+  if (n_rows == 0) return SRG_OK;
+  SRG_REQUIRE(indices && at_indptr && at_indices && out_degree && flags, "selfloop_fill_rows: NULL pointer");
+  SRG_REQUIRE(val_dtype == SRG_VAL_ONES || (data && at_val), "selfloop_fill_rows: weighted input needs data and at_val");
+  return rows_fill_launch(indptr, indices, data, val_dtype, n_rows, row0, at_indptr, at_indices, at_val, out_degree,
+                          flags, 0, as_stream(stream));
+}
+
+extern "C" int srg_pow_tables_f64(const double *degree, int64_t n, double r, double *out_left,
+                                  double *out_right, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n >= 0, "pow_tables: negative n");
+  if (n == 0) return SRG_OK;
+  SRG_REQUIRE(degree && out_left && out_right, "pow_tables: NULL pointer");
+  pow_tables_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(degree, n, r - 1.0, -r, out_left, out_right);
   SRG_LAUNCHED();
-  const int use_ppr = ppr_alpha >= 0.0 ? 1 : 0;
-  const int64_t wblocks = ceil_div64(n * 32, 256);
-  SRG_REQUIRE(wblocks <= 2147483647LL, "sym_norm: too many rows");
-  sym_norm_values_kernel<DT><<<(unsigned)wblocks, 256, 0, s>>>(
-      n, out_indptr, out_indices, at_val, deg, dl, dr, 1.0 - ppr_alpha, ppr_alpha, use_ppr,
-      out_val_f64, out_val_f32, out_flags);
+  return SRG_OK;
+}
+
+extern "C" int srg_norm_values_rows_csr(const int32_t *at_indptr, const int32_t *at_indices,
+                                        const double *at_val, const double *degree_rows,
+                                        int64_t n_rows, int64_t row0, const double *pow_left,
+                                        const double *pow_right, double ppr_alpha, int check_symmetry,
+                                        double *out_val_f64, float *out_val_f32, int32_t *flags,
+                                        void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n_rows >= 0 && row0 >= 0, "norm_values_rows: bad row range");
+  if (n_rows == 0) return SRG_OK;
+  SRG_REQUIRE(at_indptr && at_indices && degree_rows && pow_left && pow_right && flags, "norm_values_rows: NULL pointer");
+  SRG_REQUIRE(!check_symmetry || row0 == 0, "norm_values_rows: the symmetry check needs every row on this device");
+  cudaStream_t s = as_stream(stream);
+  unsigned long long *tri = nullptr;
+  if (check_symmetry) {
+    SRG_CUDA(cudaMallocAsync(&tri, 2 * sizeof(unsigned long long), s));
+    SRG_CUDA(cudaMemsetAsync(tri, 0, 2 * sizeof(unsigned long long), s));
+  }
+  const int64_t wblocks = ceil_div64(n_rows * 32, 256);
+  SRG_REQUIRE(wblocks <= 2147483647LL, "norm_values_rows: too many rows");
+  rows_values_kernel<<<(unsigned)wblocks, 256, 0, s>>>(n_rows, row0, at_indptr, at_indices, at_val, degree_rows,
+                                                       pow_left, pow_right, 1.0 - ppr_alpha, ppr_alpha,
+                                                       ppr_alpha >= 0.0 ? 1 : 0, check_symmetry, out_val_f64,
+                                                       out_val_f32, flags, tri);
   SRG_LAUNCHED();
-  cudaFreeAsync(scratch, s);
+  if (check_symmetry) {
+    tri_compare_kernel<<<1, 1, 0, s>>>(tri, flags);
+    SRG_LAUNCHED();
+    cudaFreeAsync(tri, s);
+  }
   return SRG_OK;
 }
 
@@ -342,12 +426,19 @@ extern "C" int srg_sym_norm_csr(const int32_t *indptr, const int32_t *indices, c
   SRG_REQUIRE(val_dtype == SRG_VAL_ONES || data != nullptr, "sym_norm: data is NULL but val_dtype says values");
   SRG_REQUIRE(nnz + n <= 2147483647LL, "sym_norm: nnz + n exceeds the int32 CSR range");
   cudaStream_t s = as_stream(stream);
-  switch (val_dtype) {
-    case SRG_VAL_ONES:
-      return sym_norm_typed<SRG_VAL_ONES>(indptr, indices, data, n, nnz, out_indptr, r, ppr_alpha, out_indices, out_degree, out_val_f64, out_val_f32, out_flags, s);
-    case SRG_VAL_F32:
-      return sym_norm_typed<SRG_VAL_F32>(indptr, indices, data, n, nnz, out_indptr, r, ppr_alpha, out_indices, out_degree, out_val_f64, out_val_f32, out_flags, s);
-    default:
-      return sym_norm_typed<SRG_VAL_F64>(indptr, indices, data, n, nnz, out_indptr, r, ppr_alpha, out_indices, out_degree, out_val_f64, out_val_f32, out_flags, s);
-  }
+  // scratch: dl, dr (n doubles each) [+ degree] [+ A~ values when the dtype can carry weights]
+  const int64_t cap = nnz + n;
+  const int64_t n_doubles = 2 * n + (out_degree ? 0 : n) + (val_dtype == SRG_VAL_ONES ? 0 : cap);
+  double *scratch = nullptr;
+  SRG_CUDA(cudaMallocAsync(&scratch, (size_t)n_doubles * sizeof(double), s));
+  double *dl = scratch, *dr = scratch + n;
+  double *deg = out_degree ? out_degree : scratch + 2 * n;
+  double *at_val = (val_dtype == SRG_VAL_ONES) ? nullptr : scratch + 2 * n + (out_degree ? 0 : n);
+  rc = rows_fill_launch(indptr, indices, data, val_dtype, n, 0, out_indptr, out_indices, at_val, deg, out_flags, 0, s);
+  if (!rc) rc = srg_pow_tables_f64(deg, n, r, dl, dr, s);
+  if (!rc)
+    rc = srg_norm_values_rows_csr(out_indptr, out_indices, at_val, deg, n, 0, dl, dr, ppr_alpha, 1, out_val_f64,
+                                  out_val_f32, out_flags, s);
+  cudaFreeAsync(scratch, s);
+  return rc;
 }

@@ -15,6 +15,7 @@
 //     kernel is sized for occupancy and bytes in flight, not for tensor cores.
 //
 // Long rows: handled by the split kernels further down (fixed-order partial sums, deterministic).
+#include <cstring>
 #include <string>
 
 #include "common.cuh"
@@ -294,11 +295,22 @@ __device__ __forceinline__ float4 lds_f4(unsigned smem_addr) {
   return v;
 }
 
-template <int B, bool L2_64>
+// PUSH: the row-partitioned multi-GPU hop.  Instead of one Y, every finished row is stored into the
+// next-hop feature buffer of EVERY rank (peer pointers mapped over NVLink, own buffer included) at
+// its global row index, so the all-gather of the next hop happens inside this kernel's epilogue and
+// overlaps the gathers of the rows still in flight.
+constexpr int kMaxPeers = 8;
+struct PeerDests {
+  float4 *p[kMaxPeers];
+  int count;
+};
+
+template <int B, bool L2_64, bool PUSH>
 __global__ void __launch_bounds__(kStreamWarps * 32)
 spmm_stream2_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
                     const float *__restrict__ vals, long long n_rows, const float4 *__restrict__ X,
-                    unsigned ldx, float4 *__restrict__ Y, long long ldy, int nvec, int chunks, int R) {
+                    unsigned ldx, float4 *__restrict__ Y, long long ldy, int nvec, int chunks, int R,
+                    PeerDests peers) {
   constexpr int S = 2 * B;
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ float4 smem4[];
@@ -338,7 +350,13 @@ spmm_stream2_kernel(const int *__restrict__ indptr, const int *__restrict__ indi
           acc.w = fmaf(v, x.w, acc.w);
         }
       }
-      if (active) yrow[(long long)r * ldy] = acc;
+      if (active) {
+        if (PUSH) {
+          for (int d = 0; d < peers.count; ++d) (peers.p[d] + (yrow - Y))[(long long)r * ldy] = acc;
+        } else {
+          yrow[(long long)r * ldy] = acc;
+        }
+      }
     }
     return;
   }
@@ -394,7 +412,16 @@ spmm_stream2_kernel(const int *__restrict__ indptr, const int *__restrict__ indi
             acc.w = fmaf(v, x.w, acc.w);
           }
           if ((((j < 0) ? prev_mask : endmask) >> jj) & 1u) {
-            if (active) *yrow = acc;
+            if (active) {
+              if (PUSH) {
+                const long long off = yrow - Y;
+#pragma unroll
+                for (int d = 0; d < kMaxPeers; ++d)
+                  if (d < peers.count) peers.p[d][off] = acc;
+              } else {
+                *yrow = acc;
+              }
+            }
             yrow += ldy;
             acc = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -445,10 +472,10 @@ static int launch_stream(const int *indptr, const int *indices, const float *val
   return SRG_OK;
 }
 
-template <int B, bool L2_64>
+template <int B, bool L2_64, bool PUSH = false>
 static int launch_stream2(const int *indptr, const int *indices, const float *vals, int64_t n_rows,
                           const float4 *X, int64_t ldx, float4 *Y, int64_t ldy, int nvec,
-                          cudaStream_t s) {
+                          cudaStream_t s, const PeerDests *peers = nullptr) {
   const int R = g_stream_rows < 1 ? 1 : (g_stream_rows > 32 ? 32 : g_stream_rows);
   const int chunks = (nvec + 31) / 32;
   const int64_t tasks = ceil_div64(n_rows, R) * chunks;
@@ -458,9 +485,13 @@ static int launch_stream2(const int *indptr, const int *indices, const float *va
     return SRG_ERR_RANGE;
   }
   const size_t smem = (size_t)kStreamWarps * (2 * B) * 32 * sizeof(float4);
-  SRG_CUDA(cudaFuncSetAttribute(spmm_stream2_kernel<B, L2_64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  spmm_stream2_kernel<B, L2_64><<<(unsigned)blocks, kStreamWarps * 32, smem, s>>>(
-      indptr, indices, vals, n_rows, X, (unsigned)ldx, Y, ldy, nvec, chunks, R);
+  PeerDests pd;
+  pd.count = 0;
+  for (int d = 0; d < kMaxPeers; ++d) pd.p[d] = nullptr;
+  if (peers) pd = *peers;
+  SRG_CUDA(cudaFuncSetAttribute(spmm_stream2_kernel<B, L2_64, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  spmm_stream2_kernel<B, L2_64, PUSH><<<(unsigned)blocks, kStreamWarps * 32, smem, s>>>(
+      indptr, indices, vals, n_rows, X, (unsigned)ldx, Y, ldy, nvec, chunks, R, pd);
   SRG_LAUNCHED();
   return SRG_OK;
 }
@@ -619,4 +650,67 @@ extern "C" int srg_apply_feature_mask_f32(const float *x, int64_t ld_x, const in
                                           int64_t ld_out, int64_t n, int32_t F, void *stream) {
   SRG_REQUIRE(mask != nullptr, "apply_feature_mask: mask is NULL");
   return srg_pack_features_f32(x, ld_x, out, ld_out, n, F, mask, stream);
+}
+
+// ---- multi-GPU push hop -------------------------------------------------------------------------------
+extern "C" int srg_spmm_csr_f32_push(const int32_t *indptr, const int32_t *indices, const float *vals,
+                                     int64_t n_rows, const float *X, int64_t ldx, float *const *dests,
+                                     int32_t n_dests, int64_t dest_row0, int64_t ldy, int32_t F,
+                                     void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n_rows >= 0 && F >= 0 && dest_row0 >= 0, "spmm_push: negative size");
+  SRG_REQUIRE(n_dests >= 1 && n_dests <= kMaxPeers, "spmm_push: n_dests must be 1..%d", kMaxPeers);
+  if (n_rows == 0 || F == 0) return SRG_OK;
+  SRG_REQUIRE(indptr && indices && vals && X && dests, "spmm_push: NULL pointer");
+  SRG_REQUIRE(ldx >= F && ldy >= F && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)X % 16 == 0,
+              "spmm_push: needs ld %% 4 == 0 and 16-byte aligned matrices");
+  const int nvec = (F + 3) / 4;
+  PeerDests pd;
+  pd.count = n_dests;
+  for (int d = 0; d < kMaxPeers; ++d) pd.p[d] = nullptr;
+  for (int d = 0; d < n_dests; ++d) {
+    SRG_REQUIRE(dests[d] && (uintptr_t)dests[d] % 16 == 0, "spmm_push: dests[%d] NULL or unaligned", d);
+    SRG_REQUIRE((const float *)dests[d] != X, "spmm_push: destination aliases the input");
+    pd.p[d] = reinterpret_cast<float4 *>(dests[d]) + dest_row0 * (ldy / 4);
+  }
+  // Y is only the origin the kernel measures row offsets from
+  float4 *origin = pd.p[0];
+  if (g_gather_l2_64)
+    return launch_stream2<4, true, true>(indptr, indices, vals, n_rows, reinterpret_cast<const float4 *>(X), ldx / 4,
+                                         origin, ldy / 4, nvec, as_stream(stream), &pd);
+  return launch_stream2<4, false, true>(indptr, indices, vals, n_rows, reinterpret_cast<const float4 *>(X), ldx / 4,
+                                        origin, ldy / 4, nvec, as_stream(stream), &pd);
+}
+
+// ---- peer-mapped buffers (CUDA IPC) for the push hop ---------------------------------------------------
+extern "C" int srg_ipc_alloc(void **ptr, int64_t bytes) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(ptr && bytes > 0, "ipc_alloc: bad arguments");
+  SRG_CUDA(cudaMalloc(ptr, (size_t)bytes));
+  return SRG_OK;
+}
+extern "C" int srg_ipc_free(void *ptr) {
+  if (ptr) SRG_CUDA(cudaFree(ptr));
+  return SRG_OK;
+}
+extern "C" int srg_ipc_get_handle(void *ptr, void *handle64) {
+  SRG_REQUIRE(ptr && handle64, "ipc_get_handle: NULL pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  SRG_CUDA(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, 64);
+  return SRG_OK;
+}
+extern "C" int srg_ipc_open(const void *handle64, void **ptr) {
+  SRG_REQUIRE(ptr && handle64, "ipc_open: NULL pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  SRG_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return SRG_OK;
+}
+extern "C" int srg_ipc_close(void *ptr) {
+  if (ptr) SRG_CUDA(cudaIpcCloseMemHandle(ptr));
+  return SRG_OK;
 }

@@ -1,0 +1,258 @@
+"""Row-partitioned multi-GPU propagation: one process per GPU, one exchange per hop.
+
+The reference has no multi-GPU code; this is the scheme SURVEY.md §8e defines:
+
+  * partition map: contiguous equal row blocks, ``rows_per = ceil(N / P)``, rank p owns
+    ``[p*rows_per, min(N, (p+1)*rows_per))``; column ids stay global.
+  * normalisation: stage 1/2a on the local rows, ONE all-gather of the degree vector (N x 8 B),
+    power tables and values locally (``srg_*_rows_csr``).  Symmetry of the adjacency is the
+    caller's promise here (the mirror rows live on other ranks).
+  * hop k: every rank needs all of X_{k-1}.  Two exchange modes:
+      - ``"allgather"``: NCCL all-gather of the slices (torch.distributed), then the local SpMM;
+      - ``"push"``: the SpMM epilogue stores every finished row into the next-hop buffer of every
+        rank over NVLink peer mappings (CUDA IPC), one stream-ordered tiny all-reduce orders the
+        hops across ranks.  No separate all-gather kernel runs.
+  * every output row is owned by one rank and reduced in CSR order => bitwise equal to 1 GPU.
+
+The orchestration is written against a small ``ops`` object so the CPU test-suite can drive the
+same code over gloo with the oracle as the local hop (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+__all__ = ["row_partition", "shard_rows", "propagate_sharded", "DeviceOps", "DistState", "dist_sym_norm"]
+
+
+def row_partition(n: int, world: int):
+    """(rows_per, starts[world+1]) of the contiguous equal-block partition."""
+    rows_per = -(-int(n) // int(world)) if n > 0 else 0
+    starts = np.minimum(np.arange(world + 1, dtype=np.int64) * rows_per, n)
+    return rows_per, starts
+
+
+def shard_rows(adj: sp.csr_matrix, start: int, end: int) -> sp.csr_matrix:
+    """Rows [start, end) of a CSR with GLOBAL column ids (shape (end-start) x N)."""
+    lo, hi = int(adj.indptr[start]), int(adj.indptr[end])
+    indptr = (adj.indptr[start:end + 1] - adj.indptr[start]).astype(np.int32)
+    return sp.csr_matrix((adj.data[lo:hi], adj.indices[lo:hi], indptr), shape=(end - start, adj.shape[1]), copy=False)
+
+
+def propagate_sharded(ops, local_norm, x_local, k, rows_per, world):
+    """K hops over this rank's rows.  ``ops`` provides:
+         ops.new_full()                 -> buffer holding all world*rows_per rows
+         ops.local_view(full)           -> this rank's slice of a full buffer (rows_per rows)
+         ops.load_local(full, x_local)  -> copy the rank's input rows into its slice
+         ops.exchange(full)             -> make every rank's slice visible in `full` on all ranks
+         ops.hop(local_norm, full_in, full_out) -> write this rank's rows of A^ X into full_out
+                                           (push mode: into every rank's full_out, then ops.exchange
+                                            only synchronises)
+         ops.snapshot_local(full)       -> the rank's rows as an independent array/tensor
+    Returns [hop_0_local, ..., hop_k_local]."""
+    cur, nxt = ops.new_full(), ops.new_full()
+    ops.load_local(cur, x_local)
+    ops.exchange(cur)
+    out = [ops.snapshot_local(cur)]
+    for _ in range(k):
+        ops.hop(local_norm, cur, nxt)
+        ops.exchange(nxt)
+        out.append(ops.snapshot_local(nxt))
+        cur, nxt = nxt, cur
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# device implementation
+# ------------------------------------------------------------------------------------------------
+class DistState:
+    """Per-rank device state: partition, the two full feature buffers (peer-mapped in push mode)."""
+
+    def __init__(self, n, f, world, rank, mode="push", group=None, device=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+        from .device import pad_ld
+        self.torch, self.dist, self._lib = torch, dist, _lib
+        self.lib = _lib.load()
+        self.n, self.f, self.world, self.rank, self.mode, self.group = n, f, world, rank, mode, group
+        self.rows_per, self.starts = row_partition(n, world)
+        self.row0 = int(self.starts[rank])
+        self.n_local = int(self.starts[rank + 1] - self.starts[rank])
+        self.ld = pad_ld(f)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.n_pad = self.rows_per * world
+        self._raw = []          # (ptr) owned IPC allocations
+        self._opened = []       # peer mappings
+        self.full = []          # torch views of the two local full buffers
+        self.peer_ptrs = []     # per buffer: list of world device pointers (index = rank)
+        self._tick = torch.zeros(1, dtype=torch.int32, device=self.device)
+        nbytes = self.n_pad * self.ld * 4
+        for _ in range(2):
+            if mode == "push" and world > 1:
+                p = C.c_void_p()
+                _lib.check(self.lib.srg_ipc_alloc(C.byref(p), max(nbytes, 256)))
+                self._raw.append(p)
+                t = self._wrap(p.value, nbytes)
+            else:
+                t = torch.zeros((self.n_pad, self.ld), dtype=torch.float32, device=self.device)
+            self.full.append(t)
+        if mode == "push" and world > 1:
+            for b in range(2):
+                self.full[b].zero_()
+            torch.cuda.synchronize()
+            for b in range(2):
+                h = (C.c_ubyte * 64)()
+                _lib.check(self.lib.srg_ipc_get_handle(self._raw[b], h))
+                handles = [None] * world
+                dist.all_gather_object(handles, bytes(h), group=group)
+                ptrs = []
+                for r in range(world):
+                    if r == rank:
+                        ptrs.append(self._raw[b].value)
+                    else:
+                        q = C.c_void_p()
+                        hb = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                        _lib.check(self.lib.srg_ipc_open(hb, C.byref(q)))
+                        self._opened.append(q)
+                        ptrs.append(q.value)
+                self.peer_ptrs.append(ptrs)
+
+    def _wrap(self, ptr, nbytes):
+        """torch view over a raw device allocation (no ownership)."""
+        torch = self.torch
+
+        class _Holder:
+            pass
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": (self.n_pad, self.ld), "typestr": "<f4", "data": (int(ptr), False),
+                                      "version": 2, "strides": None}
+        return torch.as_tensor(h, device=self.device)
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1 and self.dist.is_initialized():
+            self.dist.barrier(group=self.group)
+        for q in self._opened:
+            self.lib.srg_ipc_close(q)
+        self.full = []
+        for p in self._raw:
+            self.lib.srg_ipc_free(p)
+        self._opened, self._raw = [], []
+
+
+class DeviceOps:
+    """``ops`` for propagate_sharded on the GPU."""
+
+    def __init__(self, st: DistState):
+        self.st = st
+        self._next = 0
+
+    def new_full(self):
+        i = self._next
+        self._next += 1
+        assert i < 2, "two full buffers ping-pong"
+        return i
+
+    def local_view(self, i):
+        st = self.st
+        return st.full[i][st.row0:st.row0 + st.rows_per] if st.n_local == st.rows_per else \
+            st.full[i][st.rank * st.rows_per:(st.rank + 1) * st.rows_per]
+
+    def load_local(self, i, x_local_padded):
+        st = self.st
+        st.full[i][st.row0:st.row0 + st.n_local].copy_(x_local_padded)
+
+    def exchange(self, i, pushed=False):
+        st = self.st
+        if st.world == 1:
+            return
+        if pushed:
+            # rows are already in every peer's buffer: order the hops across ranks on the stream
+            st.dist.all_reduce(st._tick, group=st.group)
+        else:
+            view = st.full[i][st.rank * st.rows_per:(st.rank + 1) * st.rows_per]
+            st.dist.all_gather_into_tensor(st.full[i], view, group=st.group)
+
+    def hop(self, local_norm, i_in, i_out):
+        from . import _lib
+        from .device import _p, _stream_ptr
+        st = self.st
+        xin = st.full[i_in]
+        if st.mode == "push" and st.world > 1:
+            dests = (C.c_void_p * st.world)(*st.peer_ptrs[i_out])
+            _lib.check(st.lib.srg_spmm_csr_f32_push(_p(local_norm.indptr), _p(local_norm.indices), _p(local_norm.data),
+                                                    st.n_local, _p(xin), st.ld, dests, st.world, st.row0, st.ld, st.f,
+                                                    _stream_ptr(st.device)))
+            self._pushed = True
+        else:
+            out = st.full[i_out][st.row0:st.row0 + st.n_local]
+            _lib.check(st.lib.srg_spmm_csr_f32(_p(local_norm.indptr), _p(local_norm.indices), _p(local_norm.data),
+                                               st.n_local, _p(xin), st.ld, _p(out), st.ld, st.f, _stream_ptr(st.device)))
+            self._pushed = False
+
+    def snapshot_local(self, i):
+        st = self.st
+        return st.full[i][st.row0:st.row0 + st.n_local].clone()
+
+
+def propagate_device(st: DistState, local_norm, x_local_padded, k, keep_hops=True):
+    """K hops on the device; returns the list of local hop slices (or only the last when not keep_hops)."""
+    ops = DeviceOps(st)
+    cur, nxt = 0, 1
+    ops.load_local(cur, x_local_padded)
+    if st.world > 1:
+        if st.mode == "push":
+            # the input slice has to reach the peers once: a plain all-gather (not on the per-hop path)
+            view = st.full[cur][st.rank * st.rows_per:(st.rank + 1) * st.rows_per]
+            st.dist.all_gather_into_tensor(st.full[cur], view, group=st.group)
+        else:
+            ops.exchange(cur)
+    out = [ops.snapshot_local(cur)] if keep_hops else []
+    for _ in range(k):
+        ops.hop(local_norm, cur, nxt)
+        ops.exchange(nxt, pushed=(st.mode == "push" and st.world > 1))
+        if keep_hops:
+            out.append(ops.snapshot_local(nxt))
+        cur, nxt = nxt, cur
+    if not keep_hops:
+        out = [ops.snapshot_local(cur)]
+    return out
+
+
+def dist_sym_norm(st: DistState, a_local, r, ppr_alpha=None):
+    """Normalise this rank's rows (raw DeviceCSR with global column ids).  Returns (DeviceCSR with
+    float32 values, flags tensor)."""
+    import torch
+
+    from . import _lib
+    from .device import DeviceCSR, _p, _stream_ptr
+    lib, dev = st.lib, st.device
+    s = _stream_ptr(dev)
+    n_loc, nnz = st.n_local, a_local.nnz
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    at_indptr = torch.empty(n_loc + 1, dtype=torch.int32, device=dev)
+    _lib.check(lib.srg_selfloop_rows_csr(_p(a_local.indptr), _p(a_local.indices), _p(a_local.data), a_local.val_dtype,
+                                         n_loc, st.row0, st.n, _p(at_indptr), None, _p(flags), s))
+    cap = max(nnz + n_loc, 1)
+    at_indices = torch.empty(cap, dtype=torch.int32, device=dev)
+    at_val = torch.empty(cap, dtype=torch.float64, device=dev) if a_local.data is not None else None
+    deg_all = torch.zeros(st.n_pad, dtype=torch.float64, device=dev)
+    deg_loc = deg_all[st.rank * st.rows_per: st.rank * st.rows_per + max(n_loc, 0)]
+    _lib.check(lib.srg_selfloop_fill_rows_csr(_p(a_local.indptr), _p(a_local.indices), _p(a_local.data),
+                                              a_local.val_dtype, n_loc, st.row0, st.n, _p(at_indptr), _p(at_indices),
+                                              _p(at_val), _p(deg_loc), _p(flags), s))
+    if st.world > 1:
+        view = deg_all[st.rank * st.rows_per:(st.rank + 1) * st.rows_per]
+        st.dist.all_gather_into_tensor(deg_all, view, group=st.group)
+    dl = torch.empty(st.n_pad, dtype=torch.float64, device=dev)
+    dr = torch.empty(st.n_pad, dtype=torch.float64, device=dev)
+    _lib.check(lib.srg_pow_tables_f64(_p(deg_all), st.n_pad, float(r), _p(dl), _p(dr), s))
+    val32 = torch.empty(cap, dtype=torch.float32, device=dev)
+    alpha = -1.0 if ppr_alpha is None else float(ppr_alpha)
+    _lib.check(lib.srg_norm_values_rows_csr(_p(at_indptr), _p(at_indices), _p(at_val), _p(deg_loc), n_loc, st.row0,
+                                            _p(dl), _p(dr), alpha, 0, None, _p(val32), _p(flags), s))
+    return DeviceCSR(at_indptr, at_indices, val32, n_loc, -1), flags

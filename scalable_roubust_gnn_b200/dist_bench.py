@@ -1,0 +1,130 @@
+"""bench.py body for N > 1 GPUs (one rank per GPU, launched by torch.distributed.run).
+
+Strong scaling: the same products-shaped graph is row-partitioned over the ranks; a step is the
+sharded normalisation (one degree all-gather) + K hops with the per-hop exchange fused into the
+SpMM epilogue (push over NVLink peer mappings) or, with SRG_DIST_MODE=allgather, NCCL all-gather.
+Timed on the device (CUDA events) between barriers, max over ranks.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+
+def run(args, workloads, metric, unit):
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib, device as dev, dist as sdist, synth
+
+    world = int(os.environ["WORLD_SIZE"])
+    rank = int(os.environ["RANK"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    mode = os.environ.get("SRG_DIST_MODE", "push")
+    n, nnz, f, k = workloads[args.workload]
+    n, nnz = int(n * args.scale), int(nnz * args.scale)
+
+    t0 = time.perf_counter()
+    a = synth.uniform_graph(n, nnz)        # every rank regenerates the same graph (fixed seed) ...
+    st = sdist.DistState(n, f, world, rank, mode=mode)
+    s, e = st.row0, st.row0 + st.n_local
+    a_loc_host = sdist.shard_rows(a, s, e)  # ... and keeps its row slice
+    x_loc_host = synth.features(n, f)[s:e]
+    nnz_hat = a.nnz + n
+    del a
+    if rank == 0:
+        print(f"[bench] world={world} mode={mode} N={n} nnz_hat={nnz_hat} F={f} K={k} rows/rank={st.rows_per} "
+              f"setup {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
+    a_loc = dev.upload_csr(a_loc_host)
+    x_loc = dev.pack_features(torch.from_numpy(np.ascontiguousarray(x_loc_host)).cuda())
+
+    def step():
+        norm, flags = sdist.dist_sym_norm(st, a_loc, 0.5)
+        sdist.propagate_device(st, norm, x_loc, k, keep_hops=False)
+        return flags
+
+    for _ in range(args.warmup):
+        flags = step()
+    torch.cuda.synchronize()
+    assert int(flags.item()) & ~_lib.SRG_FLAG_WEIGHTED == 0, f"normalisation flags {int(flags.item())}"
+
+    from bench import ClockSampler  # noqa: E402  (bench.py is the entry script)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    t_step = float(ms.item()) * 1e-3 / args.steps
+    launches = _lib.launch_count() - launches0
+
+    # end to end: host slices in (pinned), host slices of every hop out, per rank
+    x_pin = torch.from_numpy(np.ascontiguousarray(x_loc_host)).pin_memory()
+    ip = torch.from_numpy(a_loc_host.indptr).pin_memory()
+    ii = torch.from_numpy(a_loc_host.indices).pin_memory()
+    dd = torch.from_numpy(a_loc_host.data).pin_memory()
+    outs = [torch.empty((st.n_local, f), dtype=torch.float32).pin_memory() for _ in range(k)]
+
+    def e2e_step():
+        a_d = dev.DeviceCSR(ip.cuda(non_blocking=True), ii.cuda(non_blocking=True), dd.cuda(non_blocking=True),
+                            st.n_local, int(a_loc_host.nnz))
+        xp = dev.pack_features(x_pin.cuda(non_blocking=True))
+        norm, _ = sdist.dist_sym_norm(st, a_d, 0.5)
+        hops = sdist.propagate_device(st, norm, xp, k, keep_hops=True)
+        for o, h in zip(outs, hops[1:]):
+            o.copy_(dev.unpack_features(h, f), non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_step()
+    dist.barrier()
+    t0 = time.perf_counter()
+    reps = max(1, min(args.steps, 5))
+    for _ in range(reps):
+        e2e_step()
+    dist.barrier()
+    t_e2e = torch.tensor([(time.perf_counter() - t0) / reps], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    t_e2e = float(t_e2e.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        from bench import comp_bytes, gather_bytes, measured_peak, workload_config
+        peak, peak_src = measured_peak()
+        value = k * nnz_hat * f / t_step
+        bg = gather_bytes(n, nnz_hat, f)
+        # per-GPU roofline: each rank gathers nnz_hat/P rows; the exchange moves (P-1)/P * N*F*4 bytes in
+        hop_s = t_step / k
+        nvlink_bytes = (world - 1) / world * n * f * 4
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(workload_config(args, n, nnz_hat, f, k), exchange=mode, partition="contiguous rows"),
+                "roofline": {"bound": "hbm", "kernel": "spmm_stream2_kernel (push epilogue)" if mode == "push" else "spmm_stream2_kernel + ncclAllGather",
+                             "achieved": bg / world / hop_s / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": bg / world / hop_s / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                             "note": "per GPU, step time / K (includes the sharded normalisation and the exchange)",
+                             "nvlink_GBps_in_per_gpu": nvlink_bytes / hop_s / 1e9,
+                             "compulsory_bytes_per_launch": comp_bytes(n, nnz_hat, f) / world},
+                "cpu_baseline": None,
+                "e2e": {"value": k * nnz_hat * f / t_e2e, "unit": unit, "ms_per_step": t_e2e * 1e3,
+                        "h2d_bytes_per_step": int(ip.numel() * 4 + ii.numel() * 4 + dd.numel() * 8 + x_pin.numel() * 4),
+                        "d2h_bytes_per_step": int(k * st.n_local * f * 4), "note": "per-rank bytes; max over ranks time"},
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    st.close()
+    dist.destroy_process_group()

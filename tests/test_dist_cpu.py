@@ -1,0 +1,97 @@
+"""CPU suite for the N>1 path: partition map, row sharding and the per-hop exchange orchestration,
+driven over gloo with world_size 2 (the local hop is the oracle; the GPU ops are covered by
+tests/test_dist_gpu.py on a multi-GPU box)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from helpers import sym_graph
+from scalable_roubust_gnn_b200 import dist as sdist
+
+
+def test_row_partition_matches_oracle_definition():
+    for n, w in [(10, 4), (8, 8), (3, 8), (2449029, 8), (111059956, 8), (1, 1), (0, 2)]:
+        rp, st = sdist.row_partition(n, w)
+        rp_o, st_o = oracle.row_partition(n, w) if n > 0 else (0, np.zeros(w + 1, dtype=np.int64))
+        assert rp == rp_o
+        np.testing.assert_array_equal(st, st_o)
+        assert st[0] == 0 and st[-1] == n and (np.diff(st) >= 0).all()
+        # owner-of-row and local offset are what the kernels assume: global = rank * rows_per + local
+        if n > 0:
+            rows = np.array([0, n // 2, n - 1])
+            owner = rows // rp
+            assert ((st[owner] <= rows) & (rows < st[owner + 1])).all()
+
+
+def test_shard_rows_concatenate_to_the_whole():
+    a = oracle.sym_norm(sym_graph(1000, 8000, 3), 0.5)
+    rp, st = sdist.row_partition(1000, 3)
+    parts = [sdist.shard_rows(a, int(st[r]), int(st[r + 1])) for r in range(3)]
+    assert sum(p.nnz for p in parts) == a.nnz
+    import scipy.sparse as sp
+    assert (sp.vstack(parts) != a).nnz == 0
+    assert all(p.shape[1] == 1000 and p.indptr[0] == 0 for p in parts)
+
+
+class _GlooOps:
+    """ops for propagate_sharded: numpy buffers, oracle hop, gloo all-gather."""
+
+    def __init__(self, n, f, rows_per, world, rank, row0, n_local):
+        self.n, self.f, self.rows_per, self.world, self.rank, self.row0, self.n_local = n, f, rows_per, world, rank, row0, n_local
+
+    def new_full(self):
+        return np.zeros((self.rows_per * self.world, self.f), dtype=np.float32)
+
+    def load_local(self, full, x_local):
+        full[self.row0:self.row0 + self.n_local] = x_local
+
+    def exchange(self, full):
+        mine = torch.from_numpy(full[self.rank * self.rows_per:(self.rank + 1) * self.rows_per].copy())
+        out = torch.from_numpy(full)
+        dist.all_gather_into_tensor(out, mine)
+
+    def hop(self, local_norm, full_in, full_out):
+        full_out[self.row0:self.row0 + self.n_local] = oracle.spmm_hop(local_norm, full_in)
+
+    def snapshot_local(self, full):
+        return full[self.row0:self.row0 + self.n_local].copy()
+
+
+def _worker(rank, world, port, n, f, k, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        adj = sym_graph(n, 8 * n, 5)
+        x = np.random.default_rng(1).random((n, f), dtype=np.float32)
+        norm = oracle.sym_norm(adj, 0.5)
+        rows_per, starts = sdist.row_partition(n, world)
+        s, e = int(starts[rank]), int(starts[rank + 1])
+        local = sdist.shard_rows(norm, s, e)
+        # the local operator multiplies the padded full buffer: pad the column space
+        import scipy.sparse as sp
+        local = sp.csr_matrix((local.data, local.indices, local.indptr), shape=(e - s, rows_per * world))
+        ops = _GlooOps(n, f, rows_per, world, rank, s, e - s)
+        hops = sdist.propagate_sharded(ops, local, x[s:e], k, rows_per, world)
+        np.save(os.path.join(out_dir, f"hops_{rank}.npy"), np.stack(hops))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [1000, 1001])
+def test_sharded_propagation_bitwise_equals_single_process(tmp_path, n):
+    world, f, k = 2, 12, 3
+    port = 29500 + (os.getpid() % 500) + n % 7
+    mp.spawn(_worker, args=(world, port, n, f, k, str(tmp_path)), nprocs=world, join=True)
+    adj = sym_graph(n, 8 * n, 5)
+    x = np.random.default_rng(1).random((n, f), dtype=np.float32)
+    want, _ = oracle.propagate(adj, x, k)
+    got = np.concatenate([np.load(tmp_path / f"hops_{r}.npy") for r in range(world)], axis=1)
+    for h in range(k + 1):
+        np.testing.assert_array_equal(got[h], want[h])

@@ -1,0 +1,61 @@
+"""Multi-GPU parity (-m gpu, needs >= 2 GPUs on the box: `gpurun --gpus 2`): the row-partitioned
+normalisation and both exchange modes against the single-GPU path, bitwise."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from helpers import sym_graph
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, n, f, k, mode, weighted, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from scalable_roubust_gnn_b200 import device as dev, dist as sdist
+        adj = sym_graph(n, 10 * n, 5, weighted=weighted)
+        x = np.random.default_rng(1).random((n, f), dtype=np.float32)
+        st = sdist.DistState(n, f, world, rank, mode=mode)
+        s, e = st.row0, st.row0 + st.n_local
+        a_loc = dev.upload_csr(sdist.shard_rows(adj, s, e))
+        norm, flags = sdist.dist_sym_norm(st, a_loc, 0.5)
+        xp = dev.pack_features(torch.from_numpy(x[s:e]).cuda())
+        hops = sdist.propagate_device(st, norm, xp, k)
+        torch.cuda.synchronize()
+        m = int(norm.indptr[-1].item())
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), hops=np.stack([h[:, :f].cpu().numpy() for h in hops]),
+                 indptr=norm.indptr.cpu().numpy(), indices=norm.indices[:m].cpu().numpy(),
+                 vals=norm.data[:m].cpu().numpy(), flags=int(flags.item()))
+        st.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("mode", ["allgather", "push"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_two_gpus_bitwise_equal_one_gpu(tmp_path, mode, weighted):
+    from scalable_roubust_gnn_b200 import device as dev
+    world, n, f, k = 2, 50001, 100, 3
+    port = 29600 + (os.getpid() % 300) + (1 if mode == "push" else 0) + (2 if weighted else 0)
+    mp.spawn(_worker, args=(world, port, n, f, k, mode, weighted, str(tmp_path)), nprocs=world, join=True)
+    adj = sym_graph(n, 10 * n, 5, weighted=weighted)
+    x = np.random.default_rng(1).random((n, f), dtype=np.float32)
+    a = dev.upload_csr(adj)
+    norm, flags, _ = dev.sym_norm(a, 0.5)
+    assert int(flags.item()) & ~16 == 0
+    hops = dev.propagate(norm, dev.pack_features(torch.from_numpy(x).cuda()), f, k)
+    want = np.stack([h[:, :f].cpu().numpy() for h in hops])
+    parts = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
+    got = np.concatenate([p["hops"] for p in parts], axis=1)
+    np.testing.assert_array_equal(got, want)                      # P = 2 bitwise == P = 1
+    m = int(norm.indptr[-1].item())
+    np.testing.assert_array_equal(np.concatenate([p["indices"] for p in parts]), norm.indices[:m].cpu().numpy())
+    np.testing.assert_array_equal(np.concatenate([p["vals"] for p in parts]), norm.data[:m].cpu().numpy())

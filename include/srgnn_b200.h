@@ -69,8 +69,8 @@ int srg_device_count(void);
 int64_t srg_launch_count(void);
 
 /* tuning / experiment knobs (profiles/ records which values the defaults come from):
- *   "spmm_variant" 0 group kernel | 1 stream kernel;  "stream_cfg" ring shape;  "stream_rows" rows
- *   per warp task;  "group_unroll";  "l2_fetch_granularity" 32|64|128 (cudaLimitMaxL2FetchGranularity) */
+ *   "spmm_variant" 0 group kernel | 1 stream kernel;  "stream_batch" 4|8;  "stream_rows" rows per
+ *   warp task;  "group_unroll" 4|8;  "gather_l2_64" 0|1;  "long_row" split threshold (0 = never) */
 int srg_set_tuning(const char *key, int64_t value);
 
 /* ---- a3: adjacency normalisation  (SSRG/operators/utils.py:81-93) ------------------------ */
@@ -177,10 +177,14 @@ int srg_apply_feature_mask_f32(const float *x, int64_t ld_x, const int32_t *mask
  * the arithmetic of the reference's vfmadd loop, so results are bit-identical to it.
  * Y is overwritten (the reference accumulates into a pre-zeroed buffer).
  * n_rows rows of the CSR are processed; column indices address rows of X (global ids).
+ * nnz: an upper bound of indptr[n_rows] (sizes the long-row scratch without a device readback);
+ * rows longer than 1024 entries (power-law hubs) are evaluated as fixed 1024-entry segments whose
+ * sums are added in order: deterministic, bit-identical for every shorter row.  Pass nnz <= 0 to
+ * force the strict in-order chain for every row.
  */
 int srg_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
-                     int64_t n_rows, const float *X, int64_t ldx, float *Y, int64_t ldy,
-                     int32_t F, void *stream);
+                     int64_t n_rows, int64_t nnz, const float *X, int64_t ldx, float *Y,
+                     int64_t ldy, int32_t F, void *stream);
 
 /* ---- (e) row-partitioned multi-GPU hop ------------------------------------------------------- */
 /*
@@ -191,8 +195,9 @@ int srg_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float 
  * orders hops across ranks (a stream-ordered collective / barrier between hops).
  */
 int srg_spmm_csr_f32_push(const int32_t *indptr, const int32_t *indices, const float *vals,
-                          int64_t n_rows, const float *X, int64_t ldx, float *const *dests,
-                          int32_t n_dests, int64_t dest_row0, int64_t ldy, int32_t F, void *stream);
+                          int64_t n_rows, int64_t nnz, const float *X, int64_t ldx,
+                          float *const *dests, int32_t n_dests, int64_t dest_row0, int64_t ldy,
+                          int32_t F, void *stream);
 /* peer-mappable device buffers: plain cudaMalloc + CUDA IPC handles (64 bytes) */
 int srg_ipc_alloc(void **ptr, int64_t bytes);
 int srg_ipc_free(void *ptr);
@@ -203,8 +208,8 @@ int srg_ipc_close(void *ptr);
 /* ---- a1: K hops, device resident  (SSRG/operators/base_operator.py:31-35) ------------------ */
 /* hops[0] = input features, hops[k] = A^ * hops[k-1], k = 1..K; all n x ld fp32 device buffers. */
 int srg_propagate_khop_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
-                           int64_t n, float *const *hops, int64_t ld, int32_t F, int32_t K,
-                           void *stream);
+                           int64_t n, int64_t nnz, float *const *hops, int64_t ld, int32_t F,
+                           int32_t K, void *stream);
 
 /* ---- a9: Chebyshev heat-wavelet filter  (wavelet/src/utils.py:89-104,125-138; pygsp cheby_op) --- */
 /*

@@ -60,14 +60,14 @@ SIGNATURES = {
     "srg_edge_gather_i64": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "srg_edges_to_sym_csr": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "srg_apply_feature_mask_f32": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
-    "srg_spmm_csr_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
-    "srg_spmm_csr_f32_push": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, C.POINTER(_vp), _i32, _i64, _i64, _i32, _vp]),
+    "srg_spmm_csr_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
+    "srg_spmm_csr_f32_push": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, C.POINTER(_vp), _i32, _i64, _i64, _i32, _vp]),
     "srg_ipc_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
     "srg_ipc_free": (C.c_int, [_vp]),
     "srg_ipc_get_handle": (C.c_int, [_vp, _vp]),
     "srg_ipc_open": (C.c_int, [_vp, C.POINTER(_vp)]),
     "srg_ipc_close": (C.c_int, [_vp]),
-    "srg_propagate_khop_f32": (C.c_int, [_vp, _vp, _vp, _i64, C.POINTER(_vp), _i64, _i32, _i32, _vp]),
+    "srg_propagate_khop_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i64, C.POINTER(_vp), _i64, _i32, _i32, _vp]),
     "srg_laplacian_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "srg_cheby_filter_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i32, _f64, C.POINTER(_f64), _i32, _i32, _f64,
                                        C.POINTER(_vp), C.POINTER(_vp), _i64, _vp, _vp, _vp]),

@@ -52,7 +52,7 @@ int require_device() {
 }
 
 int spmm_csr_f32_impl(const int32_t *indptr, const int32_t *indices, const float *vals,
-                      int64_t n_rows, const float *X, int64_t ldx, float *Y, int64_t ldy,
+                      int64_t n_rows, int64_t nnz, const float *X, int64_t ldx, float *Y, int64_t ldy,
                       int32_t F, bool accumulate, cudaStream_t s);
 
 // ---- per-device state of the host entry points -------------------------------------------------
@@ -272,6 +272,7 @@ static int construct_attempt(const int32_t *indptr, const int32_t *indices, cons
     SRG_CUDA(cudaMemcpyAsync(&flags, no.flags, 4, cudaMemcpyDeviceToHost, s));
     SRG_CUDA(cudaMemcpyAsync(out_indptr, no.indptr, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, s));
     SRG_CUDA(cudaStreamSynchronize(s));
+    flags &= ~SRG_FLAG_WEIGHTED;  // informational
     *flags_out = flags;
     if (flags) {
       pa.clean = true;
@@ -395,7 +396,7 @@ static int propagate_attempt(const int32_t *indptr, const int32_t *indices, cons
     if (have_feat) {
       SRG_CUDA(cudaStreamWaitEvent(s_c, st->ev_x, 0));
       for (int k = 1; k <= K; ++k) {
-        if ((rc = spmm_csr_f32_impl(no.indptr, no.indices, no.val32, n, hops[k - 1], ld, hops[k], ld, F, false, s_c)))
+        if ((rc = spmm_csr_f32_impl(no.indptr, no.indices, no.val32, n, nnz + n, hops[k - 1], ld, hops[k], ld, F, false, s_c)))
           return rc;
         SRG_CUDA(cudaEventRecord(st->ev_hop[k - 1], s_c));
         SRG_CUDA(cudaStreamWaitEvent(s_out, st->ev_hop[k - 1], 0));
@@ -417,6 +418,7 @@ static int propagate_attempt(const int32_t *indptr, const int32_t *indices, cons
       SRG_CUDA(cudaMemcpyAsync(out_norm_indptr, no.indptr, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, s_in));
     SRG_CUDA(cudaStreamSynchronize(s_in));
     nnz_out = h_nnz_out;
+    flags &= ~SRG_FLAG_WEIGHTED;  // informational
     *flags_out = flags;
     const int frc = flags ? 1 : 0;  // flagged: results are discarded, the caller retries or fails
     if (!frc) {
@@ -484,7 +486,7 @@ static int shim_spmm(float *answer, const float *data, const int *indices, const
   SRG_CUDA(cudaMemcpyAsync(d_x, mat, (size_t)n * F * 4, cudaMemcpyHostToDevice, s));
   // the reference accumulates into `answer` (matmul.c:37): start every chain from its content
   SRG_CUDA(cudaMemcpyAsync(d_y, answer, (size_t)n * F * 4, cudaMemcpyHostToDevice, s));
-  if ((rc = spmm_csr_f32_impl(d_indptr, d_indices, d_vals, n, d_x, F, d_y, F, (int32_t)F, true, s))) return rc;
+  if ((rc = spmm_csr_f32_impl(d_indptr, d_indices, d_vals, n, nnz, d_x, F, d_y, F, (int32_t)F, true, s))) return rc;
   SRG_CUDA(cudaMemcpyAsync(answer, d_y, (size_t)n * F * 4, cudaMemcpyDeviceToHost, s));
   SRG_CUDA(cudaStreamSynchronize(s));
   pa.clean = true;

@@ -36,6 +36,12 @@ template <> struct ValLoad<SRG_VAL_F64> {
 
 constexpr int kWeighted = SRG_FLAG_WEIGHTED;
 
+// OR bits into the flags word without hammering one address: only threads that would add a bit not
+// yet visible issue the atomic (the race is benign, it only costs a redundant atomic).
+__device__ __forceinline__ void raise_flags(int *flags, int fl) {
+  if (fl && (fl & ~*reinterpret_cast<volatile int *>(flags))) atomicOr(flags, fl);
+}
+
 // ---- stage 1: row lengths of A~ for the rows [row0, row0 + n_rows) of an n_cols-column matrix --
 template <int DT>
 __global__ void __launch_bounds__(256)
@@ -62,7 +68,7 @@ rows_count_kernel(const int *__restrict__ indptr, const int *__restrict__ indice
   }
   if (__dadd_rn(diag, 1.0) != 0.0) ++cnt;
   rowlen[a] = cnt;
-  if (fl) atomicOr(flags, fl);
+  raise_flags(flags, fl);
 }
 
 // ---- numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, *_pairwise_sum) ------
@@ -211,62 +217,71 @@ rows_values_kernel(long long n_rows, long long row0, const int *__restrict__ at_
                    const double *__restrict__ dr, double one_minus_alpha, double alpha, int use_ppr,
                    int check_sym, double *__restrict__ val64, float *__restrict__ val32,
                    int *__restrict__ flags, unsigned long long *__restrict__ tri_counts) {
-  const long long a = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (a >= n_rows) return;
   const bool weighted = (*flags & kWeighted) != 0;
   const int lane = threadIdx.x & 31;
-  const int ag = (int)(a + row0);
-  const int p0 = at_indptr[a], p1 = at_indptr[a + 1];
-  const double dla = dl[ag];
-  const double diag_unw = weighted ? 0.0 : degree[a] - (double)(p1 - p0 - 1);
-  int fl = 0, n_up = 0, n_lo = 0;
-  for (int p = p0 + lane; p < p1; p += 32) {
-    const int b = at_indices[p];
-    const double vt = weighted ? at_val[p] : (b == ag ? diag_unw : 1.0);
-    if (check_sym && b != ag) {
-      if (b > ag) {
-        ++n_up;
-        int lo = at_indptr[b], hi = at_indptr[b + 1];
-        int q = -1;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          const int c = ld_idx_64(at_indices + mid);
-          if (c == ag) {
-            q = mid;
-            break;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  int fl = 0;
+  long long n_up = 0, n_lo = 0;  // per-thread running counts; reduced once per block
+  for (long long a = warp0; a < n_rows; a += nwarps) {
+    const int ag = (int)(a + row0);
+    const int p0 = at_indptr[a], p1 = at_indptr[a + 1];
+    const double dla = dl[ag];
+    const double diag_unw = weighted ? 0.0 : degree[a] - (double)(p1 - p0 - 1);
+    for (int p = p0 + lane; p < p1; p += 32) {
+      const int b = at_indices[p];
+      const double vt = weighted ? at_val[p] : (b == ag ? diag_unw : 1.0);
+      if (check_sym && b != ag) {
+        if (b > ag) {
+          ++n_up;
+          int lo = at_indptr[b], hi = at_indptr[b + 1];
+          int q = -1;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const int c = ld_idx_64(at_indices + mid);
+            if (c == ag) {
+              q = mid;
+              break;
+            }
+            if (c < ag)
+              lo = mid + 1;
+            else
+              hi = mid;
           }
-          if (c < ag)
-            lo = mid + 1;
-          else
-            hi = mid;
+          if (q < 0 || (weighted && at_val[q] != vt)) fl |= SRG_FLAG_ASYMMETRIC;
+        } else {
+          ++n_lo;
         }
-        if (q < 0 || (weighted && at_val[q] != vt)) fl |= SRG_FLAG_ASYMMETRIC;
-      } else {
-        ++n_lo;
       }
+      double v = __dmul_rn(__dmul_rn(vt, dla), dr[b]);
+      if (use_ppr) {
+        v = __dmul_rn(one_minus_alpha, v);
+        if (b == ag) v = __dadd_rn(v, alpha);
+      }
+      if (v == 0.0) fl |= SRG_FLAG_ZERO_PRODUCT;
+      if (val64) val64[p] = v;
+      if (val32) val32[p] = __double2float_rn(v);
     }
-    double v = __dmul_rn(__dmul_rn(vt, dla), dr[b]);
-    if (use_ppr) {
-      v = __dmul_rn(one_minus_alpha, v);
-      if (b == ag) v = __dadd_rn(v, alpha);
-    }
-    if (v == 0.0) fl |= SRG_FLAG_ZERO_PRODUCT;
-    if (val64) val64[p] = v;
-    if (val32) val32[p] = __double2float_rn(v);
   }
   if (check_sym) {
-    n_up = __reduce_add_sync(0xffffffffu, n_up);
-    n_lo = __reduce_add_sync(0xffffffffu, n_lo);
-    if (lane == 0 && (n_up | n_lo)) {
-      if (n_up) atomicAdd(tri_counts, (unsigned long long)n_up);
-      if (n_lo) atomicAdd(tri_counts + 1, (unsigned long long)n_lo);
+    // upper - lower entry count of this block -> one atomic per block
+    __shared__ long long s_diff[8];
+    long long diff = n_up - n_lo;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
+    if (lane == 0) s_diff[threadIdx.x >> 5] = diff;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long t = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_diff[w];
+      if (t) atomicAdd(tri_counts, (unsigned long long)t);  // wraps: only == 0 matters
     }
   }
-  if (fl) atomicOr(flags, fl);
+  raise_flags(flags, fl);
 }
 
 __global__ void tri_compare_kernel(const unsigned long long *tri_counts, int *flags) {
-  if (tri_counts[0] != tri_counts[1]) atomicOr(flags, SRG_FLAG_ASYMMETRIC);
+  if (tri_counts[0] != 0ULL) atomicOr(flags, SRG_FLAG_ASYMMETRIC);  // #upper != #lower
 }
 
 #define SRG_DT_SWITCH(dt, CALL)                       \
@@ -397,8 +412,9 @@ extern "C" int srg_norm_values_rows_csr(const int32_t *at_indptr, const int32_t 
     SRG_CUDA(cudaMallocAsync(&tri, 2 * sizeof(unsigned long long), s));
     SRG_CUDA(cudaMemsetAsync(tri, 0, 2 * sizeof(unsigned long long), s));
   }
-  const int64_t wblocks = ceil_div64(n_rows * 32, 256);
-  SRG_REQUIRE(wblocks <= 2147483647LL, "norm_values_rows: too many rows");
+  // persistent-style grid: 148 SMs x 8 resident blocks, warps stride over the rows
+  int64_t wblocks = ceil_div64(n_rows * 32, 256);
+  if (wblocks > 148 * 8) wblocks = 148 * 8;
   rows_values_kernel<<<(unsigned)wblocks, 256, 0, s>>>(n_rows, row0, at_indptr, at_indices, at_val, degree_rows,
                                                        pow_left, pow_right, 1.0 - ppr_alpha, ppr_alpha,
                                                        ppr_alpha >= 0.0 ? 1 : 0, check_symmetry, out_val_f64,

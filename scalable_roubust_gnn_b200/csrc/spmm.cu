@@ -3,18 +3,32 @@
 // Replaces SSRG/operators/csrc/matmul.c:23-40 (FloatCSRMulDenseOMP): for every row i and feature k
 //   answer[i,k] = fma(data[j], mat[indices[j],k], answer[i,k])   for j = indptr[i] .. indptr[i+1]-1
 // in CSR order, starting from 0.  Every output element here is the same sequential fp32 FMA chain,
-// so a hop is bit-identical to the reference; only the mapping to the machine differs:
+// so a hop is bit-identical to the reference (rows longer than the long-row threshold are the one
+// exception: they are split into fixed segments whose partial sums are added in order —
+// deterministic, within fp32 rounding of the chain).
 //
-//   * a "group" of G lanes (G = 1..32, power of two) owns one (row, 4*G-float feature chunk);
-//     each lane keeps ONE float4 accumulator => 128-bit gathers, 4 FMA chains per lane.
-//   * the group loads G (index, value) pairs of its row with one coalesced read and broadcasts
-//     them with shuffles, so the CSR arrays are read exactly once per chunk.
-//   * U gathers are issued back to back before the first FMA consumes them (memory-level
-//     parallelism: U*16 B per lane in flight); the FMAs are then applied in CSR order.
-//   * HBM-bound (0.5 flop/B): no shared memory tile reuse exists for X on a random graph, so the
-//     kernel is sized for occupancy and bytes in flight, not for tensor cores.
+// The path is HBM-bound (0.5 flop/B, no reuse of X on a random graph), so there are no tensor
+// cores here; the kernels are built around bytes in flight and DRAM sectors:
 //
-// Long rows: handled by the split kernels further down (fixed-order partial sums, deterministic).
+//   stream kernel (F >= 68)  one warp owns R consecutive rows and walks their neighbours as ONE
+//       stream.  Per neighbour each lane issues a 16-byte cp.async (LDGSTS, L2 -> shared, no
+//       register staging, 64-byte DRAM fetch granule) into a per-warp ring of 2B row slots; the
+//       consumer runs one batch of B neighbours behind, applies the FMAs in CSR order and stores
+//       a row of Y whenever it crosses a row end.  The stream is processed in chunks of 32
+//       neighbours whose (index, value) pairs sit one per lane (coalesced 128-byte loads,
+//       prefetched one chunk ahead); the chunk body is fully unrolled, so shuffle lanes, ring
+//       slots and row-end tests are compile-time constants: ~13 issued instructions per gathered
+//       row.  Measured 4.35 ms per hop on the products shape = 0.955 of the measured HBM peak
+//       in gather-model bytes (profiles/).
+//   group kernel (F < 68, unaligned layouts, the accumulate-into-answer shim)  G lanes per
+//       (row, feature chunk), U register-staged gathers in flight.
+//   long rows (power-law graphs)  rows longer than the threshold are cut into segments that run
+//       as independent single-row tasks of the same stream kernel, then a combine kernel adds the
+//       segment sums in order.  The plan (list of long rows / segments) is built on the device
+//       from indptr; no host synchronisation.
+//   push (multi-GPU)  the row store of the stream kernel writes into the next-hop buffer of
+//       every rank over NVLink peer mappings: the per-hop all-gather is the kernel's epilogue.
+#include <algorithm>
 #include <cstring>
 #include <string>
 
@@ -22,10 +36,17 @@
 
 namespace srg {
 
-// ---- vector abstraction: float4 fast path, float scalar path ---------------------------------
+// ---- tuning knobs (srg_set_tuning) -----------------------------------------------------------------
+static int g_spmm_variant = 1;   // 1 = stream kernel where it applies, 0 = group kernel everywhere
+static int g_stream_rows = 4;    // rows per warp task (R)
+static int g_stream_batch = 4;   // B: 4 or 8
+static int g_gather_l2_64 = 1;   // gathers fetch 64-byte DRAM granules instead of whole 128-byte lines
+static int g_group_unroll = 4;   // U of the 32-lane group kernel (4 or 8)
+static int g_long_row = 1024;    // rows with more entries are split (0 = never split)
+
+// ---- vector abstraction for the group kernel: float4 fast path, float scalar path ------------------
 template <typename VT> struct VecOps;
 template <> struct VecOps<float4> {
-  static constexpr int W = 4;
   __device__ static __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ static __forceinline__ float4 gather(const float4 *p) { return ld_gather_f4(p); }
   __device__ static __forceinline__ void fma(float a, const float4 &x, float4 &acc) {
@@ -34,16 +55,11 @@ template <> struct VecOps<float4> {
     acc.z = fmaf(a, x.z, acc.z);
     acc.w = fmaf(a, x.w, acc.w);
   }
-  __device__ static __forceinline__ void store(float4 *p, const float4 &v) { *p = v; }
 };
 template <> struct VecOps<float> {
-  static constexpr int W = 1;
   __device__ static __forceinline__ float zero() { return 0.f; }
   __device__ static __forceinline__ float gather(const float *p) { return __ldg(p); }
-  __device__ static __forceinline__ void fma(float a, const float &x, float &acc) {
-    acc = fmaf(a, x, acc);
-  }
-  __device__ static __forceinline__ void store(float *p, const float &v) { *p = v; }
+  __device__ static __forceinline__ void fma(float a, const float &x, float &acc) { acc = fmaf(a, x, acc); }
 };
 
 constexpr int kSpmmThreads = 256;
@@ -60,8 +76,7 @@ spmm_group_kernel(const int *__restrict__ indptr, const int *__restrict__ indice
   const long long row = item / chunks;
   const int chunk = (int)(item - row * chunks);
   if (row >= n_rows) return;  // group-uniform
-  const unsigned gmask =
-      (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
   const int col = chunk * G + g;  // in units of VT
   const bool active = col < nvec;
 
@@ -93,201 +108,50 @@ spmm_group_kernel(const int *__restrict__ indptr, const int *__restrict__ indice
       }
     }
   }
-  if (active) Ops::store(Y + row * ldy + col, acc);
+  if (active) Y[row * ldy + col] = acc;
 }
-
-static int g_group_unroll = 4;  // tuning: gathers in flight per lane for the 32-lane group kernel
 
 template <typename VT, int G, bool ACCUM, int U = ((G >= 4) ? 4 : G)>
 static int launch_group(const int *indptr, const int *indices, const float *vals, int64_t n_rows,
                         const VT *X, int64_t ldx, VT *Y, int64_t ldy, int nvec, cudaStream_t s) {
   constexpr int GROUPS = kSpmmThreads / G;
   const int chunks = (nvec + G - 1) / G;
-  const int64_t items = n_rows * (int64_t)chunks;
-  const int64_t blocks = ceil_div64(items, GROUPS);
+  const int64_t blocks = ceil_div64(n_rows * (int64_t)chunks, GROUPS);
   if (blocks > 2147483647LL) {
     set_err("spmm: grid too large (%lld blocks)", (long long)blocks);
     return SRG_ERR_RANGE;
   }
   if (blocks == 0) return SRG_OK;
-  spmm_group_kernel<VT, G, U, ACCUM><<<(unsigned)blocks, kSpmmThreads, 0, s>>>(
-      indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, chunks);
+  spmm_group_kernel<VT, G, U, ACCUM><<<(unsigned)blocks, kSpmmThreads, 0, s>>>(indptr, indices, vals, n_rows, X, ldx, Y,
+                                                                               ldy, nvec, chunks);
   SRG_LAUNCHED();
   return SRG_OK;
 }
 
 template <typename VT, bool ACCUM>
-static int dispatch_group(const int *indptr, const int *indices, const float *vals,
-                          int64_t n_rows, const VT *X, int64_t ldx, VT *Y, int64_t ldy, int nvec,
-                          cudaStream_t s) {
-#define SRG_CASE(GG) \
-  return launch_group<VT, GG, ACCUM>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s)
+static int dispatch_group(const int *indptr, const int *indices, const float *vals, int64_t n_rows,
+                          const VT *X, int64_t ldx, VT *Y, int64_t ldy, int nvec, cudaStream_t s) {
+#define SRG_CASE(GG) return launch_group<VT, GG, ACCUM>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s)
   if (nvec <= 1) SRG_CASE(1);
   if (nvec <= 2) SRG_CASE(2);
   if (nvec <= 4) SRG_CASE(4);
   if (nvec <= 8) SRG_CASE(8);
   if (nvec <= 16) SRG_CASE(16);
-  if (g_group_unroll == 8)
-    return launch_group<VT, 32, ACCUM, 8>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
+  if (g_group_unroll == 8) return launch_group<VT, 32, ACCUM, 8>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
   SRG_CASE(32);
 #undef SRG_CASE
 }
 
-
-// ---- stream kernel: deep asynchronous gather pipeline through shared memory ---------------------
-// One warp owns R consecutive rows and treats their neighbours as ONE stream of positions
-// [indptr[r0], indptr[r0+R)).  A producer cursor issues, for every position, one 16-byte
-// cp.async (LDGSTS, L2 -> shared, no register staging) per lane into a per-warp ring of S row
-// slots; a consumer cursor S positions behind applies the FMAs in CSR order and flushes a row of
-// Y whenever it crosses a row end.  The in-flight depth is S rows (S*16 B per lane) independent
-// of the register budget, the index/value chunks are prefetched one chunk ahead, and nothing
-// stalls at row boundaries, so the warp keeps the memory system busy across short rows.
-// Each lane reads back only the 16 bytes it copied itself: no barrier is needed for the ring.
-__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-// same, fetching 64-byte granules from DRAM on an L2 miss instead of the default full 128-byte
-// line (measured: tools/micro/fetch_gran.cu, profiles/fetch_granularity.md)
-__device__ __forceinline__ void cp_async_16_l2_64(void *smem_dst, const void *gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-constexpr int kStreamWarps = 8;
-
-template <int S, int B, bool L2_64>
-__global__ void __launch_bounds__(kStreamWarps * 32)
-spmm_stream_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
-                   const float *__restrict__ vals, long long n_rows, const float4 *__restrict__ X,
-                   long long ldx, float4 *__restrict__ Y, long long ldy, int nvec, int chunks,
-                   int R, int stride) {
-  static_assert(S % B == 0 && (S & (S - 1)) == 0, "ring must be a power of two multiple of B");
-  constexpr int NB = S / B;
-  extern __shared__ float4 smem4[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 *ring = smem4 + (size_t)w * S * stride;  // slot = `stride` float4 (active lanes only)
-  float *vring = reinterpret_cast<float *>(smem4 + (size_t)kStreamWarps * S * stride) + w * S;
-
-  const long long task = (long long)blockIdx.x * kStreamWarps + w;
-  const long long rblock = task / chunks;
-  const int chunk = (int)(task - rblock * chunks);
-  const long long r0 = rblock * R;
-  if (r0 >= n_rows) return;
-  const int nr = (int)min((long long)R, n_rows - r0);
-  const int col = chunk * 32 + lane;
-  const bool active = col < nvec;
-
-  const int my_end = (lane < nr) ? __ldg(indptr + r0 + lane + 1) : 0;
-  const int e0 = __ldg(indptr + r0);
-  const int e1 = __shfl_sync(0xffffffffu, my_end, nr - 1);
-
-  int p = e0, q = e0;
-  // index / value chunks: lane l holds position cbase + l; the next chunk is always in flight
-  int cbase = e0;
-  int my_c = 0, nx_c = 0;
-  float my_v = 0.f, nx_v = 0.f;
-  if (cbase + lane < e1) {
-    my_c = ld_stream_i32(indices + cbase + lane);
-    my_v = ld_stream_f32(vals + cbase + lane);
-  }
-  if (cbase + 32 + lane < e1) {
-    nx_c = ld_stream_i32(indices + cbase + 32 + lane);
-    nx_v = ld_stream_f32(vals + cbase + 32 + lane);
-  }
-
-  const float4 *Xc = X + col;
-  float4 *Yc = Y + r0 * ldy + col;
-  int cr = 0;
-  int cur_end = __shfl_sync(0xffffffffu, my_end, 0);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  auto flush_rows = [&]() {
-    while (cr < nr && q == cur_end) {  // also walks over empty rows
-      if (active) Yc[(long long)cr * ldy] = acc;
-      acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      ++cr;
-      cur_end = __shfl_sync(0xffffffffu, my_end, min(cr, 31));
-    }
-  };
-  auto issue_batch = [&]() {
-#pragma unroll
-    for (int b = 0; b < B; ++b) {
-      if (p < e1) {
-        if (p == cbase + 32) {
-          cbase += 32;
-          my_c = nx_c;
-          my_v = nx_v;
-          if (cbase + 32 + lane < e1) {
-            nx_c = ld_stream_i32(indices + cbase + 32 + lane);
-            nx_v = ld_stream_f32(vals + cbase + 32 + lane);
-          }
-        }
-        const int c = __shfl_sync(0xffffffffu, my_c, p - cbase);
-        const float v = __shfl_sync(0xffffffffu, my_v, p - cbase);
-        const int slot = p & (S - 1);
-        if (lane == 0) vring[slot] = v;
-        if (active) {
-          if (L2_64)
-            cp_async_16_l2_64(ring + slot * stride + lane, Xc + (long long)c * ldx);
-          else
-            cp_async_16(ring + slot * stride + lane, Xc + (long long)c * ldx);
-        }
-        ++p;
-      }
-    }
-    cp_async_commit();
-  };
-  auto consume_batch = [&]() {
-    __syncwarp();
-#pragma unroll
-    for (int b = 0; b < B; ++b) {
-      if (q < e1) {
-        const int slot = q & (S - 1);
-        const float v = vring[slot];
-        if (active) {
-          const float4 x = ring[slot * stride + lane];
-          acc.x = fmaf(v, x.x, acc.x);
-          acc.y = fmaf(v, x.y, acc.y);
-          acc.z = fmaf(v, x.z, acc.z);
-          acc.w = fmaf(v, x.w, acc.w);
-        }
-        ++q;
-        flush_rows();
-      }
-    }
-    __syncwarp();
-  };
-
-  flush_rows();  // leading empty rows
-  const int nbatches = (e1 - e0 + B - 1) / B;
-#pragma unroll
-  for (int i = 0; i < NB - 1; ++i) issue_batch();
-  for (int it = 0; it < nbatches; ++it) {
-    issue_batch();
-    cp_async_wait<NB - 1>();
-    consume_batch();
-  }
-  cp_async_wait<0>();
-}
-
-// ---- stream kernel, unrolled form ------------------------------------------------------------------
-// Same pipeline as above with the bookkeeping taken out of the per-position path: the stream is
-// walked in chunks of 32 positions whose (index, value) live one per lane, the chunk body is fully
-// unrolled so every shuffle lane, ring slot and row-end test is a compile-time constant, row ends
-// are a 32-bit mask built once per chunk (REDUX), and the consumer lags the producer by exactly
-// one batch of B positions (ring of 2B slots), carrying the tail of a chunk into the next one.
-// ~13 issued instructions per gathered row instead of ~85: the kernel is DRAM-bound, not
-// issue-bound (profiles/spmm_stream.md).
+// ---- stream kernel ------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async_16s(unsigned smem_addr, const void *g, bool l2_64) {
   if (l2_64)
     asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
   else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ float4 lds_f4(unsigned smem_addr) {
   float4 v;
@@ -295,53 +159,82 @@ __device__ __forceinline__ float4 lds_f4(unsigned smem_addr) {
   return v;
 }
 
-// PUSH: the row-partitioned multi-GPU hop.  Instead of one Y, every finished row is stored into the
-// next-hop feature buffer of EVERY rank (peer pointers mapped over NVLink, own buffer included) at
-// its global row index, so the all-gather of the next hop happens inside this kernel's epilogue and
-// overlaps the gathers of the rows still in flight.
+constexpr int kStreamWarps = 8;
 constexpr int kMaxPeers = 8;
+
 struct PeerDests {
   float4 *p[kMaxPeers];
   int count;
 };
 
+struct StreamArgs {
+  const int *row_lo;         // first entry of row r   (CSR: indptr)
+  const int *row_hi;         // one past the last entry (CSR: indptr + 1); rows of one task are contiguous
+  const int *indices;
+  const float *vals;
+  long long n_rows;
+  const int *n_rows_dev;     // when non-NULL the row count is read from the device (segment tasks)
+  const float4 *X;
+  unsigned ldx;              // in float4
+  float4 *Y;
+  long long ldy;             // in float4
+  int nvec, chunks, R;
+  int long_len;              // rows longer than this are left to the segment kernels (0: none are)
+  PeerDests peers;
+};
+
+template <bool PUSH>
+__device__ __forceinline__ void store_row(const StreamArgs &a, float4 *yrow, const float4 &acc) {
+  if (PUSH) {
+    const long long off = yrow - a.Y;
+#pragma unroll
+    for (int d = 0; d < kMaxPeers; ++d)
+      if (d < a.peers.count) a.peers.p[d][off] = acc;
+  } else {
+    *yrow = acc;
+  }
+}
+
 template <int B, bool L2_64, bool PUSH>
-__global__ void __launch_bounds__(kStreamWarps * 32)
-spmm_stream2_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
-                    const float *__restrict__ vals, long long n_rows, const float4 *__restrict__ X,
-                    unsigned ldx, float4 *__restrict__ Y, long long ldy, int nvec, int chunks, int R,
-                    PeerDests peers) {
+__global__ void __launch_bounds__(kStreamWarps * 32) spmm_stream_kernel(const StreamArgs a) {
   constexpr int S = 2 * B;
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ float4 smem4[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned ring = (unsigned)__cvta_generic_to_shared(smem4 + (size_t)w * S * 32 + lane);
 
+  const long long n_rows = a.n_rows_dev ? (long long)*a.n_rows_dev : a.n_rows;
   const long long task = (long long)blockIdx.x * kStreamWarps + w;
-  const long long rblock = task / chunks;
-  const int chunk = (int)(task - rblock * chunks);
-  const long long r0 = rblock * R;
+  const long long rblock = task / a.chunks;
+  const int chunk = (int)(task - rblock * a.chunks);
+  const long long r0 = rblock * a.R;
   if (r0 >= n_rows) return;
-  const int nr = (int)min((long long)R, n_rows - r0);
+  const int nr = (int)min((long long)a.R, n_rows - r0);
   const int col = chunk * 32 + lane;
-  const bool active = col < nvec;
-  const float4 *Xc = X + col;
-  float4 *yrow = Y + r0 * ldy + col;
+  const bool active = col < a.nvec;
+  const float4 *Xc = a.X + col;
+  float4 *yrow = a.Y + r0 * a.ldy + col;
+  const unsigned ldx = a.ldx;
+  const long long ldy = a.ldy;
 
-  const int my_end = (lane < nr) ? __ldg(indptr + r0 + lane + 1) : 0;
-  const int e0 = __ldg(indptr + r0);
+  const int my_end = (lane < nr) ? __ldg(a.row_hi + r0 + lane) : 0;
+  const int e0 = __ldg(a.row_lo + r0);
   const int e1 = __shfl_sync(FULL, my_end, nr - 1);
   int prev_end = __shfl_up_sync(FULL, my_end, 1);
   if (lane == 0) prev_end = e0;
+  const int my_len = my_end - prev_end;
+  const bool odd_row = lane < nr && (my_len == 0 || (a.long_len > 0 && my_len > a.long_len));
 
-  if (__any_sync(FULL, lane < nr && my_end == prev_end)) {
-    // an empty row in this task (never happens for A^, which has a full diagonal): plain loop
+  if (__any_sync(FULL, odd_row)) {
+    // an empty or an over-long row in this task: rows one by one, long rows left to the segment
+    // kernels (A^ has a full diagonal, so empty rows only occur for caller-supplied matrices)
     for (int r = 0; r < nr; ++r) {
       const int st = __shfl_sync(FULL, prev_end, r), ed = __shfl_sync(FULL, my_end, r);
+      if (a.long_len > 0 && ed - st > a.long_len) continue;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int j = st; j < ed; ++j) {
-        const int c = __ldg(indices + j);
-        const float v = __ldg(vals + j);
+        const int c = __ldg(a.indices + j);
+        const float v = __ldg(a.vals + j);
         if (active) {
           const float4 x = ld_gather_f4(Xc + (unsigned long long)(unsigned)c * ldx);
           acc.x = fmaf(v, x.x, acc.x);
@@ -350,13 +243,7 @@ spmm_stream2_kernel(const int *__restrict__ indptr, const int *__restrict__ indi
           acc.w = fmaf(v, x.w, acc.w);
         }
       }
-      if (active) {
-        if (PUSH) {
-          for (int d = 0; d < peers.count; ++d) (peers.p[d] + (yrow - Y))[(long long)r * ldy] = acc;
-        } else {
-          yrow[(long long)r * ldy] = acc;
-        }
-      }
+      if (active) store_row<PUSH>(a, yrow + (long long)r * ldy, acc);
     }
     return;
   }
@@ -365,12 +252,12 @@ spmm_stream2_kernel(const int *__restrict__ indptr, const int *__restrict__ indi
   int my_c = 0, nx_c = 0;
   float my_v = 0.f, nx_v = 0.f, pv_v = 0.f;
   if (cbase + lane < e1) {
-    my_c = ld_stream_i32(indices + cbase + lane);
-    my_v = ld_stream_f32(vals + cbase + lane);
+    my_c = ld_stream_i32(a.indices + cbase + lane);
+    my_v = ld_stream_f32(a.vals + cbase + lane);
   }
   if (cbase + 32 + lane < e1) {
-    nx_c = ld_stream_i32(indices + cbase + 32 + lane);
-    nx_v = ld_stream_f32(vals + cbase + 32 + lane);
+    nx_c = ld_stream_i32(a.indices + cbase + 32 + lane);
+    nx_v = ld_stream_f32(a.vals + cbase + 32 + lane);
   }
   int prev_cnt = 0;
   unsigned prev_mask = 0;
@@ -399,7 +286,7 @@ spmm_stream2_kernel(const int *__restrict__ indptr, const int *__restrict__ indi
       cp_async_wait<1>();
 #pragma unroll
       for (int u = 0; u < B; ++u) {
-        const int j = (b - 1) * B + u;  // position consumed now (one batch behind)
+        const int j = (b - 1) * B + u;  // position consumed now (one batch behind the producer)
         const int jj = j & 31;          // lane / bit inside its own chunk
         const bool valid = (j < 0) ? (jj < prev_cnt) : (j < cnt);
         if (valid) {
@@ -412,16 +299,7 @@ spmm_stream2_kernel(const int *__restrict__ indptr, const int *__restrict__ indi
             acc.w = fmaf(v, x.w, acc.w);
           }
           if ((((j < 0) ? prev_mask : endmask) >> jj) & 1u) {
-            if (active) {
-              if (PUSH) {
-                const long long off = yrow - Y;
-#pragma unroll
-                for (int d = 0; d < kMaxPeers; ++d)
-                  if (d < peers.count) peers.p[d][off] = acc;
-              } else {
-                *yrow = acc;
-              }
-            }
+            if (active) store_row<PUSH>(a, yrow, acc);
             yrow += ldy;
             acc = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -437,105 +315,199 @@ spmm_stream2_kernel(const int *__restrict__ indptr, const int *__restrict__ indi
     my_v = nx_v;
     cbase += 32;
     if (cbase + 32 + lane < e1) {
-      nx_c = ld_stream_i32(indices + cbase + 32 + lane);
-      nx_v = ld_stream_f32(vals + cbase + 32 + lane);
+      nx_c = ld_stream_i32(a.indices + cbase + 32 + lane);
+      nx_v = ld_stream_f32(a.vals + cbase + 32 + lane);
     }
   }
   cp_async_wait<0>();
 }
 
-// tuning knobs (srg_set_tuning): which kernel serves 16 < nvec and its shape
-static int g_spmm_variant = 1;     // 0 = group kernel, 1 = stream kernel
-static int g_stream_rows = 4;      // rows per warp task
-static int g_stream_cfg = 10;      // 10/11/12: unrolled stream kernel B4/B8/B2; 0: S8/B4, 1: S8/B2, 2: S4/B2, 3: S4/B4, 4: S16/B4, 5: S16/B8, 6: S8/B1
-static int g_stream_compact = 0;   // ring slot = nvec float4 instead of 32
-static int g_gather_l2_64 = 1;     // gathers fetch 64-byte DRAM granules instead of 128-byte lines
+// ---- long rows: device-side plan, segment tasks, ordered combine ------------------------------------------
+struct LongPlan {
+  int *counts;     // [0] number of long rows, [1] number of segments
+  int *row;        // [cap_rows]   row id
+  int *first;      // [cap_rows]   first segment of the row
+  int *nseg;       // [cap_rows]   its segment count
+  int *seg_lo;     // [cap_segs]
+  int *seg_hi;     // [cap_segs]
+  float *partial;  // [cap_segs x ldp] segment sums
+  int cap_rows, cap_segs;
+  void *base;      // the single allocation behind all of the above
+};
 
-template <int S, int B, bool L2_64>
-static int launch_stream(const int *indptr, const int *indices, const float *vals, int64_t n_rows,
-                         const float4 *X, int64_t ldx, float4 *Y, int64_t ldy, int nvec,
-                         cudaStream_t s) {
-  const int R = g_stream_rows < 1 ? 1 : (g_stream_rows > 32 ? 32 : g_stream_rows);
-  const int chunks = (nvec + 31) / 32;
-  const int stride = (g_stream_compact && nvec < 32) ? nvec : 32;
-  const int64_t tasks = ceil_div64(n_rows, R) * chunks;
+__global__ void __launch_bounds__(256)
+plan_long_rows_kernel(const int *__restrict__ indptr, long long n_rows, int L, LongPlan p) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int st = indptr[r], ed = indptr[r + 1];
+  const int len = ed - st;
+  if (len <= L) return;
+  const int ns = (len + L - 1) / L;
+  const int i = atomicAdd(p.counts, 1);
+  const int s0 = atomicAdd(p.counts + 1, ns);
+  if (i >= p.cap_rows || s0 + ns > p.cap_segs) return;  // cannot happen: caps come from nnz / L
+  p.row[i] = (int)r;
+  p.first[i] = s0;
+  p.nseg[i] = ns;
+  for (int k = 0; k < ns; ++k) {
+    p.seg_lo[s0 + k] = st + k * L;
+    p.seg_hi[s0 + k] = min(ed, st + (k + 1) * L);
+  }
+}
+
+template <bool PUSH>
+__global__ void __launch_bounds__(256)
+combine_long_rows_kernel(LongPlan p, long long ldp4, float4 *Y, long long ldy, int nvec, PeerDests peers) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int n_long = min(p.counts[0], p.cap_rows);
+  const float4 *P = reinterpret_cast<const float4 *>(p.partial);
+  for (long long i = warp0; i < n_long; i += nwarps) {
+    const int row = p.row[i], s0 = p.first[i], ns = p.nseg[i];
+    for (int col = lane; col < nvec; col += 32) {
+      float4 acc = P[(long long)s0 * ldp4 + col];
+      for (int k = 1; k < ns; ++k) {
+        const float4 t = P[(long long)(s0 + k) * ldp4 + col];
+        acc.x = __fadd_rn(acc.x, t.x);
+        acc.y = __fadd_rn(acc.y, t.y);
+        acc.z = __fadd_rn(acc.z, t.z);
+        acc.w = __fadd_rn(acc.w, t.w);
+      }
+      const long long off = (long long)row * ldy + col;
+      if (PUSH) {
+        for (int d = 0; d < peers.count; ++d) peers.p[d][off] = acc;
+      } else {
+        Y[off] = acc;
+      }
+    }
+  }
+}
+
+static int alloc_long_plan(int64_t nnz, int L, int64_t ldp, LongPlan *p, cudaStream_t s) {
+  const int64_t cap_rows = nnz / L + 1, cap_segs = 2 * (nnz / L) + 2;
+  const size_t ints = 2 + 3 * (size_t)cap_rows + 2 * (size_t)cap_segs;
+  const size_t int_bytes = (ints * sizeof(int) + 255) / 256 * 256;
+  const size_t bytes = int_bytes + (size_t)cap_segs * ldp * sizeof(float);
+  char *base = nullptr;
+  SRG_CUDA(cudaMallocAsync(&base, bytes, s));
+  int *ip = reinterpret_cast<int *>(base);
+  p->base = base;
+  p->counts = ip;
+  p->row = ip + 2;
+  p->first = p->row + cap_rows;
+  p->nseg = p->first + cap_rows;
+  p->seg_lo = p->nseg + cap_rows;
+  p->seg_hi = p->seg_lo + cap_segs;
+  p->partial = reinterpret_cast<float *>(base + int_bytes);
+  p->cap_rows = (int)cap_rows;
+  p->cap_segs = (int)cap_segs;
+  SRG_CUDA(cudaMemsetAsync(p->counts, 0, 2 * sizeof(int), s));
+  return SRG_OK;
+}
+
+template <int B, bool L2_64, bool PUSH>
+static int launch_stream_t(const StreamArgs &a, int64_t blocks, cudaStream_t s) {
+  const size_t smem = (size_t)kStreamWarps * (2 * B) * 32 * sizeof(float4);
+  SRG_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<B, L2_64, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  spmm_stream_kernel<B, L2_64, PUSH><<<(unsigned)blocks, kStreamWarps * 32, smem, s>>>(a);
+  SRG_LAUNCHED();
+  return SRG_OK;
+}
+
+template <bool PUSH>
+static int launch_stream(const StreamArgs &a, int64_t max_rows, cudaStream_t s) {
+  const int64_t tasks = ceil_div64(max_rows, a.R) * a.chunks;
   const int64_t blocks = ceil_div64(tasks, kStreamWarps);
   if (blocks > 2147483647LL) {
     set_err("spmm: grid too large (%lld blocks)", (long long)blocks);
     return SRG_ERR_RANGE;
   }
-  const size_t smem = (size_t)kStreamWarps * S * stride * sizeof(float4) + (size_t)kStreamWarps * S * sizeof(float);
-  SRG_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<S, B, L2_64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  spmm_stream_kernel<S, B, L2_64><<<(unsigned)blocks, kStreamWarps * 32, smem, s>>>(
-      indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, chunks, R, stride);
-  SRG_LAUNCHED();
-  return SRG_OK;
+  if (blocks == 0) return SRG_OK;
+  if (g_stream_batch == 8)
+    return g_gather_l2_64 ? launch_stream_t<8, true, PUSH>(a, blocks, s) : launch_stream_t<8, false, PUSH>(a, blocks, s);
+  return g_gather_l2_64 ? launch_stream_t<4, true, PUSH>(a, blocks, s) : launch_stream_t<4, false, PUSH>(a, blocks, s);
 }
 
-template <int B, bool L2_64, bool PUSH = false>
-static int launch_stream2(const int *indptr, const int *indices, const float *vals, int64_t n_rows,
-                          const float4 *X, int64_t ldx, float4 *Y, int64_t ldy, int nvec,
-                          cudaStream_t s, const PeerDests *peers = nullptr) {
-  const int R = g_stream_rows < 1 ? 1 : (g_stream_rows > 32 ? 32 : g_stream_rows);
-  const int chunks = (nvec + 31) / 32;
-  const int64_t tasks = ceil_div64(n_rows, R) * chunks;
-  const int64_t blocks = ceil_div64(tasks, kStreamWarps);
-  if (blocks > 2147483647LL || ldx > 0xffffffffLL) {
-    set_err("spmm: problem too large for the stream kernel (%lld blocks, ldx %lld)", (long long)blocks, (long long)ldx);
+// one hop through the stream kernel (+ the long-row pipeline when nnz is known)
+template <bool PUSH>
+static int stream_hop(const int *indptr, const int *indices, const float *vals, int64_t n_rows, int64_t nnz,
+                      const float4 *X, int64_t ldx4, float4 *Y, int64_t ldy4, int nvec, const PeerDests *peers,
+                      cudaStream_t s) {
+  if (ldx4 > 0xffffffffLL) {
+    set_err("spmm: leading dimension too large");
     return SRG_ERR_RANGE;
   }
-  const size_t smem = (size_t)kStreamWarps * (2 * B) * 32 * sizeof(float4);
-  PeerDests pd;
-  pd.count = 0;
-  for (int d = 0; d < kMaxPeers; ++d) pd.p[d] = nullptr;
-  if (peers) pd = *peers;
-  SRG_CUDA(cudaFuncSetAttribute(spmm_stream2_kernel<B, L2_64, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  spmm_stream2_kernel<B, L2_64, PUSH><<<(unsigned)blocks, kStreamWarps * 32, smem, s>>>(
-      indptr, indices, vals, n_rows, X, (unsigned)ldx, Y, ldy, nvec, chunks, R, pd);
-  SRG_LAUNCHED();
-  return SRG_OK;
-}
-
-template <bool L2_64>
-static int dispatch_stream(const int *indptr, const int *indices, const float *vals, int64_t n_rows,
-                           const float4 *X, int64_t ldx, float4 *Y, int64_t ldy, int nvec,
-                           cudaStream_t s) {
-  switch (g_stream_cfg) {
-    case 10: return launch_stream2<4, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
-    case 11: return launch_stream2<8, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
-    case 12: return launch_stream2<2, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
-    case 1: return launch_stream<8, 2, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
-    case 2: return launch_stream<4, 2, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
-    case 3: return launch_stream<4, 4, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
-    case 4: return launch_stream<16, 4, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
-    case 5: return launch_stream<16, 8, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
-    case 6: return launch_stream<8, 1, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
-    default: return launch_stream<8, 4, L2_64>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, nvec, s);
+  StreamArgs a;
+  a.row_lo = indptr;
+  a.row_hi = indptr + 1;
+  a.indices = indices;
+  a.vals = vals;
+  a.n_rows = n_rows;
+  a.n_rows_dev = nullptr;
+  a.X = X;
+  a.ldx = (unsigned)ldx4;
+  a.Y = Y;
+  a.ldy = ldy4;
+  a.nvec = nvec;
+  a.chunks = (nvec + 31) / 32;
+  a.R = g_stream_rows < 1 ? 1 : (g_stream_rows > 32 ? 32 : g_stream_rows);
+  a.peers.count = 0;
+  for (int d = 0; d < kMaxPeers; ++d) a.peers.p[d] = nullptr;
+  if (peers) a.peers = *peers;
+  const int L = g_long_row;
+  const bool split = L > 0 && nnz > L && n_rows > 0;  // a row longer than L needs nnz > L
+  a.long_len = split ? L : 0;
+  LongPlan plan;
+  int rc;
+  if (split) {
+    const int64_t ldp = (int64_t)a.chunks * 32 * 4;  // floats per partial row (whole chunks)
+    if ((rc = alloc_long_plan(nnz, L, ldp, &plan, s))) return rc;
+    plan_long_rows_kernel<<<(unsigned)ceil_div64(n_rows, 256), 256, 0, s>>>(indptr, n_rows, L, plan);
+    SRG_LAUNCHED();
   }
+  rc = launch_stream<PUSH>(a, n_rows, s);
+  if (split && !rc) {
+    // segments as single-row tasks into the partial buffer, then the ordered combine
+    StreamArgs g = a;
+    g.row_lo = plan.seg_lo;
+    g.row_hi = plan.seg_hi;
+    g.n_rows = 0;
+    g.n_rows_dev = plan.counts + 1;
+    g.Y = reinterpret_cast<float4 *>(plan.partial);
+    g.ldy = (long long)a.chunks * 32;
+    g.R = 1;
+    g.long_len = 0;
+    g.peers.count = 0;
+    rc = launch_stream<false>(g, plan.cap_segs, s);
+    if (!rc) {
+      const int blocks = (int)std::min<int64_t>(ceil_div64((int64_t)plan.cap_rows * 32, 256), 148 * 8);
+      combine_long_rows_kernel<PUSH><<<blocks, 256, 0, s>>>(plan, (long long)a.chunks * 32, Y, ldy4, nvec, a.peers);
+      SRG_LAUNCHED();
+    }
+  }
+  if (split) cudaFreeAsync(plan.base, s);
+  return rc;
 }
 
 int spmm_csr_f32_impl(const int32_t *indptr, const int32_t *indices, const float *vals,
-                      int64_t n_rows, const float *X, int64_t ldx, float *Y, int64_t ldy,
-                      int32_t F, bool accumulate, cudaStream_t s) {
+                      int64_t n_rows, int64_t nnz, const float *X, int64_t ldx, float *Y,
+                      int64_t ldy, int32_t F, bool accumulate, cudaStream_t s) {
   SRG_REQUIRE(n_rows >= 0 && F >= 0, "spmm: negative size (n_rows=%lld, F=%d)", (long long)n_rows, F);
   if (n_rows == 0 || F == 0) return SRG_OK;
   SRG_REQUIRE(indptr && indices && vals && X && Y, "spmm: NULL pointer argument");
   SRG_REQUIRE(ldx >= F && ldy >= F, "spmm: leading dimension smaller than F (ldx=%lld ldy=%lld F=%d)",
               (long long)ldx, (long long)ldy, F);
   SRG_REQUIRE(X != Y, "spmm: in-place hop (X == Y) is not supported");
-  const bool vec_ok = (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)X % 16 == 0) &&
-                      ((uintptr_t)Y % 16 == 0);
+  const bool vec_ok = (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0);
   if (vec_ok) {
     const int nvec = (F + 3) / 4;
     const float4 *X4 = reinterpret_cast<const float4 *>(X);
     float4 *Y4 = reinterpret_cast<float4 *>(Y);
-    if (!accumulate && g_spmm_variant == 1 && nvec > 16) {
-      return g_gather_l2_64 ? dispatch_stream<true>(indptr, indices, vals, n_rows, X4, ldx / 4, Y4, ldy / 4, nvec, s)
-                            : dispatch_stream<false>(indptr, indices, vals, n_rows, X4, ldx / 4, Y4, ldy / 4, nvec, s);
-    }
-    return accumulate
-               ? dispatch_group<float4, true>(indptr, indices, vals, n_rows, X4, ldx / 4, Y4, ldy / 4, nvec, s)
-               : dispatch_group<float4, false>(indptr, indices, vals, n_rows, X4, ldx / 4, Y4, ldy / 4, nvec, s);
+    if (!accumulate && g_spmm_variant == 1 && nvec > 16)
+      return stream_hop<false>(indptr, indices, vals, n_rows, nnz, X4, ldx / 4, Y4, ldy / 4, nvec, nullptr, s);
+    return accumulate ? dispatch_group<float4, true>(indptr, indices, vals, n_rows, X4, ldx / 4, Y4, ldy / 4, nvec, s)
+                      : dispatch_group<float4, false>(indptr, indices, vals, n_rows, X4, ldx / 4, Y4, ldy / 4, nvec, s);
   }
   return accumulate ? dispatch_group<float, true>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, F, s)
                     : dispatch_group<float, false>(indptr, indices, vals, n_rows, X, ldx, Y, ldy, F, s);
@@ -580,15 +552,11 @@ extern "C" int srg_set_tuning(const char *key, int64_t value) {
   const std::string k(key);
   if (k == "spmm_variant") g_spmm_variant = (int)value;
   else if (k == "stream_rows") g_stream_rows = (int)value;
+  else if (k == "stream_batch") g_stream_batch = (int)value;
   else if (k == "group_unroll") g_group_unroll = (int)value;
   else if (k == "gather_l2_64") g_gather_l2_64 = (int)value;
-  else if (k == "stream_compact") g_stream_compact = (int)value;
-  else if (k == "stream_cfg") g_stream_cfg = (int)value;
-  else if (k == "l2_fetch_granularity") {
-    int rc = require_device();
-    if (rc) return rc;
-    SRG_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
-  } else {
+  else if (k == "long_row") g_long_row = (int)value;
+  else {
     set_err("set_tuning: unknown key '%s'", key);
     return SRG_ERR_INVALID;
   }
@@ -596,26 +564,51 @@ extern "C" int srg_set_tuning(const char *key, int64_t value) {
 }
 
 extern "C" int srg_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
-                                int64_t n_rows, const float *X, int64_t ldx, float *Y, int64_t ldy,
-                                int32_t F, void *stream) {
+                                int64_t n_rows, int64_t nnz, const float *X, int64_t ldx, float *Y,
+                                int64_t ldy, int32_t F, void *stream) {
   int rc = require_device();
   if (rc) return rc;
-  return spmm_csr_f32_impl(indptr, indices, vals, n_rows, X, ldx, Y, ldy, F, false, as_stream(stream));
+  return spmm_csr_f32_impl(indptr, indices, vals, n_rows, nnz, X, ldx, Y, ldy, F, false, as_stream(stream));
 }
 
 extern "C" int srg_propagate_khop_f32(const int32_t *indptr, const int32_t *indices,
-                                      const float *vals, int64_t n, float *const *hops, int64_t ld,
-                                      int32_t F, int32_t K, void *stream) {
+                                      const float *vals, int64_t n, int64_t nnz, float *const *hops,
+                                      int64_t ld, int32_t F, int32_t K, void *stream) {
   int rc = require_device();
   if (rc) return rc;
   SRG_REQUIRE(K >= 0, "propagate: K must be >= 0 (got %d)", K);
   SRG_REQUIRE(hops != nullptr, "propagate: hops is NULL");
   for (int k = 1; k <= K; ++k) {
-    rc = spmm_csr_f32_impl(indptr, indices, vals, n, hops[k - 1], ld, hops[k], ld, F, false,
-                           as_stream(stream));
+    rc = spmm_csr_f32_impl(indptr, indices, vals, n, nnz, hops[k - 1], ld, hops[k], ld, F, false, as_stream(stream));
     if (rc) return rc;
   }
   return SRG_OK;
+}
+
+extern "C" int srg_spmm_csr_f32_push(const int32_t *indptr, const int32_t *indices, const float *vals,
+                                     int64_t n_rows, int64_t nnz, const float *X, int64_t ldx,
+                                     float *const *dests, int32_t n_dests, int64_t dest_row0, int64_t ldy,
+                                     int32_t F, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n_rows >= 0 && F >= 0 && dest_row0 >= 0, "spmm_push: negative size");
+  SRG_REQUIRE(n_dests >= 1 && n_dests <= kMaxPeers, "spmm_push: n_dests must be 1..%d", kMaxPeers);
+  if (n_rows == 0 || F == 0) return SRG_OK;
+  SRG_REQUIRE(indptr && indices && vals && X && dests, "spmm_push: NULL pointer");
+  SRG_REQUIRE(ldx >= F && ldy >= F && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)X % 16 == 0,
+              "spmm_push: needs ld %% 4 == 0 and 16-byte aligned matrices");
+  const int nvec = (F + 3) / 4;
+  PeerDests pd;
+  pd.count = n_dests;
+  for (int d = 0; d < kMaxPeers; ++d) pd.p[d] = nullptr;
+  for (int d = 0; d < n_dests; ++d) {
+    SRG_REQUIRE(dests[d] && (uintptr_t)dests[d] % 16 == 0, "spmm_push: dests[%d] NULL or unaligned", d);
+    SRG_REQUIRE((const float *)dests[d] != X, "spmm_push: destination aliases the input");
+    pd.p[d] = reinterpret_cast<float4 *>(dests[d]) + dest_row0 * (ldy / 4);
+  }
+  // Y is only the origin the kernel measures row offsets from
+  return stream_hop<true>(indptr, indices, vals, n_rows, nnz, reinterpret_cast<const float4 *>(X), ldx / 4, pd.p[0],
+                          ldy / 4, nvec, &pd, as_stream(stream));
 }
 
 extern "C" int srg_pack_features_f32(const float *src, int64_t ld_src, float *dst, int64_t ld_dst,
@@ -650,37 +643,6 @@ extern "C" int srg_apply_feature_mask_f32(const float *x, int64_t ld_x, const in
                                           int64_t ld_out, int64_t n, int32_t F, void *stream) {
   SRG_REQUIRE(mask != nullptr, "apply_feature_mask: mask is NULL");
   return srg_pack_features_f32(x, ld_x, out, ld_out, n, F, mask, stream);
-}
-
-// ---- multi-GPU push hop -------------------------------------------------------------------------------
-extern "C" int srg_spmm_csr_f32_push(const int32_t *indptr, const int32_t *indices, const float *vals,
-                                     int64_t n_rows, const float *X, int64_t ldx, float *const *dests,
-                                     int32_t n_dests, int64_t dest_row0, int64_t ldy, int32_t F,
-                                     void *stream) {
-  int rc = require_device();
-  if (rc) return rc;
-  SRG_REQUIRE(n_rows >= 0 && F >= 0 && dest_row0 >= 0, "spmm_push: negative size");
-  SRG_REQUIRE(n_dests >= 1 && n_dests <= kMaxPeers, "spmm_push: n_dests must be 1..%d", kMaxPeers);
-  if (n_rows == 0 || F == 0) return SRG_OK;
-  SRG_REQUIRE(indptr && indices && vals && X && dests, "spmm_push: NULL pointer");
-  SRG_REQUIRE(ldx >= F && ldy >= F && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)X % 16 == 0,
-              "spmm_push: needs ld %% 4 == 0 and 16-byte aligned matrices");
-  const int nvec = (F + 3) / 4;
-  PeerDests pd;
-  pd.count = n_dests;
-  for (int d = 0; d < kMaxPeers; ++d) pd.p[d] = nullptr;
-  for (int d = 0; d < n_dests; ++d) {
-    SRG_REQUIRE(dests[d] && (uintptr_t)dests[d] % 16 == 0, "spmm_push: dests[%d] NULL or unaligned", d);
-    SRG_REQUIRE((const float *)dests[d] != X, "spmm_push: destination aliases the input");
-    pd.p[d] = reinterpret_cast<float4 *>(dests[d]) + dest_row0 * (ldy / 4);
-  }
-  // Y is only the origin the kernel measures row offsets from
-  float4 *origin = pd.p[0];
-  if (g_gather_l2_64)
-    return launch_stream2<4, true, true>(indptr, indices, vals, n_rows, reinterpret_cast<const float4 *>(X), ldx / 4,
-                                         origin, ldy / 4, nvec, as_stream(stream), &pd);
-  return launch_stream2<4, false, true>(indptr, indices, vals, n_rows, reinterpret_cast<const float4 *>(X), ldx / 4,
-                                        origin, ldy / 4, nvec, as_stream(stream), &pd);
 }
 
 // ---- peer-mapped buffers (CUDA IPC) for the push hop ---------------------------------------------------

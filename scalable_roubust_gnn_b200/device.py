@@ -35,7 +35,12 @@ class DeviceCSR:
     indices: torch.Tensor           # int32 [>= nnz]
     data: torch.Tensor | None       # float32 / float64 [>= nnz] or None (all ones)
     n: int
-    nnz: int                        # -1 when only known on the device (indptr[n])
+    nnz: int                        # stored entries, or an upper bound (see nnz_bound)
+
+    @property
+    def nnz_bound(self) -> int:
+        """Upper bound of indptr[n] that is known on the host (the capacity of the arrays)."""
+        return int(self.nnz) if self.nnz >= 0 else int(self.indices.numel())
 
     @property
     def val_dtype(self) -> int:
@@ -103,7 +108,7 @@ def sym_norm(a: DeviceCSR, r: float, ppr_alpha: float | None = None, want_f64=Fa
     alpha = -1.0 if ppr_alpha is None else float(ppr_alpha)
     _lib.check(lib.srg_sym_norm_csr(_p(a.indptr), _p(a.indices), _p(a.data), a.val_dtype, n, nnz, _p(o_indptr),
                                     float(r), alpha, _p(o_indices), _p(o_deg), _p(o_val64), _p(o_val32), _p(flags), s))
-    out = DeviceCSR(o_indptr, o_indices, o_val32, n, -1)
+    out = DeviceCSR(o_indptr, o_indices, o_val32, n, nnz + n)   # nnz: upper bound (exact count stays on the device)
     return out, flags, {"val64": o_val64, "degree": o_deg, "count": o_count}
 
 
@@ -116,8 +121,8 @@ def spmm(a: DeviceCSR, x: torch.Tensor, f: int | None = None, out: torch.Tensor 
     rows = a.n if n_rows is None else n_rows
     if out is None:
         out = torch.empty((rows, x.shape[1]), dtype=torch.float32, device=x.device)
-    _lib.check(lib.srg_spmm_csr_f32(_p(a.indptr), _p(a.indices), _p(a.data), rows, _p(x), x.stride(0), _p(out),
-                                    out.stride(0), f, _stream_ptr(x.device)))
+    _lib.check(lib.srg_spmm_csr_f32(_p(a.indptr), _p(a.indices), _p(a.data), rows, a.nnz_bound, _p(x), x.stride(0),
+                                    _p(out), out.stride(0), f, _stream_ptr(x.device)))
     return out
 
 
@@ -128,6 +133,6 @@ def propagate(a_norm: DeviceCSR, x0: torch.Tensor, f: int, k: int, hops: list | 
     if hops is None:
         hops = [x0] + [torch.empty_like(x0) for _ in range(k)]
     ptrs = (C.c_void_p * (k + 1))(*[h.data_ptr() for h in hops])
-    _lib.check(lib.srg_propagate_khop_f32(_p(a_norm.indptr), _p(a_norm.indices), _p(a_norm.data), n, ptrs, ld, f, k,
-                                          _stream_ptr(x0.device)))
+    _lib.check(lib.srg_propagate_khop_f32(_p(a_norm.indptr), _p(a_norm.indices), _p(a_norm.data), n, a_norm.nnz_bound,
+                                          ptrs, ld, f, k, _stream_ptr(x0.device)))
     return hops

@@ -185,13 +185,15 @@ class DeviceOps:
         if st.mode == "push" and st.world > 1:
             dests = (C.c_void_p * st.world)(*st.peer_ptrs[i_out])
             _lib.check(st.lib.srg_spmm_csr_f32_push(_p(local_norm.indptr), _p(local_norm.indices), _p(local_norm.data),
-                                                    st.n_local, _p(xin), st.ld, dests, st.world, st.row0, st.ld, st.f,
+                                                    st.n_local, local_norm.nnz_bound, _p(xin), st.ld, dests, st.world,
+                                                    st.row0, st.ld, st.f,
                                                     _stream_ptr(st.device)))
             self._pushed = True
         else:
             out = st.full[i_out][st.row0:st.row0 + st.n_local]
             _lib.check(st.lib.srg_spmm_csr_f32(_p(local_norm.indptr), _p(local_norm.indices), _p(local_norm.data),
-                                               st.n_local, _p(xin), st.ld, _p(out), st.ld, st.f, _stream_ptr(st.device)))
+                                               st.n_local, local_norm.nnz_bound, _p(xin), st.ld, _p(out), st.ld, st.f,
+                                               _stream_ptr(st.device)))
             self._pushed = False
 
     def snapshot_local(self, i):
@@ -255,4 +257,4 @@ def dist_sym_norm(st: DistState, a_local, r, ppr_alpha=None):
     alpha = -1.0 if ppr_alpha is None else float(ppr_alpha)
     _lib.check(lib.srg_norm_values_rows_csr(_p(at_indptr), _p(at_indices), _p(at_val), _p(deg_loc), n_loc, st.row0,
                                             _p(dl), _p(dr), alpha, 0, None, _p(val32), _p(flags), s))
-    return DeviceCSR(at_indptr, at_indices, val32, n_loc, -1), flags
+    return DeviceCSR(at_indptr, at_indices, val32, n_loc, nnz + n_loc), flags

@@ -59,18 +59,15 @@ def run(tag, ld, **kw):
     results.append({"tag": tag, "ld": ld, "ms_min": tmin, "ms_avg": tavg, "gbs": gbs, "exact": ok, **kw})
 
 ld0 = dev.pad_ld(f)
-run("group U8 (v0)", ld0, spmm_variant=0, group_unroll=8)
 run("group U4", ld0, spmm_variant=0, group_unroll=4)
-names = {0: "S8/B4", 1: "S8/B2", 2: "S4/B2", 3: "S4/B4", 4: "S16/B4", 5: "S16/B8", 6: "S8/B1"}
-run("stream S8/B4 R4 (old)", ld0, spmm_variant=1, stream_cfg=0, stream_rows=4, gather_l2_64=1, stream_compact=0)
-names2 = {10: "B4", 11: "B8", 12: "B2"}
-for l2 in (1, 0):
-    for cfg, rows in itertools.product([10, 11, 12], [4, 8, 16, 32]):
-        run(f"stream2 {names2[cfg]} R{rows} l2_64={l2}", ld0, spmm_variant=1, stream_cfg=cfg, stream_rows=rows, gather_l2_64=l2, stream_compact=0)
-run("stream S8/B4 R4 (old, again)", ld0, spmm_variant=1, stream_cfg=0, stream_rows=4, gather_l2_64=1, stream_compact=0)
+run("group U8", ld0, spmm_variant=0, group_unroll=8)
+for l2, batch, rows in itertools.product((1, 0), (4, 8), (2, 4, 8, 16)):
+    run(f"stream B{batch} R{rows} l2_64={l2}", ld0, spmm_variant=1, stream_batch=batch, stream_rows=rows, gather_l2_64=l2)
 best = min((r for r in results if r.get("spmm_variant") == 1), key=lambda r: r["ms_avg"])
 print("best stream:", best, flush=True)
-kw = {kk: best[kk] for kk in ("spmm_variant", "stream_cfg", "stream_rows", "gather_l2_64", "stream_compact")}
+kw = {kk: best[kk] for kk in ("spmm_variant", "stream_batch", "stream_rows", "gather_l2_64")}
 for ld in sorted({f if f % 4 == 0 else ld0, ld0, (f + 15) // 16 * 16, (f + 31) // 32 * 32}):
     run("best stream, ld sweep", ld, **kw)
+for lr in (0, 256, 1024, 4096):
+    run(f"best stream, long_row={lr}", ld0, long_row=lr, **kw)
 json.dump(results, open("gpurun_out/tune_spmm.json", "w"), indent=1)

@@ -14,6 +14,8 @@
 // reference's multiply order.  The only non-reproducible step of the reference is np.power,
 // whose last bit depends on the host's libm / SVML build; here the common exponents
 // (0, +-0.5, +-1) are correctly rounded and the rest use CUDA pow (<= 2 ulp).
+#include <algorithm>
+
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -43,31 +45,45 @@ __device__ __forceinline__ void raise_flags(int *flags, int fl) {
 }
 
 // ---- stage 1: row lengths of A~ for the rows [row0, row0 + n_rows) of an n_cols-column matrix --
+// One warp per row (grid-stride), lanes stride over the entries: coalesced for short rows and
+// 32-way parallel inside a power-law hub row.
+constexpr int kNormBlocks = 148 * 8;
+
 template <int DT>
 __global__ void __launch_bounds__(256)
 rows_count_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
                   const void *__restrict__ data, long long n_rows, long long row0, long long n_cols,
                   int *__restrict__ rowlen, int *__restrict__ flags) {
-  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_rows) return;
-  const int ag = (int)(a + row0);
-  const int s = indptr[a], e = indptr[a + 1];
-  int cnt = 0, prev = -1, fl = 0;
-  double diag = 0.0;
-  for (int j = s; j < e; ++j) {
-    const int b = indices[j];
-    if (b <= prev) fl |= SRG_FLAG_UNSORTED;
-    if (b < 0 || b >= n_cols) fl |= SRG_FLAG_BAD_INDEX;
-    prev = b;
-    const double v = ValLoad<DT>::at(data, j);
-    if (DT != SRG_VAL_ONES && v != 1.0) fl |= kWeighted;
-    if (b == ag)
-      diag = v;
-    else if (v != 0.0)
-      ++cnt;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  int fl = 0;
+  for (long long a = warp0; a < n_rows; a += nwarps) {
+    const int ag = (int)(a + row0);
+    const int s = indptr[a], e = indptr[a + 1];
+    int cnt = 0;
+    bool has_diag = false;
+    double diag = 0.0;
+    for (int j = s + lane; j < e; j += 32) {
+      const int b = indices[j];
+      const int pb = (j > s) ? indices[j - 1] : -1;
+      if (b <= pb) fl |= SRG_FLAG_UNSORTED;
+      if (b < 0 || b >= n_cols) fl |= SRG_FLAG_BAD_INDEX;
+      const double v = ValLoad<DT>::at(data, j);
+      if (DT != SRG_VAL_ONES && v != 1.0) fl |= kWeighted;
+      if (b == ag) {
+        has_diag = true;
+        diag = v;
+      } else if (v != 0.0) {
+        ++cnt;
+      }
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    const unsigned dm = __ballot_sync(0xffffffffu, has_diag);
+    if (dm) diag = __shfl_sync(0xffffffffu, diag, __ffs(dm) - 1);
+    if (__dadd_rn(diag, 1.0) != 0.0) ++cnt;
+    if (lane == 0) rowlen[a] = cnt;
   }
-  if (__dadd_rn(diag, 1.0) != 0.0) ++cnt;
-  rowlen[a] = cnt;
   raise_flags(flags, fl);
 }
 
@@ -131,6 +147,9 @@ __device__ double pow_tab(double x, double e) {
 }
 
 // ---- stage 2a: write A~ (indices, and values when the graph is weighted) and the row degree ------
+// One warp per row (grid-stride).  Pass A finds the diagonal value of A and how many kept entries
+// precede the diagonal; pass B compacts the kept entries with ballot ranks, leaving the slot of the
+// diagonal of A~ = A + I free for lane 0.
 template <int DT>
 __global__ void __launch_bounds__(256)
 rows_fill_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
@@ -138,55 +157,70 @@ rows_fill_kernel(const int *__restrict__ indptr, const int *__restrict__ indices
                  const int *__restrict__ at_indptr, int *__restrict__ at_indices,
                  double *__restrict__ at_val, double *__restrict__ degree,
                  const int *__restrict__ flags, int force_vals) {
-  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_rows) return;
   const bool weighted = (DT != SRG_VAL_ONES) && (force_vals || (*flags & kWeighted));
-  const int ag = (int)(a + row0);
-  const int s = indptr[a], e = indptr[a + 1];
-  const int p0 = at_indptr[a];
-  int p = p0;
-  bool placed = false;
-  double diag_a = 0.0;
-  if (DT != SRG_VAL_ONES || true) {
-    for (int j = s; j < e; ++j)
-      if (indices[j] == ag) diag_a = ValLoad<DT>::at(data, j);
-  }
-  const double diag = __dadd_rn(diag_a, 1.0);
-  for (int j = s; j < e; ++j) {
-    const int b = indices[j];
-    if (b == ag) continue;
-    if (!placed && b > ag) {
-      placed = true;
-      if (diag != 0.0) {
-        at_indices[p] = ag;
-        if (weighted) at_val[p] = diag;
-        ++p;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long a = warp0; a < n_rows; a += nwarps) {
+    const int ag = (int)(a + row0);
+    const int s = indptr[a], e = indptr[a + 1];
+    const int p0 = at_indptr[a];
+    // pass A
+    int cnt_lt = 0;
+    bool has_diag = false;
+    double diag_a = 0.0;
+    for (int j = s + lane; j < e; j += 32) {
+      const int b = indices[j];
+      const double v = ValLoad<DT>::at(data, j);
+      if (b == ag) {
+        has_diag = true;
+        diag_a = v;
+      } else if (b < ag && v != 0.0) {
+        ++cnt_lt;
       }
     }
-    const double v = ValLoad<DT>::at(data, j);
-    if (v != 0.0) {
-      at_indices[p] = b;
-      if (weighted) at_val[p] = v;
-      ++p;
+    cnt_lt = __reduce_add_sync(0xffffffffu, cnt_lt);
+    const unsigned dm = __ballot_sync(0xffffffffu, has_diag);
+    if (dm) diag_a = __shfl_sync(0xffffffffu, diag_a, __ffs(dm) - 1);
+    const double diag = __dadd_rn(diag_a, 1.0);
+    const int keepd = (diag != 0.0) ? 1 : 0;
+    // pass B
+    int base = p0;
+    for (int j0 = s; j0 < e; j0 += 32) {
+      const int j = j0 + lane;
+      const bool valid = j < e;
+      const int b = valid ? indices[j] : 0;
+      const double v = valid ? ValLoad<DT>::at(data, j) : 0.0;
+      const bool keep = valid && b != ag && v != 0.0;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int pos = base + __popc(m & lt_mask) + ((b > ag) ? keepd : 0);
+        at_indices[pos] = b;
+        if (weighted) at_val[pos] = v;
+      }
+      base += __popc(m);
+    }
+    const int len = (base - p0) + keepd;
+    if (lane == 0 && keepd) {
+      at_indices[p0 + cnt_lt] = ag;
+      if (weighted) at_val[p0 + cnt_lt] = diag;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double d;
+      if (!weighted) {
+        d = (len == 0) ? 0.0 : (double)(len - 1) + diag;  // entries 1.0, diagonal 1.0 or 2.0: exact
+      } else if (len == 0) {
+        d = 0.0;
+      } else if (len == 1) {
+        d = at_val[p0];
+      } else {
+        d = __dadd_rn(at_val[p0], np_pairwise_sum(at_val + p0 + 1, len - 1));
+      }
+      degree[a] = d;
     }
   }
-  if (!placed && diag != 0.0) {
-    at_indices[p] = ag;
-    if (weighted) at_val[p] = diag;
-    ++p;
-  }
-  const int len = p - p0;
-  double d;
-  if (!weighted) {
-    d = (double)(len - 1) + diag;  // entries are 1.0, the diagonal 1.0 or 2.0: exact in any order
-  } else if (len == 0) {
-    d = 0.0;
-  } else if (len == 1) {
-    d = at_val[p0];
-  } else {
-    d = __dadd_rn(at_val[p0], np_pairwise_sum(at_val + p0 + 1, len - 1));
-  }
-  degree[a] = d;
 }
 
 __global__ void __launch_bounds__(256)
@@ -293,7 +327,7 @@ __global__ void tri_compare_kernel(const unsigned long long *tri_counts, int *fl
 
 int rows_count_launch(const int32_t *indptr, const int32_t *indices, const void *data, int dt, int64_t n_rows,
                       int64_t row0, int64_t n_cols, int32_t *rowlen, int32_t *flags, cudaStream_t s) {
-  const unsigned blocks = (unsigned)ceil_div64(n_rows, 256);
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(n_rows * 32, 256), kNormBlocks);
   SRG_DT_SWITCH(dt, (rows_count_kernel<DTT><<<blocks, 256, 0, s>>>(indptr, indices, data, n_rows, row0, n_cols, rowlen, flags)));
   SRG_LAUNCHED();
   return SRG_OK;
@@ -302,7 +336,7 @@ int rows_count_launch(const int32_t *indptr, const int32_t *indices, const void 
 int rows_fill_launch(const int32_t *indptr, const int32_t *indices, const void *data, int dt, int64_t n_rows,
                      int64_t row0, const int32_t *at_indptr, int32_t *at_indices, double *at_val,
                      double *degree, const int32_t *flags, int force_vals, cudaStream_t s) {
-  const unsigned blocks = (unsigned)ceil_div64(n_rows, 256);
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(n_rows * 32, 256), kNormBlocks);
   SRG_DT_SWITCH(dt, (rows_fill_kernel<DTT><<<blocks, 256, 0, s>>>(indptr, indices, data, n_rows, row0, at_indptr, at_indices, at_val, degree, flags, force_vals)));
   SRG_LAUNCHED();
   return SRG_OK;

@@ -52,6 +52,7 @@ extern "C" {
 #define SRG_VAL_ONES 0 /* data == NULL, every stored entry is 1.0 (unweighted graph) */
 #define SRG_VAL_F32 1
 #define SRG_VAL_F64 2
+#define SRG_VAL_HAS_ZEROS 0x100 /* OR into val_dtype: the value array may hold explicit zeros (compacting kernels) */
 
 /* bits reported in the int32 flags word written by the normalisation entry points */
 #define SRG_FLAG_UNSORTED 1       /* input rows not strictly increasing (duplicates / unsorted)      */
@@ -59,6 +60,7 @@ extern "C" {
 #define SRG_FLAG_ZERO_PRODUCT 4   /* a normalised value is exactly 0: scipy would drop the entry     */
 #define SRG_FLAG_BAD_INDEX 8      /* a column index is outside [0, n)                                */
 #define SRG_FLAG_WEIGHTED 16      /* informational: some stored value differs from 1.0              */
+#define SRG_FLAG_EXPLICIT_ZERO 32  /* a stored value is exactly 0: retry with SRG_VAL_HAS_ZEROS          */
 
 /* ---- library / diagnostics ------------------------------------------------------------- */
 int srg_abi_version(void);
@@ -81,11 +83,15 @@ int srg_set_tuning(const char *key, int64_t value);
  *   out_count[n]    : nullable; entries per row of A~ (= integer degree incl. the self loop for
  *                     an unweighted graph)
  *   out_flags       : device int32, OR of SRG_FLAG_* (caller zeroes it)
- * Allocates scan scratch with cudaMallocAsync on `stream`.
+ *   nnz             : upper bound of indptr[n] (sizes the hub-row segment list without a readback)
+ * Rows longer than 1024 entries (power-law hubs) are processed as 1024-entry segments by separate
+ * warps.  The fast kernels require a canonical CSR without explicit zeros and raise
+ * SRG_FLAG_UNSORTED / SRG_FLAG_EXPLICIT_ZERO otherwise (retry after srg_csr_canonicalize / with
+ * val_dtype | SRG_VAL_HAS_ZEROS).  Allocates scratch with cudaMallocAsync on `stream`.
  */
 int srg_degree_selfloop_csr(const int32_t *indptr, const int32_t *indices, const void *data,
-                            int val_dtype, int64_t n, int32_t *out_indptr, int32_t *out_count,
-                            int32_t *out_flags, void *stream);
+                            int val_dtype, int64_t n, int64_t nnz, int32_t *out_indptr,
+                            int32_t *out_count, int32_t *out_flags, void *stream);
 
 /*
  * Stage 2.  R = D^(r-1) A~^T D^(-r)   (R[a,b] = (A~[b,a] * d_a^(r-1)) * d_b^(-r), fp64, this
@@ -119,17 +125,18 @@ int srg_sym_norm_csr(const int32_t *indptr, const int32_t *indices, const void *
  *                              SRG_FLAG_ASYMMETRIC otherwise; without it symmetry is the caller's promise.
  */
 int srg_selfloop_rows_csr(const int32_t *indptr, const int32_t *indices, const void *data,
-                          int val_dtype, int64_t n_rows, int64_t row0, int64_t n_cols,
+                          int val_dtype, int64_t n_rows, int64_t nnz, int64_t row0, int64_t n_cols,
                           int32_t *out_indptr, int32_t *out_count, int32_t *out_flags, void *stream);
 int srg_selfloop_fill_rows_csr(const int32_t *indptr, const int32_t *indices, const void *data,
-                               int val_dtype, int64_t n_rows, int64_t row0, int64_t n_cols,
-                               const int32_t *at_indptr, int32_t *at_indices, double *at_val,
-                               double *out_degree, const int32_t *flags, void *stream);
+                               int val_dtype, int64_t n_rows, int64_t nnz, int64_t row0,
+                               int64_t n_cols, const int32_t *at_indptr, int32_t *at_indices,
+                               double *at_val, double *out_degree, const int32_t *flags, void *stream);
 int srg_pow_tables_f64(const double *degree, int64_t n, double r, double *out_left,
                        double *out_right, void *stream);
 int srg_norm_values_rows_csr(const int32_t *at_indptr, const int32_t *at_indices,
                              const double *at_val, const double *degree_rows, int64_t n_rows,
-                             int64_t row0, const double *pow_left, const double *pow_right,
+                             int64_t nnz, int64_t row0, int64_t n_cols, const double *pow_left,
+                             const double *pow_right,
                              double ppr_alpha, int check_symmetry, double *out_val_f64,
                              float *out_val_f32, int32_t *flags, void *stream);
 

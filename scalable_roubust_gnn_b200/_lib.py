@@ -25,6 +25,8 @@ SRG_ERR_UNSUPPORTED = -95
 
 SRG_VAL_ONES, SRG_VAL_F32, SRG_VAL_F64 = 0, 1, 2
 SRG_FLAG_UNSORTED, SRG_FLAG_ASYMMETRIC, SRG_FLAG_ZERO_PRODUCT, SRG_FLAG_BAD_INDEX, SRG_FLAG_WEIGHTED = 1, 2, 4, 8, 16
+SRG_FLAG_EXPLICIT_ZERO = 32
+SRG_VAL_HAS_ZEROS = 0x100
 
 
 class SrgError(RuntimeError):
@@ -49,12 +51,12 @@ SIGNATURES = {
     "srg_device_count": (C.c_int, []),
     "srg_launch_count": (_i64, []),
     "srg_set_tuning": (C.c_int, [C.c_char_p, _i64]),
-    "srg_degree_selfloop_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp]),
+    "srg_degree_selfloop_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp]),
     "srg_sym_norm_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "srg_selfloop_rows_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
-    "srg_selfloop_fill_rows_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "srg_selfloop_rows_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "srg_selfloop_fill_rows_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "srg_pow_tables_f64": (C.c_int, [_vp, _i64, _f64, _vp, _vp, _vp]),
-    "srg_norm_values_rows_csr": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _f64, C.c_int, _vp, _vp, _vp, _vp]),
+    "srg_norm_values_rows_csr": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _f64, C.c_int, _vp, _vp, _vp, _vp]),
     "srg_sym_norm_csr_general": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "srg_csr_canonicalize": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "srg_edge_gather_i64": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),

@@ -296,7 +296,7 @@ extern "C" int srg_csr_canonicalize(const int32_t *indptr, const int32_t *indice
 namespace srg {
 // defined in norm.cu: fills A~ (pattern, values), degree and the power tables
 int selfloop_fill_dispatch(const int32_t *indptr, const int32_t *indices, const void *data, int val_dtype,
-                           int64_t n, const int32_t *at_indptr, int32_t *at_indices, double *at_val,
+                           int64_t n, int64_t nnz, const int32_t *at_indptr, int32_t *at_indices, double *at_val,
                            double *degree, double *dl, double *dr, double r, const int32_t *flags,
                            cudaStream_t s);
 }  // namespace srg
@@ -312,7 +312,7 @@ extern "C" int srg_sym_norm_csr_general(const int32_t *indptr, const int32_t *in
   SRG_REQUIRE(n >= 0 && nnz >= 0, "sym_norm_general: negative size");
   if (n == 0) return SRG_OK;
   SRG_REQUIRE(indptr && indices && at_indptr && out_indptr && out_indices && out_flags, "sym_norm_general: NULL pointer");
-  SRG_REQUIRE(val_dtype >= 0 && val_dtype <= 2, "sym_norm_general: bad val_dtype");
+  SRG_REQUIRE((val_dtype & 0xff) <= 2, "sym_norm_general: bad val_dtype");
   SRG_REQUIRE(nnz + n <= 2147483647LL, "sym_norm_general: nnz + n exceeds the int32 CSR range");
   cudaStream_t s = as_stream(stream);
   const int64_t cap = nnz + n;
@@ -326,10 +326,10 @@ extern "C" int srg_sym_norm_csr_general(const int32_t *indptr, const int32_t *in
   double *deg = out_degree ? out_degree : dscratch;
   double *dl = dscratch + n, *dr = dscratch + 2 * n;
   double *at_val = dscratch + 3 * n, *vals = at_val + cap;
-  rc = selfloop_fill_dispatch(indptr, indices, data, val_dtype, n, at_indptr, at_indices, at_val, deg, dl, dr, r, out_flags, s);
+  rc = selfloop_fill_dispatch(indptr, indices, data, val_dtype, n, nnz, at_indptr, at_indices, at_val, deg, dl, dr, r, out_flags, s);
   if (!rc) {
     general_norm_vals_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, s>>>(
-        at_indptr, at_indices, at_val, deg, n, dl, dr, keys, vals, val_dtype == SRG_VAL_ONES ? 1 : 0);
+        at_indptr, at_indices, at_val, deg, n, dl, dr, keys, vals, (val_dtype & 0xff) == SRG_VAL_ONES ? 1 : 0);
     SRG_LAUNCHED();
   }
   // The number of A~ entries is only known on the device (at_indptr[n]): this directed-graph path

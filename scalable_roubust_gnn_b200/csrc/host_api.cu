@@ -127,7 +127,7 @@ static int check_flags(int flags) {
     set_err("adjacency has a column index outside [0, n)");
     return SRG_ERR_INVALID;
   }
-  if (flags & (SRG_FLAG_UNSORTED | SRG_FLAG_ASYMMETRIC)) {
+  if (flags & (SRG_FLAG_UNSORTED | SRG_FLAG_ASYMMETRIC | SRG_FLAG_EXPLICIT_ZERO)) {
     set_err("internal: normalisation retry did not resolve flags 0x%x", flags);
     return SRG_ERR_CUDA;
   }
@@ -148,8 +148,9 @@ struct NormOut {
 
 static int run_norm(PoolAllocs &pa, const int32_t *d_indptr, const int32_t *d_indices,
                     const void *d_data, int val_dtype, int64_t n, int64_t nnz, double r,
-                    double ppr_alpha, bool want64, bool want32, cudaStream_t s, bool canon,
-                    bool general, NormOut *o) {
+                    double ppr_alpha, bool want64, bool want32, cudaStream_t s, int mode,
+                    NormOut *o) {
+  const bool canon = mode & 1, general = mode & 2, zeros = mode & 4;
   int rc;
   if ((rc = pa.alloc(&o->flags, 1))) return rc;
   SRG_CUDA(cudaMemsetAsync(o->flags, 0, sizeof(int32_t), s));
@@ -169,12 +170,13 @@ static int run_norm(PoolAllocs &pa, const int32_t *d_indptr, const int32_t *d_in
     d_data = c_vals;
     val_dtype = SRG_VAL_F64;
   }
+  if (zeros) val_dtype |= SRG_VAL_HAS_ZEROS;  // explicit zeros: the compacting kernels
   int32_t *at_indptr;
   if ((rc = pa.alloc(&at_indptr, n + 1))) return rc;
   if ((rc = pa.alloc(&o->indices, nnz + n))) return rc;
   if (want64 && (rc = pa.alloc(&o->val64, nnz + n))) return rc;
   if (want32 && (rc = pa.alloc(&o->val32, nnz + n))) return rc;
-  rc = srg_degree_selfloop_csr(d_indptr, d_indices, d_data, val_dtype, n, at_indptr, nullptr, o->flags, s);
+  rc = srg_degree_selfloop_csr(d_indptr, d_indices, d_data, val_dtype, n, nnz, at_indptr, nullptr, o->flags, s);
   if (rc) return rc;
   if (!general) {
     o->indptr = at_indptr;
@@ -187,17 +189,16 @@ static int run_norm(PoolAllocs &pa, const int32_t *d_indptr, const int32_t *d_in
 }
 
 // which retry the flags ask for: returns true when another attempt with (canon, general) makes sense
-static bool next_attempt(int flags, bool *canon, bool *general) {
+// mode bits: 1 canonicalise first, 2 general (transpose) path, 4 input holds explicit zeros
+static bool next_attempt(int flags, int *mode) {
   if (flags & SRG_FLAG_BAD_INDEX) return false;
-  if ((flags & SRG_FLAG_UNSORTED) && !*canon) {
-    *canon = true;
-    return true;
-  }
-  if ((flags & SRG_FLAG_ASYMMETRIC) && !*general) {
-    *general = true;
-    return true;
-  }
-  return false;
+  int want = *mode;
+  if (flags & SRG_FLAG_UNSORTED) want |= 1;
+  if (flags & SRG_FLAG_EXPLICIT_ZERO) want |= 4;
+  if (flags & SRG_FLAG_ASYMMETRIC) want |= 2;
+  if (want == *mode) return false;
+  *mode = want;
+  return true;
 }
 
 }  // namespace srg
@@ -232,7 +233,7 @@ extern "C" int srg_release_workspace(void) {
 static int construct_attempt(const int32_t *indptr, const int32_t *indices, const void *data,
                              int val_dtype, int64_t n, int64_t nnz, double r, double ppr_alpha,
                              int32_t *out_indptr, int32_t *out_indices, double *out_data,
-                             int64_t *out_nnz, int device, bool canon, bool general, int *flags_out) {
+                             int64_t *out_nnz, int device, int mode, int *flags_out) {
   int rc = require_device();
   if (rc) return rc;
   SRG_REQUIRE(n >= 0 && nnz >= 0, "construct_adj: negative size");
@@ -267,7 +268,7 @@ static int construct_attempt(const int32_t *indptr, const int32_t *indices, cons
     }
     NormOut no;
     if ((rc = run_norm(pa, d_indptr, d_indices, d_data, val_dtype, n, nnz, r, ppr_alpha,
-                       out_data != nullptr, false, s, canon, general, &no)))
+                       out_data != nullptr, false, s, mode, &no)))
       return rc;
     SRG_CUDA(cudaMemcpyAsync(&flags, no.flags, 4, cudaMemcpyDeviceToHost, s));
     SRG_CUDA(cudaMemcpyAsync(out_indptr, no.indptr, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, s));
@@ -293,14 +294,14 @@ extern "C" int srg_construct_adj_host(const int32_t *indptr, const int32_t *indi
                                       double r, double ppr_alpha, int32_t *out_indptr,
                                       int32_t *out_indices, double *out_data, int64_t *out_nnz,
                                       int device) {
-  bool canon = false, general = false;
+  int mode = 0;
   for (;;) {
     int flags = 0;
     int rc = construct_attempt(indptr, indices, data, val_dtype, n, nnz, r, ppr_alpha, out_indptr, out_indices,
-                               out_data, out_nnz, device, canon, general, &flags);
+                               out_data, out_nnz, device, mode, &flags);
     if (rc) return rc;
     if (!flags) return SRG_OK;
-    if (!next_attempt(flags, &canon, &general)) return check_flags(flags);
+    if (!next_attempt(flags, &mode)) return check_flags(flags);
   }
 }
 
@@ -309,7 +310,7 @@ static int propagate_attempt(const int32_t *indptr, const int32_t *indices, cons
                              int32_t F, const int32_t *feature_mask, int32_t K, double r,
                              double ppr_alpha, float *const *out_hops, int32_t *out_norm_indptr,
                              int32_t *out_norm_indices, double *out_norm_data, int64_t *out_nnz,
-                             int device, bool canon, bool general, int *flags_out) {
+                             int device, int mode, int *flags_out) {
   int rc = require_device();
   if (rc) return rc;
   SRG_REQUIRE(n >= 0 && nnz >= 0 && F >= 0 && K >= 0, "propagate_host: negative size");
@@ -379,7 +380,7 @@ static int propagate_attempt(const int32_t *indptr, const int32_t *indices, cons
     SRG_CUDA(cudaStreamWaitEvent(s_c, st->ev_csr, 0));
     NormOut no;
     if ((rc = run_norm(pa, d_indptr, d_indices, d_data, val_dtype, n, nnz, r, ppr_alpha,
-                       out_norm_data != nullptr, true, s_c, canon, general, &no)))
+                       out_norm_data != nullptr, true, s_c, mode, &no)))
       return rc;
     SRG_CUDA(cudaEventRecord(st->ev_norm, s_c));
 
@@ -443,15 +444,15 @@ extern "C" int srg_propagate_host(const int32_t *indptr, const int32_t *indices,
                                   double ppr_alpha, float *const *out_hops,
                                   int32_t *out_norm_indptr, int32_t *out_norm_indices,
                                   double *out_norm_data, int64_t *out_nnz, int device) {
-  bool canon = false, general = false;
+  int mode = 0;
   for (;;) {
     int flags = 0;
     int rc = propagate_attempt(indptr, indices, data, val_dtype, n, nnz, features, F, feature_mask, K, r, ppr_alpha,
-                               out_hops, out_norm_indptr, out_norm_indices, out_norm_data, out_nnz, device, canon,
-                               general, &flags);
+                               out_hops, out_norm_indptr, out_norm_indices, out_norm_data, out_nnz, device, mode,
+                               &flags);
     if (rc) return rc;
     if (!flags) return SRG_OK;
-    if (!next_attempt(flags, &canon, &general)) return check_flags(flags);
+    if (!next_attempt(flags, &mode)) return check_flags(flags);
   }
 }
 

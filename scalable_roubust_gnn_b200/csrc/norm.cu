@@ -239,49 +239,241 @@ __device__ __forceinline__ int ld_idx_64(const int *p) {
   return v;
 }
 
+// ---- row / segment tasks ---------------------------------------------------------------------------
+// The fast kernels below run one warp per TASK.  A task is a whole row, or — for rows longer than
+// kSegLen entries (power-law hubs) — one kSegLen-entry segment of it, so a hub is spread over many
+// warps.  Segments are listed on the device by seg_plan_kernel (no host round trip); the kernels
+// grid-stride over n_rows + *n_seg tasks.
+constexpr int kSegLen = 1024;
+struct SegPlan {
+  int *n_seg;    // device counter
+  int *seg_row;  // [cap]
+  int *seg_lo;   // [cap]
+  int *seg_hi;   // [cap]
+  int cap;
+};
+
+__global__ void __launch_bounds__(256)
+seg_plan_kernel(const int *__restrict__ indptr, long long n_rows, SegPlan p) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int st = indptr[r], ed = indptr[r + 1];
+  if (ed - st <= kSegLen) return;
+  const int ns = (ed - st + kSegLen - 1) / kSegLen;
+  const int s0 = atomicAdd(p.n_seg, ns);
+  for (int k = 0; k < ns && s0 + k < p.cap; ++k) {
+    p.seg_row[s0 + k] = (int)r;
+    p.seg_lo[s0 + k] = st + k * kSegLen;
+    p.seg_hi[s0 + k] = min(ed, st + (k + 1) * kSegLen);
+  }
+}
+
+struct Task {
+  long long a;  // local row
+  int s, e;     // the row's whole range
+  int lo, hi;   // the part this task covers
+};
+// task t of n_rows + n_seg; returns false when the task is void (a long row's row-task, or t beyond the end)
+__device__ __forceinline__ bool get_task(const int *__restrict__ indptr, long long n_rows, const SegPlan &p,
+                                         long long t, Task &k) {
+  if (t < n_rows) {
+    k.a = t;
+    k.s = indptr[t];
+    k.e = indptr[t + 1];
+    k.lo = k.s;
+    k.hi = k.e;
+    return k.e - k.s <= kSegLen;
+  }
+  const long long i = t - n_rows;
+  if (i >= min(*p.n_seg, p.cap)) return false;
+  k.a = p.seg_row[i];
+  k.s = indptr[k.a];
+  k.e = indptr[k.a + 1];
+  k.lo = p.seg_lo[i];
+  k.hi = p.seg_hi[i];
+  return true;
+}
+
+// position of the first entry >= key in the sorted range [lo, hi)
+__device__ __forceinline__ int lower_bound_idx(const int *__restrict__ idx, int lo, int hi, int key) {
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (idx[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ---- fast stage 1: canonical input without explicit zeros (anything else raises a flag) ----------------
+template <int DT>
+__global__ void __launch_bounds__(256)
+rows_count_fast_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
+                       const void *__restrict__ data, long long n_rows, long long row0, long long n_cols,
+                       SegPlan plan, int *__restrict__ rowlen, int *__restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long n_tasks = n_rows + plan.cap;
+  int fl = 0;
+  for (long long t = warp0; t < n_tasks; t += nwarps) {
+    Task k;
+    if (!get_task(indptr, n_rows, plan, t, k)) {
+      if (t >= n_rows && t - n_rows >= *plan.n_seg) break;
+      continue;
+    }
+    const int ag = (int)(k.a + row0);
+    for (int j = k.lo + lane; j < k.hi; j += 32) {
+      const int b = indices[j];
+      const int pb = (j > k.s) ? indices[j - 1] : -1;
+      if (b <= pb) fl |= SRG_FLAG_UNSORTED;
+      if (b < 0 || b >= n_cols) fl |= SRG_FLAG_BAD_INDEX;
+      if (DT != SRG_VAL_ONES) {
+        const double v = ValLoad<DT>::at(data, j);
+        if (v != 1.0) fl |= (v == 0.0) ? (kWeighted | SRG_FLAG_EXPLICIT_ZERO) : kWeighted;
+      }
+    }
+    if (k.lo == k.s && lane == 0) {  // the row's first task also owns the row-level result
+      const int q = lower_bound_idx(indices, k.s, k.e, ag);
+      const bool hd = q < k.e && indices[q] == ag;
+      const double dv = hd ? ValLoad<DT>::at(data, q) : 0.0;
+      const int keepd = (__dadd_rn(dv, 1.0) != 0.0) ? 1 : 0;
+      rowlen[k.a] = (k.e - k.s) - (hd ? 1 : 0) + keepd;
+    }
+  }
+  raise_flags(flags, fl);
+}
+
+// ---- fast stage 2a: every kept entry's output slot follows from its input slot ------------------------
+template <int DT>
+__global__ void __launch_bounds__(256)
+rows_fill_fast_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
+                      const void *__restrict__ data, long long n_rows, long long row0, SegPlan plan,
+                      const int *__restrict__ at_indptr, int *__restrict__ at_indices,
+                      double *__restrict__ at_val, double *__restrict__ degree,
+                      const int *__restrict__ flags, int force_vals) {
+  const bool weighted = (DT != SRG_VAL_ONES) && (force_vals || (*flags & kWeighted));
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long n_tasks = n_rows + plan.cap;
+  for (long long t = warp0; t < n_tasks; t += nwarps) {
+    Task k;
+    if (!get_task(indptr, n_rows, plan, t, k)) {
+      if (t >= n_rows && t - n_rows >= *plan.n_seg) break;
+      continue;
+    }
+    const int ag = (int)(k.a + row0);
+    const int p0 = at_indptr[k.a];
+    int q = 0;
+    if (lane == 0) q = lower_bound_idx(indices, k.s, k.e, ag);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    const bool hd = q < k.e && indices[q] == ag;
+    const double diag = __dadd_rn(hd ? ValLoad<DT>::at(data, q) : 0.0, 1.0);
+    const int keepd = (diag != 0.0) ? 1 : 0;
+    const int shift = keepd - (hd ? 1 : 0);  // applied to entries right of the diagonal
+    for (int j = k.lo + lane; j < k.hi; j += 32) {
+      const int b = indices[j];
+      if (b == ag) continue;
+      const int pos = p0 + (j - k.s) + ((b > ag) ? shift : 0);
+      at_indices[pos] = b;
+      if (weighted) at_val[pos] = ValLoad<DT>::at(data, j);
+    }
+    if (k.lo == k.s && lane == 0) {
+      const int len = (k.e - k.s) - (hd ? 1 : 0) + keepd;
+      if (keepd) {
+        at_indices[p0 + (q - k.s)] = ag;
+        if (weighted) at_val[p0 + (q - k.s)] = diag;
+      }
+      if (!weighted) degree[k.a] = (len == 0) ? 0.0 : (double)(len - 1) + diag;  // 1.0 entries: exact
+    }
+  }
+}
+
+// weighted graphs only: degree = A~.sum(1) in numpy's add.reduceat order, one thread per row
+__global__ void __launch_bounds__(256)
+rows_degree_weighted_kernel(long long n_rows, const int *__restrict__ at_indptr, const double *__restrict__ at_val,
+                            double *__restrict__ degree, const int *__restrict__ flags, int force) {
+  if (!force && !(*flags & kWeighted)) return;
+  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_rows) return;
+  const int p0 = at_indptr[a], len = at_indptr[a + 1] - p0;
+  double d = 0.0;
+  if (len == 1) d = at_val[p0];
+  else if (len > 1) d = __dadd_rn(at_val[p0], np_pairwise_sum(at_val + p0 + 1, len - 1));
+  degree[a] = d;
+}
+
+// mirror lookup: position of `key` in the sorted range [lo, hi) of idx, or -1.  Column ids of a row
+// are roughly uniform, so the key sits near the interpolated position: a 16-entry window around it
+// is fetched with 16 INDEPENDENT loads (one memory round trip instead of a chain of dependent
+// bisection probes); only a miss outside the window falls back to bisecting the remaining side.
+__device__ __forceinline__ int find_sorted(const int *__restrict__ idx, int lo, int hi, int key, long long n_cols) {
+  const int len = hi - lo;
+  if (len <= 0) return -1;
+  const int g = lo + (int)(((long long)len * key) / n_cols);
+  const int w0 = max(lo, min(g - 8, hi - 16));
+  int w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = (w0 + i < hi) ? ld_idx_64(idx + w0 + i) : 0x7fffffff;
+  int q = -1;
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (w[i] == key) q = w0 + i;
+  if (q >= 0) return q;
+  int l, r;
+  if (w[0] > key) {
+    l = lo;
+    r = w0;
+  } else if (w0 + 16 < hi && w[15] < key) {
+    l = w0 + 16;
+    r = hi;
+  } else {
+    return -1;  // bracketed by the window and absent
+  }
+  while (l < r) {
+    const int mid = (l + r) >> 1;
+    const int v = ld_idx_64(idx + mid);
+    if (v == key) return mid;
+    if (v < key) l = mid + 1; else r = mid;
+  }
+  return -1;
+}
+
 // ---- stage 2b: R[a,b] = (A~[b,a] * dl[a]) * dr[b] on a symmetric A~ -------------------------------
 // For a symmetric matrix A~[b,a] = A~[a,b], so every value comes from the row itself.  Symmetry is
 // VERIFIED, not assumed (check_sym): every upper entry (b > a) must find its mirror (b,a) with the
-// same value (binary search in row b), and the number of upper and lower entries must agree; the
-// mirror map is injective, so together these prove pattern and value symmetry.  One warp per row.
+// same value, and the number of upper and lower entries must agree; the mirror map is injective,
+// so together these prove pattern and value symmetry.  One warp per row / segment task.
 __global__ void __launch_bounds__(256)
-rows_values_kernel(long long n_rows, long long row0, const int *__restrict__ at_indptr,
-                   const int *__restrict__ at_indices, const double *__restrict__ at_val,
-                   const double *__restrict__ degree, const double *__restrict__ dl,
-                   const double *__restrict__ dr, double one_minus_alpha, double alpha, int use_ppr,
-                   int check_sym, double *__restrict__ val64, float *__restrict__ val32,
-                   int *__restrict__ flags, unsigned long long *__restrict__ tri_counts) {
+rows_values_kernel(long long n_rows, long long row0, long long n_cols, SegPlan plan,
+                   const int *__restrict__ at_indptr, const int *__restrict__ at_indices,
+                   const double *__restrict__ at_val, const double *__restrict__ degree,
+                   const double *__restrict__ dl, const double *__restrict__ dr, double one_minus_alpha,
+                   double alpha, int use_ppr, int check_sym, double *__restrict__ val64,
+                   float *__restrict__ val32, int *__restrict__ flags,
+                   unsigned long long *__restrict__ tri_counts) {
   const bool weighted = (*flags & kWeighted) != 0;
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long n_tasks = n_rows + plan.cap;
   int fl = 0;
   long long n_up = 0, n_lo = 0;  // per-thread running counts; reduced once per block
-  for (long long a = warp0; a < n_rows; a += nwarps) {
-    const int ag = (int)(a + row0);
-    const int p0 = at_indptr[a], p1 = at_indptr[a + 1];
+  for (long long t = warp0; t < n_tasks; t += nwarps) {
+    Task k;
+    if (!get_task(at_indptr, n_rows, plan, t, k)) {
+      if (t >= n_rows && t - n_rows >= *plan.n_seg) break;
+      continue;
+    }
+    const int ag = (int)(k.a + row0);
     const double dla = dl[ag];
-    const double diag_unw = weighted ? 0.0 : degree[a] - (double)(p1 - p0 - 1);
-    for (int p = p0 + lane; p < p1; p += 32) {
+    const double diag_unw = weighted ? 0.0 : degree[k.a] - (double)(k.e - k.s - 1);
+    for (int p = k.lo + lane; p < k.hi; p += 32) {
       const int b = at_indices[p];
       const double vt = weighted ? at_val[p] : (b == ag ? diag_unw : 1.0);
       if (check_sym && b != ag) {
         if (b > ag) {
           ++n_up;
-          int lo = at_indptr[b], hi = at_indptr[b + 1];
-          int q = -1;
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            const int c = ld_idx_64(at_indices + mid);
-            if (c == ag) {
-              q = mid;
-              break;
-            }
-            if (c < ag)
-              lo = mid + 1;
-            else
-              hi = mid;
-          }
+          const int q = find_sorted(at_indices, at_indptr[b], at_indptr[b + 1], ag, n_cols);
           if (q < 0 || (weighted && at_val[q] != vt)) fl |= SRG_FLAG_ASYMMETRIC;
         } else {
           ++n_lo;
@@ -306,9 +498,9 @@ rows_values_kernel(long long n_rows, long long row0, const int *__restrict__ at_
     if (lane == 0) s_diff[threadIdx.x >> 5] = diff;
     __syncthreads();
     if (threadIdx.x == 0) {
-      long long t = 0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_diff[w];
-      if (t) atomicAdd(tri_counts, (unsigned long long)t);  // wraps: only == 0 matters
+      long long tt = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tt += s_diff[w];
+      if (tt) atomicAdd(tri_counts, (unsigned long long)tt);  // wraps: only == 0 matters
     }
   }
   raise_flags(flags, fl);
@@ -325,29 +517,81 @@ __global__ void tri_compare_kernel(const unsigned long long *tri_counts, int *fl
     default: { constexpr int DTT = SRG_VAL_F64; CALL; } break;            \
   }
 
-int rows_count_launch(const int32_t *indptr, const int32_t *indices, const void *data, int dt, int64_t n_rows,
-                      int64_t row0, int64_t n_cols, int32_t *rowlen, int32_t *flags, cudaStream_t s) {
-  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(n_rows * 32, 256), kNormBlocks);
-  SRG_DT_SWITCH(dt, (rows_count_kernel<DTT><<<blocks, 256, 0, s>>>(indptr, indices, data, n_rows, row0, n_cols, rowlen, flags)));
+struct PlanHolder {
+  SegPlan p;
+  int *base = nullptr;
+};
+// device-side list of the segments of rows longer than kSegLen; nnz_bound >= indptr[n_rows]
+static int make_plan(const int *indptr, int64_t n_rows, int64_t nnz_bound, cudaStream_t s, PlanHolder *h) {
+  const int64_t cap = 2 * (nnz_bound / kSegLen) + 2;
+  SRG_CUDA(cudaMallocAsync(&h->base, (size_t)(1 + 3 * cap) * sizeof(int), s));
+  h->p.n_seg = h->base;
+  h->p.seg_row = h->base + 1;
+  h->p.seg_lo = h->p.seg_row + cap;
+  h->p.seg_hi = h->p.seg_lo + cap;
+  h->p.cap = (int)cap;
+  SRG_CUDA(cudaMemsetAsync(h->base, 0, sizeof(int), s));
+  seg_plan_kernel<<<(unsigned)ceil_div64(n_rows, 256), 256, 0, s>>>(indptr, n_rows, h->p);
   SRG_LAUNCHED();
+  return SRG_OK;
+}
+static void free_plan(PlanHolder *h, cudaStream_t s) {
+  if (h->base) cudaFreeAsync(h->base, s);
+  h->base = nullptr;
+}
+
+static inline unsigned norm_grid(int64_t n_rows) {
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n_rows * 32, 256), kNormBlocks));
+}
+
+// dt may carry SRG_VAL_HAS_ZEROS: the compacting (slower) kernels that tolerate explicit zeros
+int rows_count_launch(const int32_t *indptr, const int32_t *indices, const void *data, int dt, int64_t n_rows,
+                      int64_t nnz, int64_t row0, int64_t n_cols, int32_t *rowlen, int32_t *flags, cudaStream_t s) {
+  const bool zeros = (dt & SRG_VAL_HAS_ZEROS) != 0;
+  dt &= 0xff;
+  if (zeros) {
+    SRG_DT_SWITCH(dt, (rows_count_kernel<DTT><<<norm_grid(n_rows), 256, 0, s>>>(indptr, indices, data, n_rows, row0, n_cols, rowlen, flags)));
+    SRG_LAUNCHED();
+    return SRG_OK;
+  }
+  PlanHolder h;
+  int rc = make_plan(indptr, n_rows, nnz, s, &h);
+  if (rc) return rc;
+  SRG_DT_SWITCH(dt, (rows_count_fast_kernel<DTT><<<norm_grid(n_rows), 256, 0, s>>>(indptr, indices, data, n_rows, row0, n_cols, h.p, rowlen, flags)));
+  SRG_LAUNCHED();
+  free_plan(&h, s);
   return SRG_OK;
 }
 
 int rows_fill_launch(const int32_t *indptr, const int32_t *indices, const void *data, int dt, int64_t n_rows,
-                     int64_t row0, const int32_t *at_indptr, int32_t *at_indices, double *at_val,
+                     int64_t nnz, int64_t row0, const int32_t *at_indptr, int32_t *at_indices, double *at_val,
                      double *degree, const int32_t *flags, int force_vals, cudaStream_t s) {
-  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(n_rows * 32, 256), kNormBlocks);
-  SRG_DT_SWITCH(dt, (rows_fill_kernel<DTT><<<blocks, 256, 0, s>>>(indptr, indices, data, n_rows, row0, at_indptr, at_indices, at_val, degree, flags, force_vals)));
+  const bool zeros = (dt & SRG_VAL_HAS_ZEROS) != 0;
+  dt &= 0xff;
+  if (zeros) {
+    SRG_DT_SWITCH(dt, (rows_fill_kernel<DTT><<<norm_grid(n_rows), 256, 0, s>>>(indptr, indices, data, n_rows, row0, at_indptr, at_indices, at_val, degree, flags, force_vals)));
+    SRG_LAUNCHED();
+    return SRG_OK;
+  }
+  PlanHolder h;
+  int rc = make_plan(indptr, n_rows, nnz, s, &h);
+  if (rc) return rc;
+  SRG_DT_SWITCH(dt, (rows_fill_fast_kernel<DTT><<<norm_grid(n_rows), 256, 0, s>>>(indptr, indices, data, n_rows, row0, h.p, at_indptr, at_indices, at_val, degree, flags, force_vals)));
   SRG_LAUNCHED();
+  free_plan(&h, s);
+  if (dt != SRG_VAL_ONES) {
+    rows_degree_weighted_kernel<<<(unsigned)ceil_div64(n_rows, 256), 256, 0, s>>>(n_rows, at_indptr, at_val, degree, flags, force_vals);
+    SRG_LAUNCHED();
+  }
   return SRG_OK;
 }
 
 // used by the general (transpose) path in coo.cu: A~ with explicit values, degree, power tables
 int selfloop_fill_dispatch(const int32_t *indptr, const int32_t *indices, const void *data, int val_dtype,
-                           int64_t n, const int32_t *at_indptr, int32_t *at_indices, double *at_val,
+                           int64_t n, int64_t nnz, const int32_t *at_indptr, int32_t *at_indices, double *at_val,
                            double *degree, double *dl, double *dr, double r, const int32_t *flags,
                            cudaStream_t s) {
-  int rc = rows_fill_launch(indptr, indices, data, val_dtype, n, 0, at_indptr, at_indices, at_val, degree, flags, 1, s);
+  int rc = rows_fill_launch(indptr, indices, data, val_dtype, n, nnz, 0, at_indptr, at_indices, at_val, degree, flags, 1, s);
   if (rc) return rc;
   pow_tables_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(degree, n, r - 1.0, -r, dl, dr);
   SRG_LAUNCHED();
@@ -363,14 +607,15 @@ static int check_rows_args(const char *who, const int32_t *indptr, const int32_t
   SRG_REQUIRE(n_rows >= 0 && row0 >= 0 && n_cols >= 0 && row0 + n_rows <= n_cols,
               "%s: bad row range (n_rows=%lld row0=%lld n_cols=%lld)", who, (long long)n_rows, (long long)row0, (long long)n_cols);
   SRG_REQUIRE(n_cols <= 2147483647LL, "%s: more than 2^31-1 columns", who);
-  SRG_REQUIRE(val_dtype >= 0 && val_dtype <= 2, "%s: bad val_dtype %d", who, val_dtype);
+  SRG_REQUIRE((val_dtype & 0xff) >= 0 && (val_dtype & 0xff) <= 2 && (val_dtype & ~(0xff | SRG_VAL_HAS_ZEROS)) == 0,
+              "%s: bad val_dtype %d", who, val_dtype);
   SRG_REQUIRE(n_rows == 0 || indptr, "%s: indptr is NULL", who);
   (void)indices; (void)data;
   return SRG_OK;
 }
 
 extern "C" int srg_selfloop_rows_csr(const int32_t *indptr, const int32_t *indices, const void *data,
-                                     int val_dtype, int64_t n_rows, int64_t row0, int64_t n_cols,
+                                     int val_dtype, int64_t n_rows, int64_t nnz, int64_t row0, int64_t n_cols,
                                      int32_t *out_indptr, int32_t *out_count, int32_t *out_flags,
                                      void *stream) {
   int rc = require_device();
@@ -383,26 +628,27 @@ extern "C" int srg_selfloop_rows_csr(const int32_t *indptr, const int32_t *indic
     return SRG_OK;
   }
   SRG_REQUIRE(indices != nullptr, "selfloop_rows: indices is NULL");
-  SRG_REQUIRE(val_dtype == SRG_VAL_ONES || data != nullptr, "selfloop_rows: data is NULL but val_dtype says values");
+  SRG_REQUIRE((val_dtype & 0xff) == SRG_VAL_ONES || data != nullptr, "selfloop_rows: data is NULL but val_dtype says values");
+  SRG_REQUIRE(nnz >= 0, "selfloop_rows: negative nnz");
   int *scratch = nullptr;
   const int64_t scratch_ints = (out_count ? 0 : n_rows) + scan_scratch_ints(n_rows);
   SRG_CUDA(cudaMallocAsync(&scratch, scratch_ints * sizeof(int), s));
   int *rowlen = out_count ? out_count : scratch + scan_scratch_ints(n_rows);
-  rc = rows_count_launch(indptr, indices, data, val_dtype, n_rows, row0, n_cols, rowlen, out_flags, s);
+  rc = rows_count_launch(indptr, indices, data, val_dtype, n_rows, nnz, row0, n_cols, rowlen, out_flags, s);
   if (!rc) rc = exclusive_scan_i32(rowlen, n_rows, out_indptr, scratch, s);
   cudaFreeAsync(scratch, s);
   return rc;
 }
 
 extern "C" int srg_degree_selfloop_csr(const int32_t *indptr, const int32_t *indices,
-                                       const void *data, int val_dtype, int64_t n,
+                                       const void *data, int val_dtype, int64_t n, int64_t nnz,
                                        int32_t *out_indptr, int32_t *out_count,
                                        int32_t *out_flags, void *stream) {
-  return srg_selfloop_rows_csr(indptr, indices, data, val_dtype, n, 0, n, out_indptr, out_count, out_flags, stream);
+  return srg_selfloop_rows_csr(indptr, indices, data, val_dtype, n, nnz, 0, n, out_indptr, out_count, out_flags, stream);
 }
 
 extern "C" int srg_selfloop_fill_rows_csr(const int32_t *indptr, const int32_t *indices,
-                                          const void *data, int val_dtype, int64_t n_rows,
+                                          const void *data, int val_dtype, int64_t n_rows, int64_t nnz,
                                           int64_t row0, int64_t n_cols, const int32_t *at_indptr,
                                           int32_t *at_indices, double *at_val, double *out_degree,
                                           const int32_t *flags, void *stream) {
@@ -411,8 +657,8 @@ extern "C" int srg_selfloop_fill_rows_csr(const int32_t *indptr, const int32_t *
   if ((rc = check_rows_args("selfloop_fill_rows", indptr, indices, data, val_dtype, n_rows, row0, n_cols))) return rc;
   if (n_rows == 0) return SRG_OK;
   SRG_REQUIRE(indices && at_indptr && at_indices && out_degree && flags, "selfloop_fill_rows: NULL pointer");
-  SRG_REQUIRE(val_dtype == SRG_VAL_ONES || (data && at_val), "selfloop_fill_rows: weighted input needs data and at_val");
-  return rows_fill_launch(indptr, indices, data, val_dtype, n_rows, row0, at_indptr, at_indices, at_val, out_degree,
+  SRG_REQUIRE((val_dtype & 0xff) == SRG_VAL_ONES || (data && at_val), "selfloop_fill_rows: weighted input needs data and at_val");
+  return rows_fill_launch(indptr, indices, data, val_dtype, n_rows, nnz, row0, at_indptr, at_indices, at_val, out_degree,
                           flags, 0, as_stream(stream));
 }
 
@@ -430,13 +676,14 @@ extern "C" int srg_pow_tables_f64(const double *degree, int64_t n, double r, dou
 
 extern "C" int srg_norm_values_rows_csr(const int32_t *at_indptr, const int32_t *at_indices,
                                         const double *at_val, const double *degree_rows,
-                                        int64_t n_rows, int64_t row0, const double *pow_left,
+                                        int64_t n_rows, int64_t nnz, int64_t row0, int64_t n_cols,
+                                        const double *pow_left,
                                         const double *pow_right, double ppr_alpha, int check_symmetry,
                                         double *out_val_f64, float *out_val_f32, int32_t *flags,
                                         void *stream) {
   int rc = require_device();
   if (rc) return rc;
-  SRG_REQUIRE(n_rows >= 0 && row0 >= 0, "norm_values_rows: bad row range");
+  SRG_REQUIRE(n_rows >= 0 && row0 >= 0 && nnz >= 0 && n_cols >= row0 + n_rows, "norm_values_rows: bad row range");
   if (n_rows == 0) return SRG_OK;
   SRG_REQUIRE(at_indptr && at_indices && degree_rows && pow_left && pow_right && flags, "norm_values_rows: NULL pointer");
   SRG_REQUIRE(!check_symmetry || row0 == 0, "norm_values_rows: the symmetry check needs every row on this device");
@@ -446,14 +693,15 @@ extern "C" int srg_norm_values_rows_csr(const int32_t *at_indptr, const int32_t 
     SRG_CUDA(cudaMallocAsync(&tri, 2 * sizeof(unsigned long long), s));
     SRG_CUDA(cudaMemsetAsync(tri, 0, 2 * sizeof(unsigned long long), s));
   }
-  // persistent-style grid: 148 SMs x 8 resident blocks, warps stride over the rows
-  int64_t wblocks = ceil_div64(n_rows * 32, 256);
-  if (wblocks > 148 * 8) wblocks = 148 * 8;
-  rows_values_kernel<<<(unsigned)wblocks, 256, 0, s>>>(n_rows, row0, at_indptr, at_indices, at_val, degree_rows,
-                                                       pow_left, pow_right, 1.0 - ppr_alpha, ppr_alpha,
+  // persistent-style grid: 148 SMs x 8 resident blocks, warps stride over the row / segment tasks
+  PlanHolder h;
+  if ((rc = make_plan(at_indptr, n_rows, nnz, s, &h))) return rc;
+  rows_values_kernel<<<norm_grid(n_rows), 256, 0, s>>>(n_rows, row0, n_cols, h.p, at_indptr, at_indices, at_val,
+                                                       degree_rows, pow_left, pow_right, 1.0 - ppr_alpha, ppr_alpha,
                                                        ppr_alpha >= 0.0 ? 1 : 0, check_symmetry, out_val_f64,
                                                        out_val_f32, flags, tri);
   SRG_LAUNCHED();
+  free_plan(&h, s);
   if (check_symmetry) {
     tri_compare_kernel<<<1, 1, 0, s>>>(tri, flags);
     SRG_LAUNCHED();
@@ -472,23 +720,24 @@ extern "C" int srg_sym_norm_csr(const int32_t *indptr, const int32_t *indices, c
   SRG_REQUIRE(n >= 0 && nnz >= 0, "sym_norm: negative size");
   if (n == 0) return SRG_OK;
   SRG_REQUIRE(indptr && indices && out_indptr && out_indices && out_flags, "sym_norm: NULL pointer");
-  SRG_REQUIRE(val_dtype >= 0 && val_dtype <= 2, "sym_norm: bad val_dtype %d", val_dtype);
-  SRG_REQUIRE(val_dtype == SRG_VAL_ONES || data != nullptr, "sym_norm: data is NULL but val_dtype says values");
+  const int dt = val_dtype & 0xff;
+  SRG_REQUIRE(dt >= 0 && dt <= 2, "sym_norm: bad val_dtype %d", val_dtype);
+  SRG_REQUIRE(dt == SRG_VAL_ONES || data != nullptr, "sym_norm: data is NULL but val_dtype says values");
   SRG_REQUIRE(nnz + n <= 2147483647LL, "sym_norm: nnz + n exceeds the int32 CSR range");
   cudaStream_t s = as_stream(stream);
   // scratch: dl, dr (n doubles each) [+ degree] [+ A~ values when the dtype can carry weights]
   const int64_t cap = nnz + n;
-  const int64_t n_doubles = 2 * n + (out_degree ? 0 : n) + (val_dtype == SRG_VAL_ONES ? 0 : cap);
+  const int64_t n_doubles = 2 * n + (out_degree ? 0 : n) + (dt == SRG_VAL_ONES ? 0 : cap);
   double *scratch = nullptr;
   SRG_CUDA(cudaMallocAsync(&scratch, (size_t)n_doubles * sizeof(double), s));
   double *dl = scratch, *dr = scratch + n;
   double *deg = out_degree ? out_degree : scratch + 2 * n;
-  double *at_val = (val_dtype == SRG_VAL_ONES) ? nullptr : scratch + 2 * n + (out_degree ? 0 : n);
-  rc = rows_fill_launch(indptr, indices, data, val_dtype, n, 0, out_indptr, out_indices, at_val, deg, out_flags, 0, s);
+  double *at_val = (dt == SRG_VAL_ONES) ? nullptr : scratch + 2 * n + (out_degree ? 0 : n);
+  rc = rows_fill_launch(indptr, indices, data, val_dtype, n, nnz, 0, out_indptr, out_indices, at_val, deg, out_flags, 0, s);
   if (!rc) rc = srg_pow_tables_f64(deg, n, r, dl, dr, s);
   if (!rc)
-    rc = srg_norm_values_rows_csr(out_indptr, out_indices, at_val, deg, n, 0, dl, dr, ppr_alpha, 1, out_val_f64,
-                                  out_val_f32, out_flags, s);
+    rc = srg_norm_values_rows_csr(out_indptr, out_indices, at_val, deg, n, cap, 0, n, dl, dr, ppr_alpha, 1,
+                                  out_val_f64, out_val_f32, out_flags, s);
   cudaFreeAsync(scratch, s);
   return rc;
 }

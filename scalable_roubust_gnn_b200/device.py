@@ -98,7 +98,7 @@ def sym_norm(a: DeviceCSR, r: float, ppr_alpha: float | None = None, want_f64=Fa
     flags = torch.zeros(1, dtype=torch.int32, device=dev)
     o_indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
     o_count = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    _lib.check(lib.srg_degree_selfloop_csr(_p(a.indptr), _p(a.indices), _p(a.data), a.val_dtype, n, _p(o_indptr),
+    _lib.check(lib.srg_degree_selfloop_csr(_p(a.indptr), _p(a.indices), _p(a.data), a.val_dtype, n, nnz, _p(o_indptr),
                                            _p(o_count), _p(flags), s))
     cap = max(nnz + n, 1)
     o_indices = torch.empty(cap, dtype=torch.int32, device=dev)

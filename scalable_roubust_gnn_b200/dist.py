@@ -238,14 +238,14 @@ def dist_sym_norm(st: DistState, a_local, r, ppr_alpha=None):
     flags = torch.zeros(1, dtype=torch.int32, device=dev)
     at_indptr = torch.empty(n_loc + 1, dtype=torch.int32, device=dev)
     _lib.check(lib.srg_selfloop_rows_csr(_p(a_local.indptr), _p(a_local.indices), _p(a_local.data), a_local.val_dtype,
-                                         n_loc, st.row0, st.n, _p(at_indptr), None, _p(flags), s))
+                                         n_loc, nnz, st.row0, st.n, _p(at_indptr), None, _p(flags), s))
     cap = max(nnz + n_loc, 1)
     at_indices = torch.empty(cap, dtype=torch.int32, device=dev)
     at_val = torch.empty(cap, dtype=torch.float64, device=dev) if a_local.data is not None else None
     deg_all = torch.zeros(st.n_pad, dtype=torch.float64, device=dev)
     deg_loc = deg_all[st.rank * st.rows_per: st.rank * st.rows_per + max(n_loc, 0)]
     _lib.check(lib.srg_selfloop_fill_rows_csr(_p(a_local.indptr), _p(a_local.indices), _p(a_local.data),
-                                              a_local.val_dtype, n_loc, st.row0, st.n, _p(at_indptr), _p(at_indices),
+                                              a_local.val_dtype, n_loc, nnz, st.row0, st.n, _p(at_indptr), _p(at_indices),
                                               _p(at_val), _p(deg_loc), _p(flags), s))
     if st.world > 1:
         view = deg_all[st.rank * st.rows_per:(st.rank + 1) * st.rows_per]
@@ -255,6 +255,6 @@ def dist_sym_norm(st: DistState, a_local, r, ppr_alpha=None):
     _lib.check(lib.srg_pow_tables_f64(_p(deg_all), st.n_pad, float(r), _p(dl), _p(dr), s))
     val32 = torch.empty(cap, dtype=torch.float32, device=dev)
     alpha = -1.0 if ppr_alpha is None else float(ppr_alpha)
-    _lib.check(lib.srg_norm_values_rows_csr(_p(at_indptr), _p(at_indices), _p(at_val), _p(deg_loc), n_loc, st.row0,
-                                            _p(dl), _p(dr), alpha, 0, None, _p(val32), _p(flags), s))
+    _lib.check(lib.srg_norm_values_rows_csr(_p(at_indptr), _p(at_indices), _p(at_val), _p(deg_loc), n_loc, nnz + n_loc,
+                                            st.row0, st.n_pad, _p(dl), _p(dr), alpha, 0, None, _p(val32), _p(flags), s))
     return DeviceCSR(at_indptr, at_indices, val32, n_loc, nnz + n_loc), flags

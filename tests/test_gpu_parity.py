@@ -395,3 +395,35 @@ def test_rmat_graph_propagation_vs_oracle():
     got = SymLaplacianGraphOp(2).propagate(adj, x)
     for g, w in zip(got, want):
         np.testing.assert_allclose(g.numpy(), w, rtol=1e-5, atol=1e-6)
+
+
+def test_explicit_zeros_and_cancelled_diagonal():
+    """Stored zeros and a -1 diagonal (A + I cancels it): scipy drops both; so must the device path
+    (fast kernels flag the zeros, the compacting kernels redo the job)."""
+    n = 400
+    base = sym_graph(n, 3000, 17, weighted=True).tolil()
+    base[3, 3] = -1.0          # cancelled by +I -> row 3 has no diagonal in A~
+    base[5, 5] = 2.5           # ordinary weighted self loop
+    a = base.tocsr()
+    a.sort_indices()
+    # plant explicit zeros symmetrically
+    rng = np.random.default_rng(1)
+    coo = a.tocoo()
+    pick = rng.choice(len(coo.data), 40, replace=False)
+    dense_zero = set()
+    for p in pick:
+        i, j = int(coo.row[p]), int(coo.col[p])
+        if i != j:
+            dense_zero.add((i, j)); dense_zero.add((j, i))
+    data = a.data.copy()
+    rows = np.repeat(np.arange(n), np.diff(a.indptr))
+    for k in range(len(data)):
+        if (int(rows[k]), int(a.indices[k])) in dense_zero:
+            data[k] = 0.0
+    az = sp.csr_matrix((data, a.indices.copy(), a.indptr.copy()), shape=(n, n))
+    assert (az.data == 0).sum() >= 40
+    want = oracle.sym_norm(az, 0.5)
+    got = adj_to_symmetric_norm(az, 0.5)
+    assert_same_structure(got, want)
+    assert ulp_diff64(got.data, want.data).max() <= ULP64
+    assert want[3, 3] == 0 and got[3, 3] == 0

@@ -48,6 +48,18 @@ int require_device() {
     set_err("no CUDA device visible: libsrgnn_b200 has no CPU fallback");
     return SRG_ERR_NODEV;
   }
+  // the kernels take their scratch from the stream-ordered pool: keep freed blocks cached across
+  // synchronisation points instead of returning them to the driver (once per device)
+  static std::atomic<unsigned long long> pool_done{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !(pool_done.load() >> dev & 1ULL)) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thresh = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    pool_done.fetch_or(1ULL << dev);
+  }
   return SRG_OK;
 }
 

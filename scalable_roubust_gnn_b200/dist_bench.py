@@ -20,6 +20,7 @@ def run(args, workloads, metric, unit):
     import torch.distributed as dist
 
     from . import _lib, device as dev, dist as sdist, synth
+    lib = _lib.load()
 
     world = int(os.environ["WORLD_SIZE"])
     rank = int(os.environ["RANK"])
@@ -80,14 +81,27 @@ def run(args, workloads, metric, unit):
     dd = torch.from_numpy(a_loc_host.data).pin_memory()
     outs = [torch.empty((st.n_local, f), dtype=torch.float32).pin_memory() for _ in range(k)]
 
+    # device staging allocated once: the timed region is copies + kernels, not cudaMalloc
+    d_ip = torch.empty_like(ip, device="cuda")
+    d_ii = torch.empty_like(ii, device="cuda")
+    d_dd = torch.empty_like(dd, device="cuda")
+    d_x = torch.empty_like(x_pin, device="cuda")
+    d_flat = torch.empty((st.n_local, f), dtype=torch.float32, device="cuda")
+    copy_stream = torch.cuda.Stream()
+
     def e2e_step():
-        a_d = dev.DeviceCSR(ip.cuda(non_blocking=True), ii.cuda(non_blocking=True), dd.cuda(non_blocking=True),
-                            st.n_local, int(a_loc_host.nnz))
-        xp = dev.pack_features(x_pin.cuda(non_blocking=True))
+        d_ip.copy_(ip, non_blocking=True)
+        d_ii.copy_(ii, non_blocking=True)
+        d_dd.copy_(dd, non_blocking=True)
+        d_x.copy_(x_pin, non_blocking=True)
+        a_d = dev.DeviceCSR(d_ip, d_ii, d_dd, st.n_local, int(a_loc_host.nnz))
+        xp = dev.pack_features(d_x)
         norm, _ = sdist.dist_sym_norm(st, a_d, 0.5)
         hops = sdist.propagate_device(st, norm, xp, k, keep_hops=True)
         for o, h in zip(outs, hops[1:]):
-            o.copy_(dev.unpack_features(h, f), non_blocking=True)
+            lib.srg_unpack_features_f32(h.data_ptr(), st.ld, d_flat.data_ptr(), f, st.n_local, f,
+                                        torch.cuda.current_stream().cuda_stream)
+            o.copy_(d_flat, non_blocking=True)
         torch.cuda.synchronize()
 
     e2e_step()

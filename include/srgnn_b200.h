@@ -103,12 +103,15 @@ int srg_degree_selfloop_csr(const int32_t *indptr, const int32_t *indices, const
  *                                order (first element + 8-lane pairwise sum of the rest)
  *   out_val_f64 / out_val_f32  : either may be NULL; f32 = round-to-nearest of the fp64 value,
  *                                i.e. the `adj.data.astype(np.float32)` of utils.py:39
+ * When stage 1 flagged the input (UNSORTED / BAD_INDEX / EXPLICIT_ZERO) nothing is computed and
+ * out_indptr is overwritten with zeros (an empty matrix), so hops launched before the flags are
+ * read gather nothing.
  * Symmetric-pattern path: sets SRG_FLAG_ASYMMETRIC (outputs then undefined) when A~ has an entry
  * (a,b) without (b,a); SRG_FLAG_ZERO_PRODUCT when a value is exactly 0 (scipy drops those).
  * Allocates scratch with cudaMallocAsync on `stream`.
  */
 int srg_sym_norm_csr(const int32_t *indptr, const int32_t *indices, const void *data,
-                     int val_dtype, int64_t n, int64_t nnz, const int32_t *out_indptr, double r,
+                     int val_dtype, int64_t n, int64_t nnz, int32_t *out_indptr, double r,
                      double ppr_alpha, int32_t *out_indices, double *out_degree,
                      double *out_val_f64, float *out_val_f32, int32_t *out_flags, void *stream);
 
@@ -123,6 +126,8 @@ int srg_sym_norm_csr(const int32_t *indptr, const int32_t *indices, const void *
  *                              (row0 must be 0: every row local) verifies A~ == A~^T exactly (mirror
  *                              lookup of every upper entry + upper/lower counts) and raises
  *                              SRG_FLAG_ASYMMETRIC otherwise; without it symmetry is the caller's promise.
+ *                              nnz = allocated capacity (entries) of at_indices / at_val / outputs.
+ *                              If stage 1 flagged the input, at_indptr is zeroed (empty matrix).
  */
 int srg_selfloop_rows_csr(const int32_t *indptr, const int32_t *indices, const void *data,
                           int val_dtype, int64_t n_rows, int64_t nnz, int64_t row0, int64_t n_cols,
@@ -133,7 +138,7 @@ int srg_selfloop_fill_rows_csr(const int32_t *indptr, const int32_t *indices, co
                                double *at_val, double *out_degree, const int32_t *flags, void *stream);
 int srg_pow_tables_f64(const double *degree, int64_t n, double r, double *out_left,
                        double *out_right, void *stream);
-int srg_norm_values_rows_csr(const int32_t *at_indptr, const int32_t *at_indices,
+int srg_norm_values_rows_csr(int32_t *at_indptr, const int32_t *at_indices,
                              const double *at_val, const double *degree_rows, int64_t n_rows,
                              int64_t nnz, int64_t row0, int64_t n_cols, const double *pow_left,
                              const double *pow_right,

@@ -37,6 +37,8 @@ template <> struct ValLoad<SRG_VAL_F64> {
 };
 
 constexpr int kWeighted = SRG_FLAG_WEIGHTED;
+// input defects found by stage 1: later stages must not trust positions / indices derived from it
+constexpr int kFatal = SRG_FLAG_UNSORTED | SRG_FLAG_BAD_INDEX | SRG_FLAG_EXPLICIT_ZERO;
 
 // OR bits into the flags word without hammering one address: only threads that would add a bit not
 // yet visible issue the atomic (the race is benign, it only costs a redundant atomic).
@@ -350,6 +352,7 @@ rows_fill_fast_kernel(const int *__restrict__ indptr, const int *__restrict__ in
                       const int *__restrict__ at_indptr, int *__restrict__ at_indices,
                       double *__restrict__ at_val, double *__restrict__ degree,
                       const int *__restrict__ flags, int force_vals) {
+  if (*flags & kFatal) return;  // defective input: the slot arithmetic below would run out of bounds
   const bool weighted = (DT != SRG_VAL_ONES) && (force_vals || (*flags & kWeighted));
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -392,6 +395,7 @@ rows_fill_fast_kernel(const int *__restrict__ indptr, const int *__restrict__ in
 __global__ void __launch_bounds__(256)
 rows_degree_weighted_kernel(long long n_rows, const int *__restrict__ at_indptr, const double *__restrict__ at_val,
                             double *__restrict__ degree, const int *__restrict__ flags, int force) {
+  if (*flags & kFatal) return;
   if (!force && !(*flags & kWeighted)) return;
   const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_rows) return;
@@ -402,32 +406,45 @@ rows_degree_weighted_kernel(long long n_rows, const int *__restrict__ at_indptr,
   degree[a] = d;
 }
 
-// mirror lookup: position of `key` in the sorted range [lo, hi) of idx, or -1.  Column ids of a row
-// are roughly uniform, so the key sits near the interpolated position: a 16-entry window around it
-// is fetched with 16 INDEPENDENT loads (one memory round trip instead of a chain of dependent
-// bisection probes); only a miss outside the window falls back to bisecting the remaining side.
-__device__ __forceinline__ int find_sorted(const int *__restrict__ idx, int lo, int hi, int key, long long n_cols) {
+// mirror lookup: position of `key` in the sorted range [lo, hi) of idx, or -1.
+// What bounds this kernel is the number of per-thread loads (every lane hits a different line, so
+// each load is its own L1 wavefront), not latency: bisection costs ~5 dependent loads.  Column ids
+// of a row are roughly uniform, so the key sits near the interpolated position: ONE 16-entry window
+// around it is fetched with two 256-bit loads (LDG.E.256, 32-byte aligned) and searched in
+// registers; only a miss outside the window bisects the remaining side.
+// win_max: largest 8-aligned window start that keeps [w0, w0+16) inside the allocation, or -1 when
+// the array is too small / not 32-byte aligned (then plain bisection).
+__device__ __forceinline__ void ld_idx8(const int *p, int *w) {
+  asm volatile("ld.global.nc.L2::64B.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
+__device__ __forceinline__ int find_sorted(const int *__restrict__ idx, int lo, int hi, int key, long long n_cols,
+                                           int win_max) {
   const int len = hi - lo;
   if (len <= 0) return -1;
-  const int g = lo + (int)(((long long)len * key) / n_cols);
-  const int w0 = max(lo, min(g - 8, hi - 16));
-  int w[16];
+  int l = lo, r = hi;
+  if (win_max >= 0) {
+    const int g = lo + (int)(((long long)len * key) / n_cols);
+    const int w0 = min(max(g - 8, 0) & ~7, win_max);
+    int w[16];
+    ld_idx8(idx + w0, w);
+    ld_idx8(idx + w0 + 8, w + 8);
+    const int f = max(w0, lo), t = min(w0 + 15, hi - 1);  // valid part of the window
+    int q = -1, vf = 0, vt = 0;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) w[i] = (w0 + i < hi) ? ld_idx_64(idx + w0 + i) : 0x7fffffff;
-  int q = -1;
-#pragma unroll
-  for (int i = 0; i < 16; ++i)
-    if (w[i] == key) q = w0 + i;
-  if (q >= 0) return q;
-  int l, r;
-  if (w[0] > key) {
-    l = lo;
-    r = w0;
-  } else if (w0 + 16 < hi && w[15] < key) {
-    l = w0 + 16;
-    r = hi;
-  } else {
-    return -1;  // bracketed by the window and absent
+    for (int i = 0; i < 16; ++i) {
+      const int pos = w0 + i;
+      if (pos >= lo && pos < hi && w[i] == key) q = pos;
+      if (pos == f) vf = w[i];
+      if (pos == t) vt = w[i];
+    }
+    if (q >= 0) return q;
+    if (f <= t) {
+      if (vf > key) r = f;
+      else if (vt < key) l = t + 1;
+      else return -1;  // bracketed by the window and absent
+    }
   }
   while (l < r) {
     const int mid = (l + r) >> 1;
@@ -439,60 +456,74 @@ __device__ __forceinline__ int find_sorted(const int *__restrict__ idx, int lo, 
 }
 
 // ---- stage 2b: R[a,b] = (A~[b,a] * dl[a]) * dr[b] on a symmetric A~ -------------------------------
-// For a symmetric matrix A~[b,a] = A~[a,b], so every value comes from the row itself.  Symmetry is
+// For a symmetric matrix A~[b,a] = A~[a,b], so every value comes from the entry itself.  Symmetry is
 // VERIFIED, not assumed (check_sym): every upper entry (b > a) must find its mirror (b,a) with the
 // same value, and the number of upper and lower entries must agree; the mirror map is injective,
-// so together these prove pattern and value symmetry.  One warp per row / segment task.
+// so together these prove pattern and value symmetry.
+// The kernel is latency-bound (entry -> row pointer of b -> window of row b), so it is ENTRY
+// parallel: one thread per stored entry, every thread an independent chain, hub rows need no special
+// case.  The row of each entry comes from expand_rows_kernel (one coalesced pass).
 __global__ void __launch_bounds__(256)
-rows_values_kernel(long long n_rows, long long row0, long long n_cols, SegPlan plan,
-                   const int *__restrict__ at_indptr, const int *__restrict__ at_indices,
-                   const double *__restrict__ at_val, const double *__restrict__ degree,
-                   const double *__restrict__ dl, const double *__restrict__ dr, double one_minus_alpha,
-                   double alpha, int use_ppr, int check_sym, double *__restrict__ val64,
-                   float *__restrict__ val32, int *__restrict__ flags,
-                   unsigned long long *__restrict__ tri_counts) {
-  const bool weighted = (*flags & kWeighted) != 0;
+expand_rows_kernel(const int *__restrict__ at_indptr, long long n_rows, SegPlan plan, int *__restrict__ at_rows) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long n_tasks = n_rows + plan.cap;
-  int fl = 0;
-  long long n_up = 0, n_lo = 0;  // per-thread running counts; reduced once per block
   for (long long t = warp0; t < n_tasks; t += nwarps) {
     Task k;
     if (!get_task(at_indptr, n_rows, plan, t, k)) {
       if (t >= n_rows && t - n_rows >= *plan.n_seg) break;
       continue;
     }
-    const int ag = (int)(k.a + row0);
+    for (int p = k.lo + lane; p < k.hi; p += 32) at_rows[p] = (int)k.a;
+  }
+}
+
+__global__ void __launch_bounds__(256, 4)
+entry_values_kernel(long long n_rows, long long row0, long long n_cols, const int *__restrict__ at_indptr,
+                    const int *__restrict__ at_indices, const int *__restrict__ at_rows,
+                    const double *__restrict__ at_val, const double *__restrict__ degree,
+                    const double *__restrict__ dl, const double *__restrict__ dr, double one_minus_alpha,
+                    double alpha, int use_ppr, int check_sym, double *__restrict__ val64,
+                    float *__restrict__ val32, int *__restrict__ flags,
+                    unsigned long long *__restrict__ tri_counts, int win_max) {
+  if (*flags & kFatal) return;  // A~ was not written
+  const bool weighted = (*flags & kWeighted) != 0;
+  const long long total = at_indptr[n_rows];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  int fl = 0;
+  long long diff = 0;  // (#upper - #lower) seen by this thread
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += stride) {
+    const int a = at_rows[p];
+    const int b = at_indices[p];
+    const int ag = (int)(a + row0);
     const double dla = dl[ag];
-    const double diag_unw = weighted ? 0.0 : degree[k.a] - (double)(k.e - k.s - 1);
-    for (int p = k.lo + lane; p < k.hi; p += 32) {
-      const int b = at_indices[p];
-      const double vt = weighted ? at_val[p] : (b == ag ? diag_unw : 1.0);
-      if (check_sym && b != ag) {
-        if (b > ag) {
-          ++n_up;
-          const int q = find_sorted(at_indices, at_indptr[b], at_indptr[b + 1], ag, n_cols);
-          if (q < 0 || (weighted && at_val[q] != vt)) fl |= SRG_FLAG_ASYMMETRIC;
-        } else {
-          ++n_lo;
-        }
+    const double drb = dr[b];
+    double vt;
+    if (weighted) vt = at_val[p];
+    else if (b == ag) vt = degree[a] - (double)(at_indptr[a + 1] - at_indptr[a] - 1);  // 1.0 or 2.0, exact
+    else vt = 1.0;
+    if (check_sym && b != ag) {
+      if (b > ag) {
+        ++diff;
+        const int q = find_sorted(at_indices, at_indptr[b], at_indptr[b + 1], ag, n_cols, win_max);
+        if (q < 0 || (weighted && at_val[q] != vt)) fl |= SRG_FLAG_ASYMMETRIC;
+      } else {
+        --diff;
       }
-      double v = __dmul_rn(__dmul_rn(vt, dla), dr[b]);
-      if (use_ppr) {
-        v = __dmul_rn(one_minus_alpha, v);
-        if (b == ag) v = __dadd_rn(v, alpha);
-      }
-      if (v == 0.0) fl |= SRG_FLAG_ZERO_PRODUCT;
-      if (val64) val64[p] = v;
-      if (val32) val32[p] = __double2float_rn(v);
     }
+    double v = __dmul_rn(__dmul_rn(vt, dla), drb);
+    if (use_ppr) {
+      v = __dmul_rn(one_minus_alpha, v);
+      if (b == ag) v = __dadd_rn(v, alpha);
+    }
+    if (v == 0.0) fl |= SRG_FLAG_ZERO_PRODUCT;
+    if (val64) val64[p] = v;
+    if (val32) val32[p] = __double2float_rn(v);
   }
   if (check_sym) {
-    // upper - lower entry count of this block -> one atomic per block
     __shared__ long long s_diff[8];
-    long long diff = n_up - n_lo;
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
     if (lane == 0) s_diff[threadIdx.x >> 5] = diff;
@@ -508,6 +539,15 @@ rows_values_kernel(long long n_rows, long long row0, long long n_cols, SegPlan p
 
 __global__ void tri_compare_kernel(const unsigned long long *tri_counts, int *flags) {
   if (tri_counts[0] != 0ULL) atomicOr(flags, SRG_FLAG_ASYMMETRIC);  // #upper != #lower
+}
+
+// defective input: hand back an EMPTY matrix (all row pointers 0) so that a caller who launches
+// hops before looking at the flags gathers nothing instead of chasing uninitialised indices
+__global__ void __launch_bounds__(256)
+void_on_fatal_kernel(const int *__restrict__ flags, int *indptr, long long n_plus_1) {
+  if (!(*flags & kFatal)) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_plus_1) indptr[i] = 0;
 }
 
 #define SRG_DT_SWITCH(dt, CALL)                       \
@@ -674,7 +714,7 @@ extern "C" int srg_pow_tables_f64(const double *degree, int64_t n, double r, dou
   return SRG_OK;
 }
 
-extern "C" int srg_norm_values_rows_csr(const int32_t *at_indptr, const int32_t *at_indices,
+extern "C" int srg_norm_values_rows_csr(int32_t *at_indptr, const int32_t *at_indices,
                                         const double *at_val, const double *degree_rows,
                                         int64_t n_rows, int64_t nnz, int64_t row0, int64_t n_cols,
                                         const double *pow_left,
@@ -693,15 +733,25 @@ extern "C" int srg_norm_values_rows_csr(const int32_t *at_indptr, const int32_t 
     SRG_CUDA(cudaMallocAsync(&tri, 2 * sizeof(unsigned long long), s));
     SRG_CUDA(cudaMemsetAsync(tri, 0, 2 * sizeof(unsigned long long), s));
   }
-  // persistent-style grid: 148 SMs x 8 resident blocks, warps stride over the row / segment tasks
+  // 256-bit window loads need a 32-byte aligned index array with >= 16 entries of capacity (nnz)
+  const int win_max = ((uintptr_t)at_indices % 32 == 0 && nnz >= 16) ? (int)((nnz - 16) & ~7LL) : -1;
   PlanHolder h;
   if ((rc = make_plan(at_indptr, n_rows, nnz, s, &h))) return rc;
-  rows_values_kernel<<<norm_grid(n_rows), 256, 0, s>>>(n_rows, row0, n_cols, h.p, at_indptr, at_indices, at_val,
-                                                       degree_rows, pow_left, pow_right, 1.0 - ppr_alpha, ppr_alpha,
-                                                       ppr_alpha >= 0.0 ? 1 : 0, check_symmetry, out_val_f64,
-                                                       out_val_f32, flags, tri);
+  int *at_rows = nullptr;
+  SRG_CUDA(cudaMallocAsync(&at_rows, (size_t)std::max<int64_t>(nnz, 1) * sizeof(int), s));
+  expand_rows_kernel<<<norm_grid(n_rows), 256, 0, s>>>(at_indptr, n_rows, h.p, at_rows);
   SRG_LAUNCHED();
   free_plan(&h, s);
+  // one thread per stored entry, 4 entries per thread: grid from the capacity bound
+  const int64_t eblocks = std::max<int64_t>(1, std::min<int64_t>(ceil_div64(nnz, 256 * 4), 2147483647LL));
+  entry_values_kernel<<<(unsigned)eblocks, 256, 0, s>>>(n_rows, row0, n_cols, at_indptr, at_indices, at_rows, at_val,
+                                                        degree_rows, pow_left, pow_right, 1.0 - ppr_alpha, ppr_alpha,
+                                                        ppr_alpha >= 0.0 ? 1 : 0, check_symmetry, out_val_f64,
+                                                        out_val_f32, flags, tri, win_max);
+  SRG_LAUNCHED();
+  cudaFreeAsync(at_rows, s);
+  void_on_fatal_kernel<<<(unsigned)ceil_div64(n_rows + 1, 256), 256, 0, s>>>(flags, at_indptr, n_rows + 1);
+  SRG_LAUNCHED();
   if (check_symmetry) {
     tri_compare_kernel<<<1, 1, 0, s>>>(tri, flags);
     SRG_LAUNCHED();
@@ -711,7 +761,7 @@ extern "C" int srg_norm_values_rows_csr(const int32_t *at_indptr, const int32_t 
 }
 
 extern "C" int srg_sym_norm_csr(const int32_t *indptr, const int32_t *indices, const void *data,
-                                int val_dtype, int64_t n, int64_t nnz, const int32_t *out_indptr,
+                                int val_dtype, int64_t n, int64_t nnz, int32_t *out_indptr,
                                 double r, double ppr_alpha, int32_t *out_indices,
                                 double *out_degree, double *out_val_f64, float *out_val_f32,
                                 int32_t *out_flags, void *stream) {

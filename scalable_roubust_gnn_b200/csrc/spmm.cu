@@ -173,7 +173,7 @@ struct StreamArgs {
   const int *indices;
   const float *vals;
   long long n_rows;
-  const int *n_rows_dev;     // when non-NULL the row count is read from the device (segment tasks)
+  const int *n_rows_dev;     // when non-NULL the row count is min(*n_rows_dev, n_rows) (segment tasks)
   const float4 *X;
   unsigned ldx;              // in float4
   float4 *Y;
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) spmm_stream_kernel(const St
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned ring = (unsigned)__cvta_generic_to_shared(smem4 + (size_t)w * S * 32 + lane);
 
-  const long long n_rows = a.n_rows_dev ? (long long)*a.n_rows_dev : a.n_rows;
+  const long long n_rows = a.n_rows_dev ? min((long long)*a.n_rows_dev, a.n_rows) : a.n_rows;
   const long long task = (long long)blockIdx.x * kStreamWarps + w;
   const long long rblock = task / a.chunks;
   const int chunk = (int)(task - rblock * a.chunks);
@@ -472,7 +472,7 @@ static int stream_hop(const int *indptr, const int *indices, const float *vals, 
     StreamArgs g = a;
     g.row_lo = plan.seg_lo;
     g.row_hi = plan.seg_hi;
-    g.n_rows = 0;
+    g.n_rows = plan.cap_segs;        // the device count is clamped to the capacity
     g.n_rows_dev = plan.counts + 1;
     g.Y = reinterpret_cast<float4 *>(plan.partial);
     g.ldy = (long long)a.chunks * 32;

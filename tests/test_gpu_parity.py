@@ -427,3 +427,70 @@ def test_explicit_zeros_and_cancelled_diagonal():
     assert_same_structure(got, want)
     assert ulp_diff64(got.data, want.data).max() <= ULP64
     assert want[3, 3] == 0 and got[3, 3] == 0
+
+
+# ---- full BASELINE size: size-independent properties + sampled exact rows -----------------------------
+def test_products_scale_properties():
+    """BASELINE config 4 shape (N 2.45M, nnz(A^) 64.3M, F 100) on one GPU: the oracle is too slow for the
+    whole graph, so check (a) D^-1 A~ is row-stochastic (constant features are a fixed point), (b) 256
+    sampled output rows bit-for-bit against the C oracle fed with the same normalised rows, (c) run-to-run
+    determinism, (d) K hops == K single hops, (e) integer structure invariants."""
+    from scalable_roubust_gnn_b200 import synth
+    n, nnz, f, k = synth.SHAPES["products"]
+    adj = synth.uniform_graph(n, nnz)
+    a = dev.upload_csr(adj, ones_as_null=True)
+    norm, flags, ex = dev.sym_norm(a, 0.5, want_degree=True)
+    assert int(flags.item()) == 0
+    indptr = norm.indptr.cpu().numpy()
+    m = int(indptr[-1])
+    assert m == adj.nnz + n                                          # full diagonal added, nothing dropped
+    np.testing.assert_array_equal(np.diff(indptr), np.diff(adj.indptr) + 1)
+    np.testing.assert_array_equal(ex["degree"].cpu().numpy(), (np.diff(adj.indptr) + 1).astype(np.float64))
+    x = torch.from_numpy(synth.features(n, f)).cuda()
+    xp = dev.pack_features(x)
+    hops = dev.propagate(norm, xp, f, 3)
+    y1 = dev.spmm(norm, xp, f)
+    assert torch.equal(y1, hops[1]) and torch.equal(dev.spmm(norm, y1, f), hops[2])      # (c), (d)
+    # (b) sampled rows, exact
+    rng = np.random.default_rng(5)
+    rows = np.sort(rng.choice(n, 256, replace=False))
+    idx_all = norm.indices[:m].cpu().numpy()
+    val_all = norm.data[:m].cpu().numpy()
+    sub_ptr = np.zeros(len(rows) + 1, dtype=np.int32)
+    sub_ptr[1:] = np.cumsum(indptr[rows + 1] - indptr[rows])
+    sel = np.concatenate([np.arange(indptr[r], indptr[r + 1]) for r in rows])
+    sub = sp.csr_matrix((val_all[sel].astype(np.float64), idx_all[sel], sub_ptr), shape=(len(rows), n))
+    want = oracle.spmm_hop(sub, x.cpu().numpy())
+    np.testing.assert_array_equal(y1[:, :f].cpu().numpy()[rows], want)
+    # values of the sampled rows against the formula d_a^-1/2 d_b^-1/2 (fp64 -> fp32)
+    deg = (np.diff(adj.indptr) + 1).astype(np.float64)
+    exp_vals = ((1.0 * deg[np.repeat(rows, np.diff(sub_ptr))] ** -0.5) * deg[idx_all[sel]] ** -0.5).astype(np.float32)
+    assert (np.abs(val_all[sel].view(np.int32).astype(np.int64) - exp_vals.view(np.int32).astype(np.int64)) <= 1).all()
+    # (a) r = 0: rows of D^-1 A~^T sum to one
+    norm0, fl0, _ = dev.sym_norm(a, 0.0)
+    ones = dev.pack_features(torch.ones((n, f), device="cuda"))
+    y = dev.spmm(norm0, ones, f)[:, :f]
+    assert torch.allclose(y, torch.ones_like(y), rtol=1e-5, atol=1e-6)
+
+
+def test_reference_style_ctypes_binding():
+    """Bind FloatCSRMulDenseOMP the way SSRG/operators/utils.py:21-45 does (numpy.ctypeslib, ndpointer
+    argtypes, flattened float32 arrays) against our library file: the literal ABI drop-in."""
+    import numpy.ctypeslib as ctl
+    from ctypes import c_int
+    import os
+    lib = ctl.load_library("libsrgnn_b200.so", os.path.dirname(_lib.LIB_PATH))
+    arr_i = ctl.ndpointer(dtype=np.int32, ndim=1, flags="CONTIGUOUS")
+    arr_f = ctl.ndpointer(dtype=np.float32, ndim=1, flags="CONTIGUOUS")
+    lib.FloatCSRMulDenseOMP.argtypes = [arr_f, arr_f, arr_i, arr_i, arr_f, c_int, c_int]
+    lib.FloatCSRMulDenseOMP.restype = None
+    adj = oracle.sym_norm(sym_graph(4000, 50000, 9), 0.5)
+    feat = np.random.default_rng(2).random((4000, 47), dtype=np.float32)
+    answer = np.zeros(feat.shape).astype(np.float32).flatten()
+    lib.FloatCSRMulDenseOMP(answer, adj.data.astype(np.float32), adj.indices, adj.indptr, feat.flatten(), 4000, 47)
+    np.testing.assert_array_equal(answer.reshape(feat.shape), oracle.spmm_hop(adj, feat))
+    lib.FloatCSRMulDense.argtypes = [arr_f, c_int, arr_f, arr_i, arr_i, arr_f, c_int, c_int]
+    lib.FloatCSRMulDense.restype = c_int
+    answer2 = np.zeros(feat.shape).astype(np.float32).flatten()
+    assert lib.FloatCSRMulDense(answer2, adj.nnz, adj.data.astype(np.float32), adj.indices, adj.indptr, feat.flatten(), 4000, 47) == 0
+    np.testing.assert_array_equal(answer2, answer)

@@ -16,6 +16,7 @@ SHAPES = {
     "arxiv": (169343, 1166243, 128, 3),
     "products": (2449029, 61859140, 100, 3),
     "papers100M": (111059956, 1615685872, 128, 3),
+    "papers100M_16th": (111059956 // 16, 1615685872 // 16, 128, 3),   # 1/16-scale stand-in
 }
 
 

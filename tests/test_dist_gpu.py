@@ -12,7 +12,14 @@ from helpers import sym_graph
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, n, f, k, mode, weighted, out_dir):
+def _graph(n, weighted, rmat):
+    if rmat:
+        from scalable_roubust_gnn_b200 import synth
+        return synth.rmat_graph(n, 24 * n, seed=3)        # hubs longer than the 1024-entry split threshold
+    return sym_graph(n, 10 * n, 5, weighted=weighted)
+
+
+def _worker(rank, world, port, n, f, k, mode, weighted, out_dir, rmat=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -20,7 +27,7 @@ def _worker(rank, world, port, n, f, k, mode, weighted, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from scalable_roubust_gnn_b200 import device as dev, dist as sdist
-        adj = sym_graph(n, 10 * n, 5, weighted=weighted)
+        adj = _graph(n, weighted, rmat)
         x = np.random.default_rng(1).random((n, f), dtype=np.float32)
         st = sdist.DistState(n, f, world, rank, mode=mode)
         s, e = st.row0, st.row0 + st.n_local
@@ -46,7 +53,7 @@ def test_two_gpus_bitwise_equal_one_gpu(tmp_path, mode, weighted):
     world, n, f, k = 2, 50001, 100, 3
     port = 29600 + (os.getpid() % 300) + (1 if mode == "push" else 0) + (2 if weighted else 0)
     mp.spawn(_worker, args=(world, port, n, f, k, mode, weighted, str(tmp_path)), nprocs=world, join=True)
-    adj = sym_graph(n, 10 * n, 5, weighted=weighted)
+    adj = _graph(n, weighted, False)
     x = np.random.default_rng(1).random((n, f), dtype=np.float32)
     a = dev.upload_csr(adj)
     norm, flags, _ = dev.sym_norm(a, 0.5)
@@ -59,3 +66,23 @@ def test_two_gpus_bitwise_equal_one_gpu(tmp_path, mode, weighted):
     m = int(norm.indptr[-1].item())
     np.testing.assert_array_equal(np.concatenate([p["indices"] for p in parts]), norm.indices[:m].cpu().numpy())
     np.testing.assert_array_equal(np.concatenate([p["vals"] for p in parts]), norm.data[:m].cpu().numpy())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("mode", ["allgather", "push"])
+def test_two_gpus_power_law_rows(tmp_path, mode):
+    """R-MAT graph with hub rows: the segment + combine path (and its push variant) across 2 GPUs equals
+    the single-GPU result bit for bit (same segments, same order)."""
+    from scalable_roubust_gnn_b200 import device as dev
+    world, n, f, k = 2, 60000, 100, 2
+    port = 29700 + (os.getpid() % 200) + (1 if mode == "push" else 0)
+    mp.spawn(_worker, args=(world, port, n, f, k, mode, False, str(tmp_path), True), nprocs=world, join=True)
+    adj = _graph(n, False, True)
+    assert np.diff(adj.indptr).max() > 1024
+    x = np.random.default_rng(1).random((n, f), dtype=np.float32)
+    norm, flags, _ = dev.sym_norm(dev.upload_csr(adj), 0.5)
+    hops = dev.propagate(norm, dev.pack_features(torch.from_numpy(x).cuda()), f, k)
+    want = np.stack([h[:, :f].cpu().numpy() for h in hops])
+    parts = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
+    got = np.concatenate([p["hops"] for p in parts], axis=1)
+    np.testing.assert_array_equal(got, want)

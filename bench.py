@@ -317,6 +317,9 @@ def run_ours(args):
 
 
 def main():
+    # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout must carry the JSON line only
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -210,6 +210,10 @@ int srg_spmm_csr_f32_push(const int32_t *indptr, const int32_t *indices, const f
                           int64_t n_rows, int64_t nnz, const float *X, int64_t ldx,
                           float *const *dests, int32_t n_dests, int64_t dest_row0, int64_t ldy,
                           int32_t F, void *stream);
+/* input exchange without a collective: copy n_rows x ld floats into rows dest_row0.. of every
+ * destination buffer (own + peers) */
+int srg_push_rows_f32(const float *src, int64_t n_rows, int64_t ld, float *const *dests,
+                      int32_t n_dests, int64_t dest_row0, void *stream);
 /* peer-mappable device buffers: plain cudaMalloc + CUDA IPC handles (64 bytes) */
 int srg_ipc_alloc(void **ptr, int64_t bytes);
 int srg_ipc_free(void *ptr);

@@ -645,6 +645,41 @@ extern "C" int srg_apply_feature_mask_f32(const float *x, int64_t ld_x, const in
   return srg_pack_features_f32(x, ld_x, out, ld_out, n, F, mask, stream);
 }
 
+// copy this rank's rows into the same rows of every destination buffer (peer stores over NVLink):
+// the input exchange of the multi-GPU path without a collective
+__global__ void __launch_bounds__(256)
+push_rows_kernel(const float4 *__restrict__ src, long long n_vec, PeerDests peers) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    const float4 v = src[i];
+#pragma unroll
+    for (int d = 0; d < kMaxPeers; ++d)
+      if (d < peers.count) peers.p[d][i] = v;
+  }
+}
+
+extern "C" int srg_push_rows_f32(const float *src, int64_t n_rows, int64_t ld, float *const *dests,
+                                 int32_t n_dests, int64_t dest_row0, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n_rows >= 0 && ld >= 0 && dest_row0 >= 0, "push_rows: negative size");
+  SRG_REQUIRE(n_dests >= 1 && n_dests <= kMaxPeers, "push_rows: n_dests must be 1..%d", kMaxPeers);
+  if (n_rows == 0 || ld == 0) return SRG_OK;
+  SRG_REQUIRE(src && dests && ld % 4 == 0 && (uintptr_t)src % 16 == 0, "push_rows: needs ld %% 4 == 0 and 16-byte alignment");
+  PeerDests pd;
+  pd.count = n_dests;
+  for (int d = 0; d < kMaxPeers; ++d) pd.p[d] = nullptr;
+  for (int d = 0; d < n_dests; ++d) {
+    SRG_REQUIRE(dests[d] && (uintptr_t)dests[d] % 16 == 0, "push_rows: dests[%d] NULL or unaligned", d);
+    pd.p[d] = reinterpret_cast<float4 *>(dests[d]) + dest_row0 * (ld / 4);
+  }
+  const long long n_vec = n_rows * (ld / 4);
+  const int blocks = (int)std::min<int64_t>(ceil_div64(n_vec, 256), 148 * 4);
+  push_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4 *>(src), n_vec, pd);
+  SRG_LAUNCHED();
+  return SRG_OK;
+}
+
 // ---- peer-mapped buffers (CUDA IPC) for the push hop ---------------------------------------------------
 extern "C" int srg_ipc_alloc(void **ptr, int64_t bytes) {
   int rc = require_device();

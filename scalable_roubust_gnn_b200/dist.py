@@ -90,6 +90,9 @@ class DistState:
         self.full = []          # torch views of the two local full buffers
         self.peer_ptrs = []     # per buffer: list of world device pointers (index = rank)
         self._tick = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # the input exchange runs on a side stream so that it overlaps the normalisation
+        self.side = torch.cuda.Stream(device=self.device)
+        self._x_event = None
         nbytes = self.n_pad * self.ld * 4
         for _ in range(2):
             if mode == "push" and world > 1:
@@ -201,16 +204,42 @@ class DeviceOps:
         return st.full[i][st.row0:st.row0 + st.n_local].clone()
 
 
+def start_input_exchange(st: DistState, x_local_padded):
+    """Start moving this rank's input rows into full buffer 0 of EVERY rank on a side stream; call it
+    BEFORE dist_sym_norm so the exchange overlaps the normalisation.  Push mode: one kernel storing to
+    the peer mappings (no collective); all-gather mode: copy + NCCL all-gather."""
+    import torch
+
+    from . import _lib
+    from .device import _p
+    side = st.side
+    side.wait_stream(torch.cuda.current_stream(st.device))
+    with torch.cuda.stream(side):
+        if st.mode == "push" and st.world > 1:
+            dests = (C.c_void_p * st.world)(*st.peer_ptrs[0])
+            _lib.check(st.lib.srg_push_rows_f32(_p(x_local_padded), st.n_local, st.ld, dests, st.world, st.row0,
+                                                C.c_void_p(side.cuda_stream)))
+        else:
+            st.full[0][st.row0:st.row0 + st.n_local].copy_(x_local_padded)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    x_local_padded.record_stream(side)
+    st._x_event = ev
+
+
 def propagate_device(st: DistState, local_norm, x_local_padded, k, keep_hops=True):
-    """K hops on the device; returns the list of local hop slices (or only the last when not keep_hops)."""
+    """K hops on the device; returns the list of local hop slices (or only the last when not keep_hops).
+    If start_input_exchange was called for this input, only its completion is awaited here."""
+    import torch
     ops = DeviceOps(st)
     cur, nxt = 0, 1
-    ops.load_local(cur, x_local_padded)
+    if st._x_event is None:
+        start_input_exchange(st, x_local_padded)
+    torch.cuda.current_stream(st.device).wait_event(st._x_event)
+    st._x_event = None
     if st.world > 1:
         if st.mode == "push":
-            # the input slice has to reach the peers once: a plain all-gather (not on the per-hop path)
-            view = st.full[cur][st.rank * st.rows_per:(st.rank + 1) * st.rows_per]
-            st.dist.all_gather_into_tensor(st.full[cur], view, group=st.group)
+            st.dist.all_reduce(st._tick, group=st.group)      # every rank's rows have landed everywhere
         else:
             ops.exchange(cur)
     out = [ops.snapshot_local(cur)] if keep_hops else []

@@ -22,6 +22,9 @@ def run(args, workloads, metric, unit):
     from . import _lib, device as dev, dist as sdist, synth
     lib = _lib.load()
 
+    if os.environ.get("SRG_DEBUG_HANG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["SRG_DEBUG_HANG"]), exit=True)
     world = int(os.environ["WORLD_SIZE"])
     rank = int(os.environ["RANK"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
@@ -46,6 +49,7 @@ def run(args, workloads, metric, unit):
     x_loc = dev.pack_features(torch.from_numpy(np.ascontiguousarray(x_loc_host)).cuda())
 
     def step():
+        sdist.start_input_exchange(st, x_loc)          # overlaps the normalisation
         norm, flags = sdist.dist_sym_norm(st, a_loc, 0.5)
         sdist.propagate_device(st, norm, x_loc, k, keep_hops=False)
         return flags
@@ -96,6 +100,7 @@ def run(args, workloads, metric, unit):
         d_x.copy_(x_pin, non_blocking=True)
         a_d = dev.DeviceCSR(d_ip, d_ii, d_dd, st.n_local, int(a_loc_host.nnz))
         xp = dev.pack_features(d_x)
+        sdist.start_input_exchange(st, xp)
         norm, _ = sdist.dist_sym_norm(st, a_d, 0.5)
         hops = sdist.propagate_device(st, norm, xp, k, keep_hops=True)
         for o, h in zip(outs, hops[1:]):

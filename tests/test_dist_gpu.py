@@ -19,6 +19,11 @@ def _graph(n, weighted, rmat):
     return sym_graph(n, 10 * n, 5, weighted=weighted)
 
 
+def rank_overlap(mode, weighted):
+    """exercise both the overlapped and the in-line input exchange across the parametrisations"""
+    return mode == "push" or weighted
+
+
 def _worker(rank, world, port, n, f, k, mode, weighted, out_dir, rmat=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -32,8 +37,10 @@ def _worker(rank, world, port, n, f, k, mode, weighted, out_dir, rmat=False):
         st = sdist.DistState(n, f, world, rank, mode=mode)
         s, e = st.row0, st.row0 + st.n_local
         a_loc = dev.upload_csr(sdist.shard_rows(adj, s, e))
-        norm, flags = sdist.dist_sym_norm(st, a_loc, 0.5)
         xp = dev.pack_features(torch.from_numpy(x[s:e]).cuda())
+        if rank_overlap(mode, weighted):
+            sdist.start_input_exchange(st, xp)            # overlapped input exchange variant
+        norm, flags = sdist.dist_sym_norm(st, a_loc, 0.5)
         hops = sdist.propagate_device(st, norm, xp, k)
         torch.cuda.synchronize()
         m = int(norm.indptr[-1].item())

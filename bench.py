@@ -37,6 +37,16 @@ METRIC = "K-hop SpMM propagation throughput (normalisation + K hops)"
 UNIT = "edge*feat/s"
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line of this run, on the real stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -74,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -186,7 +196,7 @@ def run_reference(args):
                          "hop_only_value": float(np.mean([r["hop_value"] for r in runs]))},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, n, nnz_hat, f, k):
@@ -208,7 +218,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from scalable_roubust_gnn_b200 import dist_bench
-        return dist_bench.run(args, WORKLOADS, METRIC, UNIT)
+        return dist_bench.run(args, WORKLOADS, METRIC, UNIT, emit)
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     lib = _lib.load()
@@ -237,14 +247,18 @@ def run_ours(args):
                 ev[i].record()
         return norm, flags
 
+    # the clock sampler (an nvidia-smi child polling every 100 ms) starts BEFORE the warm-up: its start-up
+    # (NVML initialisation) stalls the first kernels that follow it, which must not be timed ones
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         norm, flags = step()
     torch.cuda.synchronize()
     assert int(flags.item()) & ~16 == 0, f"normalisation flags {int(flags.item())}"
     nnz_hat = int(norm.indptr[-1].item())
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    step()                                      # one more untimed pass after the readbacks above
+    torch.cuda.synchronize()
+    sampler.lines.clear()                       # keep only samples taken during the timed region
     launches0 = _lib.launch_count()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(k + 2)] for _ in range(args.steps)]
     torch.cuda.synchronize()
@@ -313,13 +327,16 @@ def run_ours(args):
             "norm_ms": float(np.mean(norm_ms)), "hop_ms": float(np.mean(hop_ms)),
             "step_ms_all": [round(v, 3) for v in step_ms], "norm_ms_all": [round(v, 3) for v in norm_ms],
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
-    # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout must carry the JSON line only
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout must carry ONE JSON line, but libraries (NCCL's version banner) write to fd 1 too: keep a
+    # private copy of the real stdout for the JSON and point fd 1 at stderr for everybody else
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -15,7 +15,7 @@ import time
 import numpy as np
 
 
-def run(args, workloads, metric, unit):
+def run(args, workloads, metric, unit, emit):
     import torch
     import torch.distributed as dist
 
@@ -54,15 +54,17 @@ def run(args, workloads, metric, unit):
         sdist.propagate_device(st, norm, x_loc, k, keep_hops=False)
         return flags
 
+    from bench import ClockSampler  # noqa: E402  (bench.py is the entry script)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                        # before the warm-up: its start-up must not hit timed steps
     for _ in range(args.warmup):
         flags = step()
     torch.cuda.synchronize()
     assert int(flags.item()) & ~_lib.SRG_FLAG_WEIGHTED == 0, f"normalisation flags {int(flags.item())}"
-
-    from bench import ClockSampler  # noqa: E402  (bench.py is the entry script)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    step()
+    torch.cuda.synchronize()
+    sampler.lines.clear()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
@@ -144,6 +146,6 @@ def run(args, workloads, metric, unit):
                         "h2d_bytes_per_step": int(ip.numel() * 4 + ii.numel() * 4 + dd.numel() * 8 + x_pin.numel() * 4),
                         "d2h_bytes_per_step": int(k * st.n_local * f * 4), "note": "per-rank bytes; max over ranks time"},
                 "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        emit(line)
     st.close()
     dist.destroy_process_group()

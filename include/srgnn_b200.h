@@ -253,6 +253,39 @@ int srg_cheby_filter_f64(const int32_t *lap_indptr, const int32_t *lap_indices,
                          double tol, double *const *out_r, float *const *out_r32, int64_t ld32,
                          double *work0, double *work1, void *stream);
 
+/* ---- 8f-1: message-operator aggregation of the hop list, on the device ------------------------- */
+/* the non-learnable aggregators of SSRG/operators/message_operator/: last_message_op.py:9,
+ * sum_message_op.py:9, mean_message_op.py:9, max_message_op.py:11, min_message_op.py:11,
+ * concat_message_op.py:9, simple_weighted_message_op.py:44-58 (+ utils.py:426-437) */
+#define SRG_AGG_NONE 0
+#define SRG_AGG_LAST 1
+#define SRG_AGG_SUM 2
+#define SRG_AGG_MEAN 3
+#define SRG_AGG_MAX 4
+#define SRG_AGG_MIN 5
+#define SRG_AGG_CONCAT 6
+#define SRG_AGG_WEIGHTED 7
+/* fold one hop matrix x (n x ld_x) into acc[:, col0:col0+F] (n x ld_acc).  first != 0 initialises acc
+ * from x; mode -1 finalises a mean (acc / weight).  The arithmetic is the reference's torch
+ * expression evaluated in hop order (sequential fp32 adds; weighted: product first). */
+int srg_aggregate_update_f32(float *acc, int64_t ld_acc, int32_t col0, const float *x, int64_t ld_x,
+                             int64_t n, int32_t F, int32_t mode, float weight, int32_t first,
+                             void *stream);
+/*
+ * srg_propagate_host + the aggregation, with ONLY the aggregate coming back:
+ *   out_agg (host, n x F_out, F_out = F or (agg_end-agg_start)*F for CONCAT) =
+ *       msg_op.aggregate(graph_op.propagate(adj, feature))  over the hop slice [agg_start, agg_end)
+ *   agg_weights: host array of agg_end-agg_start floats (WEIGHTED only).
+ * Two ping-pong hop buffers + the accumulator stay on the device; K-1 of the K device->host copies
+ * of srg_propagate_host disappear.
+ */
+int srg_propagate_aggregate_host(const int32_t *indptr, const int32_t *indices, const void *data,
+                                 int val_dtype, int64_t n, int64_t nnz, const float *features,
+                                 int32_t F, const int32_t *feature_mask, int32_t K, double r,
+                                 double ppr_alpha, int32_t agg_mode, int32_t agg_start,
+                                 int32_t agg_end, const float *agg_weights, float *out_agg,
+                                 int device);
+
 /* layout helpers: host layout (ld == F) <-> padded device layout (ld % 8 == 0, pad = 0).
  * mask (optional, int32 n x F, SSRG/data_process.py:38-39) is applied as x * mask
  * (SSRG/data_augument.py:28) while repacking. */

@@ -27,6 +27,7 @@ SRG_VAL_ONES, SRG_VAL_F32, SRG_VAL_F64 = 0, 1, 2
 SRG_FLAG_UNSORTED, SRG_FLAG_ASYMMETRIC, SRG_FLAG_ZERO_PRODUCT, SRG_FLAG_BAD_INDEX, SRG_FLAG_WEIGHTED = 1, 2, 4, 8, 16
 SRG_FLAG_EXPLICIT_ZERO = 32
 SRG_VAL_HAS_ZEROS = 0x100
+SRG_AGG_NONE, SRG_AGG_LAST, SRG_AGG_SUM, SRG_AGG_MEAN, SRG_AGG_MAX, SRG_AGG_MIN, SRG_AGG_CONCAT, SRG_AGG_WEIGHTED = range(8)
 
 
 class SrgError(RuntimeError):
@@ -76,6 +77,9 @@ SIGNATURES = {
                                        C.POINTER(_vp), C.POINTER(_vp), _i64, _vp, _vp, _vp]),
     "srg_pack_features_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp]),
     "srg_unpack_features_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),
+    "srg_aggregate_update_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i64, _i32, _i32, C.c_float, _i32, _vp]),
+    "srg_propagate_aggregate_host": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _i32, _vp, _i32, _f64, _f64,
+                                               _i32, _i32, _i32, _vp, _vp, C.c_int]),
     "srg_propagate_host": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _i32, _vp, _i32, _f64, _f64,
                                      C.POINTER(_vp), _vp, _vp, _vp, C.POINTER(_i64), C.c_int]),
     "srg_construct_adj_host": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _f64, _f64, _vp, _vp, _vp,

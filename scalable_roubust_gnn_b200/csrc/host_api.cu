@@ -11,6 +11,7 @@
 //   copy-out stream: after hop k: unpack to the host layout and D2H, overlapping hop k+1
 // Device memory comes from the stream-ordered pool (cudaMallocAsync) whose release threshold is
 // raised so repeated calls reuse the same blocks.
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -200,6 +201,14 @@ static int run_norm(PoolAllocs &pa, const int32_t *d_indptr, const int32_t *d_in
                                   o->indptr, o->indices, nullptr, o->val64, o->val32, o->flags, s);
 }
 
+// aggregation of the hop list requested by srg_propagate_aggregate_host (mode SRG_AGG_NONE: none)
+struct AggSpec {
+  int mode = SRG_AGG_NONE;
+  int start = 0, end = 0;
+  const float *weights = nullptr;  // host, end - start entries (WEIGHTED)
+  float *out = nullptr;            // host, n x f_out
+};
+
 // which retry the flags ask for: returns true when another attempt with (canon, general) makes sense
 // mode bits: 1 canonicalise first, 2 general (transpose) path, 4 input holds explicit zeros
 static bool next_attempt(int flags, int *mode) {
@@ -322,18 +331,19 @@ static int propagate_attempt(const int32_t *indptr, const int32_t *indices, cons
                              int32_t F, const int32_t *feature_mask, int32_t K, double r,
                              double ppr_alpha, float *const *out_hops, int32_t *out_norm_indptr,
                              int32_t *out_norm_indices, double *out_norm_data, int64_t *out_nnz,
-                             int device, int mode, int *flags_out) {
+                             int device, int mode, int *flags_out, const AggSpec *agg = nullptr) {
   int rc = require_device();
   if (rc) return rc;
+  const bool do_agg = agg && agg->mode != SRG_AGG_NONE;
   SRG_REQUIRE(n >= 0 && nnz >= 0 && F >= 0 && K >= 0, "propagate_host: negative size");
   SRG_REQUIRE(indptr, "propagate_host: indptr is NULL");
   SRG_REQUIRE(nnz == 0 || indices, "propagate_host: indices is NULL");
   SRG_REQUIRE(val_dtype >= 0 && val_dtype <= 2, "propagate_host: bad val_dtype");
   SRG_REQUIRE(val_dtype == SRG_VAL_ONES || nnz == 0 || data, "propagate_host: data is NULL");
   SRG_REQUIRE(n * (int64_t)F == 0 || features, "propagate_host: features is NULL");
-  SRG_REQUIRE(K == 0 || out_hops, "propagate_host: out_hops is NULL");
+  SRG_REQUIRE(K == 0 || out_hops || do_agg, "propagate_host: out_hops is NULL");
   SRG_REQUIRE(nnz + n <= 2147483647LL, "propagate_host: nnz + n exceeds the int32 CSR range");
-  for (int k = 0; k < K; ++k)
+  for (int k = 0; k < K && !do_agg; ++k)
     SRG_REQUIRE(n * (int64_t)F == 0 || out_hops[k], "propagate_host: out_hops[%d] is NULL", k);
   if (out_nnz) *out_nnz = 0;
   if (n == 0) {
@@ -365,15 +375,32 @@ static int propagate_attempt(const int32_t *indptr, const int32_t *indices, cons
     if (val_dtype != SRG_VAL_ONES && (rc = pa.alloc(&d_data, nnz * (int64_t)val_bytes(val_dtype)))) return rc;
     std::vector<float *> hops(K + 1, nullptr);
     const bool have_feat = (int64_t)F * n > 0;
+    // with an aggregation only two hop buffers ping-pong and an accumulator collects the result
+    const int n_bufs = do_agg ? std::min(K + 1, 2) : K + 1;
     if (have_feat)
-      for (int k = 0; k <= K; ++k)
-        if ((rc = pa.alloc(&hops[k], n * ld))) return rc;
+      for (int k = 0; k <= K; ++k) {
+        if (k < n_bufs) {
+          if ((rc = pa.alloc(&hops[k], n * ld))) return rc;
+        } else {
+          hops[k] = hops[k - 2];
+        }
+      }
+    const int agg_cnt = do_agg ? agg->end - agg->start : 0;
+    const int64_t f_out = do_agg ? (agg->mode == SRG_AGG_CONCAT ? (int64_t)agg_cnt * F : F) : 0;
+    const int64_t ld_acc = pad8(f_out);
+    float *d_acc = nullptr, *d_acc_flat = nullptr;
+    if (do_agg && have_feat && agg->mode != SRG_AGG_LAST) {
+      if ((rc = pa.alloc(&d_acc, n * ld_acc))) return rc;
+    }
+    if (do_agg && have_feat && (ld_acc != f_out)) {
+      if ((rc = pa.alloc(&d_acc_flat, n * f_out))) return rc;
+    }
     float *d_flat_in = nullptr, *d_flat_out[2] = {nullptr, nullptr};
     int32_t *d_mask = nullptr;
     const bool need_pack = have_feat && (padded || feature_mask);
     if (need_pack && (rc = pa.alloc(&d_flat_in, n * (int64_t)F))) return rc;
     if (have_feat && feature_mask && (rc = pa.alloc(&d_mask, n * (int64_t)F))) return rc;
-    if (have_feat && padded && K > 0) {
+    if (have_feat && padded && K > 0 && !do_agg) {
       if ((rc = pa.alloc(&d_flat_out[0], n * (int64_t)F))) return rc;
       if (K > 1 && (rc = pa.alloc(&d_flat_out[1], n * (int64_t)F))) return rc;
     }
@@ -406,7 +433,7 @@ static int propagate_attempt(const int32_t *indptr, const int32_t *indices, cons
     }
 
     // hops + overlapped copy-out
-    if (have_feat) {
+    if (have_feat && !do_agg) {
       SRG_CUDA(cudaStreamWaitEvent(s_c, st->ev_x, 0));
       for (int k = 1; k <= K; ++k) {
         if ((rc = spmm_csr_f32_impl(no.indptr, no.indices, no.val32, n, nnz + n, hops[k - 1], ld, hops[k], ld, F, false, s_c)))
@@ -421,6 +448,34 @@ static int propagate_attempt(const int32_t *indptr, const int32_t *indices, cons
         }
         SRG_CUDA(cudaMemcpyAsync(out_hops[k - 1], src, (size_t)n * F * 4, cudaMemcpyDeviceToHost, s_out));
       }
+    }
+    if (have_feat && do_agg) {
+      // hop k is folded into the accumulator as soon as it exists; only the aggregate goes back
+      SRG_CUDA(cudaStreamWaitEvent(s_c, st->ev_x, 0));
+      bool first = true;
+      for (int k = 0; k <= K; ++k) {
+        if (k > 0 &&
+            (rc = spmm_csr_f32_impl(no.indptr, no.indices, no.val32, n, nnz + n, hops[k - 1], ld, hops[k], ld, F, false, s_c)))
+          return rc;
+        if (agg->mode == SRG_AGG_LAST || k < agg->start || k >= agg->end) continue;
+        const int slot = k - agg->start;
+        const float wgt = (agg->mode == SRG_AGG_WEIGHTED) ? agg->weights[slot] : 1.0f;
+        const int col0 = (agg->mode == SRG_AGG_CONCAT) ? slot * F : 0;
+        if ((rc = srg_aggregate_update_f32(d_acc, ld_acc, col0, hops[k], ld, n, F, agg->mode, wgt,
+                                           (first || agg->mode == SRG_AGG_CONCAT) ? 1 : 0, s_c)))
+          return rc;
+        first = false;
+      }
+      if (agg->mode == SRG_AGG_MEAN &&
+          (rc = srg_aggregate_update_f32(d_acc, ld_acc, 0, nullptr, 0, n, F, -1, (float)agg_cnt, 0, s_c)))
+        return rc;
+      const float *res = (agg->mode == SRG_AGG_LAST) ? hops[K] : d_acc;
+      const int64_t ld_res = (agg->mode == SRG_AGG_LAST) ? ld : ld_acc;
+      if (ld_res != f_out) {
+        if ((rc = srg_unpack_features_f32(res, ld_res, d_acc_flat, f_out, n, (int32_t)f_out, s_c))) return rc;
+        res = d_acc_flat;
+      }
+      SRG_CUDA(cudaMemcpyAsync(agg->out, res, (size_t)n * f_out * 4, cudaMemcpyDeviceToHost, s_c));
     }
     // normalised CSR back to the host if requested (after the hop copies are queued)
     SRG_CUDA(cudaStreamWaitEvent(s_in, st->ev_norm, 0));
@@ -462,6 +517,39 @@ extern "C" int srg_propagate_host(const int32_t *indptr, const int32_t *indices,
     int rc = propagate_attempt(indptr, indices, data, val_dtype, n, nnz, features, F, feature_mask, K, r, ppr_alpha,
                                out_hops, out_norm_indptr, out_norm_indices, out_norm_data, out_nnz, device, mode,
                                &flags);
+    if (rc) return rc;
+    if (!flags) return SRG_OK;
+    if (!next_attempt(flags, &mode)) return check_flags(flags);
+  }
+}
+
+extern "C" int srg_propagate_aggregate_host(const int32_t *indptr, const int32_t *indices, const void *data,
+                                            int val_dtype, int64_t n, int64_t nnz, const float *features,
+                                            int32_t F, const int32_t *feature_mask, int32_t K, double r,
+                                            double ppr_alpha, int32_t agg_mode, int32_t agg_start,
+                                            int32_t agg_end, const float *agg_weights, float *out_agg,
+                                            int device) {
+  SRG_REQUIRE(agg_mode >= SRG_AGG_LAST && agg_mode <= SRG_AGG_WEIGHTED, "propagate_aggregate: bad agg_mode %d", agg_mode);
+  SRG_REQUIRE(K >= 0, "propagate_aggregate: K must be >= 0");
+  if (agg_mode == SRG_AGG_LAST) {
+    agg_start = K;
+    agg_end = K + 1;
+  }
+  SRG_REQUIRE(agg_start >= 0 && agg_start < agg_end && agg_end <= K + 1,
+              "propagate_aggregate: hop slice [%d, %d) outside [0, %d]", agg_start, agg_end, K + 1);
+  SRG_REQUIRE(agg_mode != SRG_AGG_WEIGHTED || agg_weights, "propagate_aggregate: weights are NULL");
+  SRG_REQUIRE(n * (int64_t)F == 0 || out_agg, "propagate_aggregate: out_agg is NULL");
+  AggSpec agg;
+  agg.mode = agg_mode;
+  agg.start = agg_start;
+  agg.end = agg_end;
+  agg.weights = agg_weights;
+  agg.out = out_agg;
+  int mode = 0;
+  for (;;) {
+    int flags = 0;
+    int rc = propagate_attempt(indptr, indices, data, val_dtype, n, nnz, features, F, feature_mask, K, r, ppr_alpha,
+                               nullptr, nullptr, nullptr, nullptr, nullptr, device, mode, &flags, &agg);
     if (rc) return rc;
     if (!flags) return SRG_OK;
     if (!next_attempt(flags, &mode)) return check_flags(flags);

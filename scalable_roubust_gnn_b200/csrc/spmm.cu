@@ -543,9 +543,65 @@ unpack_features_kernel(const float *__restrict__ src, long long ld_src, float *_
   for (int c = threadIdx.x; c < F; c += 32) d[c] = s[c];
 }
 
+// ---- message-operator aggregation over the hop list (SSRG/operators/message_operator/*.py) ---------
+// acc (n x ld_acc) is updated from one hop matrix x (n x ld_x); arithmetic mirrors the reference's
+// torch expressions: `sum(list)` = sequential fp32 adds in hop order, weighted = products first
+// (`feat * w`), then the same sequential sum, mean = sum / count (true division).
+__global__ void __launch_bounds__(256)
+agg_update_kernel(float *__restrict__ acc, long long ld_acc, int col0, const float *__restrict__ x,
+                  long long ld_x, long long n, int F, int mode, float w, int first) {
+  const long long row = (long long)blockIdx.x * 8 + threadIdx.y;
+  if (row >= n) return;
+  float *a = acc + row * ld_acc + col0;
+  const float *xr = x ? x + row * ld_x : nullptr;
+  for (int c = threadIdx.x; c < F; c += 32) {
+    float v;
+    switch (mode) {
+      case SRG_AGG_SUM:
+      case SRG_AGG_MEAN:
+        v = first ? xr[c] : __fadd_rn(a[c], xr[c]);
+        break;
+      case SRG_AGG_WEIGHTED:
+        v = first ? __fmul_rn(xr[c], w) : __fadd_rn(a[c], __fmul_rn(xr[c], w));
+        break;
+      case SRG_AGG_MAX:
+        v = first ? xr[c] : fmaxf(a[c], xr[c]);
+        break;
+      case SRG_AGG_MIN:
+        v = first ? xr[c] : fminf(a[c], xr[c]);
+        break;
+      case -1:  // finalise the mean: acc / count
+        v = __fdiv_rn(a[c], w);
+        break;
+      default:  // SRG_AGG_LAST / SRG_AGG_CONCAT: plain copy into the column block
+        v = xr[c];
+        break;
+    }
+    a[c] = v;
+  }
+}
+
 }  // namespace srg
 
 using namespace srg;
+
+extern "C" int srg_aggregate_update_f32(float *acc, int64_t ld_acc, int32_t col0, const float *x,
+                                        int64_t ld_x, int64_t n, int32_t F, int32_t mode, float weight,
+                                        int32_t first, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n >= 0 && F >= 0 && col0 >= 0, "aggregate_update: bad sizes");
+  SRG_REQUIRE((mode >= SRG_AGG_LAST && mode <= SRG_AGG_WEIGHTED) || mode == -1, "aggregate_update: bad mode %d", mode);
+  if (n == 0 || F == 0) return SRG_OK;
+  SRG_REQUIRE(acc && (x || mode == -1), "aggregate_update: NULL pointer");
+  SRG_REQUIRE(ld_acc >= col0 + F && (mode == -1 || ld_x >= F), "aggregate_update: leading dimension too small");
+  const int64_t blocks = ceil_div64(n, 8);
+  SRG_REQUIRE(blocks <= 2147483647LL, "aggregate_update: too many rows");
+  agg_update_kernel<<<(unsigned)blocks, dim3(32, 8), 0, as_stream(stream)>>>(acc, ld_acc, col0, x, ld_x, n, F, mode,
+                                                                            weight, first);
+  SRG_LAUNCHED();
+  return SRG_OK;
+}
 
 extern "C" int srg_set_tuning(const char *key, int64_t value) {
   SRG_REQUIRE(key != nullptr, "set_tuning: NULL key");

@@ -85,6 +85,30 @@ class GraphOp:
         return [torch.FloatTensor(feature)] + hops
 
 
+    def propagate_aggregate(self, adj, feature, msg_op):
+        """``msg_op.aggregate(self.propagate(adj, feature))`` with the aggregation folded into the device
+        pipeline: only the aggregate is copied back (SSRG/models/base_scalable/base_model.py:36-43 is the
+        call pair this replaces).  Falls back to the two-step form for operators without a fused spec."""
+        spec = msg_op.fused_spec(self.prop_steps + 1) if hasattr(msg_op, "fused_spec") else None
+        params = self._norm_params()
+        if spec is None or params is None:
+            return msg_op.aggregate(self.propagate(adj, feature))
+        if not isinstance(adj, sp.csr_matrix):
+            raise TypeError("The adjacency matrix must be a scipy csr sparse matrix!")
+        if isinstance(feature, Tensor):
+            feature = feature.numpy()
+        if not isinstance(feature, np.ndarray):
+            raise TypeError("The feature matrix must be a numpy.ndarray!")
+        if feature.ndim != 2 or adj.shape[1] != feature.shape[0]:
+            raise ValueError("Dimension mismatch detected for the adjacency and the feature matrix!")
+        if feature.dtype != np.float32:
+            raise ctypes.ArgumentError("The feature matrix must be float32!")
+        r, alpha = params
+        out = _u.propagate_aggregate_host(adj, feature, self.prop_steps, r, alpha, spec, device=self.device)
+        self._adj, self._adj_source = None, adj
+        return out
+
+
 def ada_platform_one_step_propagation(adj, x):
     """One hop ``adj @ x`` (SSRG/operators/base_operator.py:309-314).  The reference switches on
     the platform between its OpenMP library and scipy; here there is one path: the GPU."""

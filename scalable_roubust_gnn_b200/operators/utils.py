@@ -21,7 +21,8 @@ import torch
 
 from .. import _lib
 
-__all__ = ["csr_sparse_dense_matmul", "adj_to_symmetric_norm", "propagate_host", "csr_host_parts"]
+__all__ = ["csr_sparse_dense_matmul", "adj_to_symmetric_norm", "propagate_host", "propagate_aggregate_host",
+           "csr_host_parts"]
 
 
 def _ptr(a):
@@ -165,3 +166,26 @@ def _propagate(lib, adj, feature, K, r, ppr_alpha, feature_mask, device, pin, re
                                  copy=False)
         adj_norm.has_sorted_indices = True
     return hops, adj_norm
+
+
+def propagate_aggregate_host(adj, feature, prop_steps, r, ppr_alpha, spec, feature_mask=None, device=0, pin=True):
+    """One library call: normalisation + K hops + message-operator aggregation; returns the aggregate as
+    a CPU float32 tensor (pinned when a GPU is present).  ``spec`` = (agg_mode, start, end, weights)."""
+    lib = _lib.load()
+    mode, lo, hi, weights = spec
+    indptr, indices, data, vt, n, nnz = csr_host_parts(adj)
+    feature = np.ascontiguousarray(feature)
+    F = feature.shape[1]
+    mask = None
+    if feature_mask is not None:
+        mask = feature_mask.numpy() if isinstance(feature_mask, torch.Tensor) else np.asarray(feature_mask)
+        mask = np.ascontiguousarray(mask, dtype=np.int32)
+    f_out = F * (hi - lo) if mode == _lib.SRG_AGG_CONCAT else F
+    out = _empty((n, f_out), torch.float32, _use_pinned(pin))
+    w = None if weights is None else weights.numpy().astype(np.float32)
+    alpha = -1.0 if ppr_alpha is None else float(ppr_alpha)
+    rc = lib.srg_propagate_aggregate_host(_ptr(indptr), _ptr(indices), _ptr(data), vt, n, nnz, _ptr(feature), F,
+                                          _ptr(mask), int(prop_steps), float(r), alpha, int(mode), int(lo), int(hi),
+                                          _ptr(w), _ptr(out), int(device))
+    _lib.check(rc)
+    return out

@@ -112,6 +112,25 @@ def main():
 
     np.savez_compressed(os.path.join(HERE, "reference_propagation.npz"), **out)
 
+    # ---- message operators of the reference on a reference hop list ------------------------------
+    from operators.message_operator.concat_message_op import ConcatMessageOp
+    from operators.message_operator.last_message_op import LastMessageOp
+    from operators.message_operator.max_message_op import SimMaxMessageOp
+    from operators.message_operator.mean_message_op import MeanMessageOp
+    from operators.message_operator.min_message_op import SimMinMessageOp
+    from operators.message_operator.simple_weighted_message_op import SimpleWeightedMessageOp
+    from operators.message_operator.sum_message_op import SumMessageOp
+    mo = {}
+    a, x = graphs["rand_unw"]
+    hops = Sym(3, r=0.5).propagate(a, x)
+    ops = {"last": LastMessageOp(), "mean": MeanMessageOp(0, 4), "sum": SumMessageOp(0, 4), "sum13": SumMessageOp(1, 3),
+           "max": SimMaxMessageOp(0, 4), "min": SimMinMessageOp(0, 4), "concat": ConcatMessageOp(0, 4),
+           "concat24": ConcatMessageOp(2, 4), "alpha": SimpleWeightedMessageOp(0, 4, "alpha", 0.5),
+           "hand": SimpleWeightedMessageOp(0, 4, "hand_crafted", [0.1, 0.2, 0.3, 0.4])}
+    for name, op in ops.items():
+        mo[name] = op.aggregate(list(hops)).numpy()
+    np.savez_compressed(os.path.join(HERE, "reference_message_ops.npz"), **mo)
+
     # ---- sparsity masks (reference data fixtures) ----------------------------------------------
     masks = {}
     for ds, n_feat_shape in [("cora_0_0.7", (2708, 1433)), ("cora_0.7_0.7", (2708, 1433)),

@@ -1,0 +1,83 @@
+"""Message operators: the mirrored classes against the reference's own outputs (CPU), and
+the fused device aggregation against both the reference golden vectors and the unfused two-step form."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import golden_csr
+from scalable_roubust_gnn_b200.operators import (ConcatMessageOp, LastMessageOp, MeanMessageOp, SimMaxMessageOp,
+                                                 SimMinMessageOp, SimpleWeightedMessageOp, SumMessageOp,
+                                                 SymLaplacianGraphOp)
+
+GOLDEN = "tests/golden/reference_message_ops.npz"
+
+
+def make_ops():
+    return {"last": LastMessageOp(), "mean": MeanMessageOp(0, 4), "sum": SumMessageOp(0, 4), "sum13": SumMessageOp(1, 3),
+            "max": SimMaxMessageOp(0, 4), "min": SimMinMessageOp(0, 4), "concat": ConcatMessageOp(0, 4),
+            "concat24": ConcatMessageOp(2, 4), "alpha": SimpleWeightedMessageOp(0, 4, "alpha", 0.5),
+            "hand": SimpleWeightedMessageOp(0, 4, "hand_crafted", [0.1, 0.2, 0.3, 0.4])}
+
+
+@pytest.fixture(scope="module")
+def golden_mo():
+    import os
+    from conftest import ROOT
+    return np.load(os.path.join(ROOT, GOLDEN))
+
+
+def reference_hops(golden_prop):
+    norm = golden_csr(golden_prop, "rand_unw_r0.5_norm")
+    hops = [golden_prop["rand_unw_x"]]
+    for _ in range(3):
+        hops.append(oracle.spmm_hop(norm, hops[-1]))
+    np.testing.assert_array_equal(hops[3], golden_prop["rand_unw_r0.5_hop3"])
+    return [torch.from_numpy(h) for h in hops]
+
+
+@pytest.mark.parametrize("name", sorted(make_ops()))
+def test_mirrored_ops_match_reference_on_cpu_lists(golden_prop, golden_mo, name):
+    op = make_ops()[name]
+    got = op.aggregate(reference_hops(golden_prop))
+    np.testing.assert_array_equal(got.numpy(), golden_mo[name])
+
+
+def test_message_op_contract():
+    with pytest.raises(TypeError, match="The feature matrices must be tensors!"):
+        SumMessageOp(0, 2).aggregate([np.ones(3), np.ones(3)])
+    with pytest.raises(ValueError, match="Invalid weighted combination type"):
+        SimpleWeightedMessageOp(0, 2, "beta", 0.5)
+    with pytest.raises(TypeError, match="The alpha must be a float!"):
+        SimpleWeightedMessageOp(0, 2, "alpha", 1)
+    assert LastMessageOp().aggr_type == "last" and MeanMessageOp(0, 2).aggr_type == "mean"
+    assert SimpleWeightedMessageOp(0, 2, "alpha", 0.5).aggr_type == "simple_weighted"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(make_ops()))
+def test_fused_aggregation_vs_reference_and_unfused(golden_prop, golden_mo, name):
+    adj = golden_csr(golden_prop, "rand_unw_adj")
+    x = golden_prop["rand_unw_x"]
+    op = make_ops()[name]
+    gop = SymLaplacianGraphOp(3, r=0.5)
+    fused = gop.propagate_aggregate(adj, x, op)
+    assert isinstance(fused, torch.Tensor) and fused.dtype == torch.float32 and not fused.is_cuda
+    np.testing.assert_allclose(fused.numpy(), golden_mo[name], rtol=1e-5, atol=1e-6)
+    unfused = op.aggregate(gop.propagate(adj, x))
+    if name in ("alpha", "hand"):
+        # torch's strided sum may associate differently from the in-order device sum
+        np.testing.assert_allclose(fused.numpy(), unfused.numpy(), rtol=2e-7, atol=1e-7)
+    else:
+        np.testing.assert_array_equal(fused.numpy(), unfused.numpy())
+
+
+@pytest.mark.gpu
+def test_fused_aggregation_wide_features_and_masks():
+    from helpers import sym_graph
+    adj = sym_graph(3000, 30000, 4)
+    x = np.random.default_rng(0).random((3000, 100), dtype=np.float32)
+    gop = SymLaplacianGraphOp(4, r=0.5)
+    hops = gop.propagate(adj, x)
+    for op in (LastMessageOp(), MeanMessageOp(0, 5), ConcatMessageOp(0, 5), SimMaxMessageOp(1, 4)):
+        np.testing.assert_array_equal(gop.propagate_aggregate(adj, x, op).numpy(), op.aggregate(hops).numpy())

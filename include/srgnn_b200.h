@@ -253,6 +253,25 @@ int srg_cheby_filter_f64(const int32_t *lap_indptr, const int32_t *lap_indices,
                          double tol, double *const *out_r, float *const *out_r32, int64_t ld32,
                          double *work0, double *work1, void *stream);
 
+/* ---- 8f-3: wavelet post-processing on the device ------------------------------------------------ */
+/* thresholded dense float32 block (n x B, the out_r32 of srg_cheby_filter_f64) -> block CSR with global
+ * column ids col0 + j (wavelet/src/utils.py:99-103, base_model.py:247-251).  Call it first with
+ * out_cols == NULL (count only: out_indptr[n] is the entry count) to size out_cols / out_vals, then
+ * again to fill them.  row_totals (nullable, n ints) is incremented by the per-row counts. */
+int srg_dense_block_to_csr_f32(const float *dense, int64_t ld, int64_t n, int32_t B, int32_t col0,
+                               int32_t *out_indptr, int32_t *out_cols, float *out_vals,
+                               int64_t capacity, int32_t *row_totals, void *stream);
+/* append the rows of one block CSR to the merged CSR at cursor[row] and advance the cursor; calling it
+ * block after block in column order is sparse.hstack (base_model.py:265) without a sort */
+int srg_csr_block_scatter_f32(int64_t n, const int32_t *block_indptr, const int32_t *block_cols,
+                              const float *block_vals, int32_t *cursor, int32_t *out_cols,
+                              float *out_vals, void *stream);
+/* sklearn.preprocessing.normalize(X, norm='l1', axis=1) on a float32 CSR, in place
+ * (wavelet/src/utils.py:106-112): sequential double sum of |v| per row, v = float32(v / sum) when sum != 0 */
+int srg_csr_row_normalize_l1_f32(int64_t n, const int32_t *indptr, float *vals, void *stream);
+/* int32 exclusive prefix sum, out has n + 1 entries */
+int srg_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out, void *stream);
+
 /* ---- 8f-1: message-operator aggregation of the hop list, on the device ------------------------- */
 /* the non-learnable aggregators of SSRG/operators/message_operator/: last_message_op.py:9,
  * sum_message_op.py:9, mean_message_op.py:9, max_message_op.py:11, min_message_op.py:11,

@@ -250,6 +250,21 @@ def wavelet_threshold(coeffs, tol):
     return sp.csr_matrix(c, dtype=np.float32)
 
 
+def l1_normalize_rows(m):
+    """sklearn.preprocessing.normalize(m, norm='l1', axis=1) for a float32 CSR (wavelet/src/utils.py:106-112).
+    sklearn's _inplace_csr_row_normalize_l1 accumulates sum(|v|) sequentially in a C double and stores
+    float32(v / sum) when the sum is non-zero (checked against sklearn in tests/test_oracle.py)."""
+    m = sp.csr_matrix(m, dtype=np.float32, copy=True)
+    for i in range(m.shape[0]):
+        s, e = m.indptr[i], m.indptr[i + 1]
+        tot = 0.0
+        for v in m.data[s:e]:
+            tot += abs(float(v))
+        if tot != 0.0:
+            m.data[s:e] = (m.data[s:e].astype(np.float64) / tot).astype(np.float32)
+    return m
+
+
 # ------------------------------------------------------------------------------------------------
 # row partition (new functionality; the oracle is its 3-line definition)
 # ------------------------------------------------------------------------------------------------

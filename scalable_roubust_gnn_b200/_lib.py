@@ -77,6 +77,10 @@ SIGNATURES = {
                                        C.POINTER(_vp), C.POINTER(_vp), _i64, _vp, _vp, _vp]),
     "srg_pack_features_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp]),
     "srg_unpack_features_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),
+    "srg_dense_block_to_csr_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "srg_csr_block_scatter_f32": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "srg_csr_row_normalize_l1_f32": (C.c_int, [_i64, _vp, _vp, _vp]),
+    "srg_exclusive_scan_i32": (C.c_int, [_vp, _i64, _vp, _vp]),
     "srg_aggregate_update_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i64, _i32, _i32, C.c_float, _i32, _vp]),
     "srg_propagate_aggregate_host": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _i32, _vp, _i32, _f64, _f64,
                                                _i32, _i32, _i32, _vp, _vp, C.c_int]),

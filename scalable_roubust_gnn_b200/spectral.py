@@ -120,30 +120,69 @@ class WaveletSparsifier:
         return np.stack([heat_cheby_coeffs(s, self.lmax, self.approximation_order) for s in self.scales])
 
     def calculate_all_wavelets(self, normalize=True):
-        coeffs = self.chebyshev_coefficients()
-        blocks = [[] for _ in self.scales]
-        for j0 in range(0, self.n, self.block):
-            b = min(self.block, self.n - j0)
-            ld = (b + 1) // 2 * 2
-            x = torch.zeros((self.n, ld), dtype=torch.float64, device=self.device)
-            idx = torch.arange(b, device=self.device)
-            x[j0 + idx, idx] = 1.0
-            _, r32 = cheby_filter(self.lap, x[:, :b] if ld == b else x.as_strided((self.n, b), (ld, 1)), self.lmax,
-                                  coeffs, tol=self.tolerance, want_f32=True)
-            for s, r in enumerate(r32):
-                blocks[s].append(sp.csr_matrix(r.cpu().numpy()))
-        self.phi_matrices = [sp.hstack(bl).tocsr() for bl in blocks]
-        if normalize:
-            self.normalize_matrices()
+        """Psi(-s), Psi(+s) as scipy CSR float32 (reference: utils.py:125-138).  Chebyshev filter,
+        threshold, sparsification, block merge and L1 normalisation all run on the device; only the
+        final CSR arrays are copied back."""
+        phis = self.calculate_all_wavelets_device(normalize=normalize)
+        out = []
+        for indptr, cols, vals in phis:
+            m = int(indptr[-1].item())
+            out.append(sp.csr_matrix((vals[:m].cpu().numpy(), cols[:m].cpu().numpy(), indptr.cpu().numpy()),
+                                     shape=(self.n, self.n)))
+        self.phi_matrices = out
         return self.phi_matrices
 
+    def calculate_all_wavelets_device(self, normalize=True):
+        """Same, device resident: a list (one per scale) of (indptr int32[n+1], cols int32, vals float32)."""
+        lib = _lib.load()
+        dev_ = self.device
+        n = self.n
+        s = _stream_ptr(torch.device(dev_) if isinstance(dev_, str) else dev_)
+        coeffs = self.chebyshev_coefficients()
+        n_scales = len(self.scales)
+        blocks = [[] for _ in range(n_scales)]          # per scale: (indptr, cols, vals) of every column block
+        totals = [torch.zeros(n, dtype=torch.int32, device=dev_) for _ in range(n_scales)]
+        for j0 in range(0, n, self.block):
+            b = min(self.block, n - j0)
+            ld = (b + 1) // 2 * 2
+            x = torch.zeros((n, ld), dtype=torch.float64, device=dev_)
+            idx = torch.arange(b, device=dev_)
+            x[j0 + idx, idx] = 1.0
+            xv = x[:, :b] if ld == b else x.as_strided((n, b), (ld, 1))
+            _, r32 = cheby_filter(self.lap, xv, self.lmax, coeffs, tol=self.tolerance, want_f32=True)
+            for sc, r in enumerate(r32):
+                bptr = torch.empty(n + 1, dtype=torch.int32, device=dev_)
+                _lib.check(lib.srg_dense_block_to_csr_f32(_p(r), r.stride(0), n, b, j0, _p(bptr), None, None, 0, None, s))
+                cnt = int(bptr[-1].item())
+                bcols = torch.empty(max(cnt, 1), dtype=torch.int32, device=dev_)
+                bvals = torch.empty(max(cnt, 1), dtype=torch.float32, device=dev_)
+                _lib.check(lib.srg_dense_block_to_csr_f32(_p(r), r.stride(0), n, b, j0, _p(bptr), _p(bcols), _p(bvals),
+                                                          cnt, _p(totals[sc]), s))
+                blocks[sc].append((bptr, bcols, bvals))
+        out = []
+        for sc in range(n_scales):
+            indptr = torch.empty(n + 1, dtype=torch.int32, device=dev_)
+            _lib.check(lib.srg_exclusive_scan_i32(_p(totals[sc]), n, _p(indptr), s))
+            m = int(indptr[-1].item())
+            cols = torch.empty(max(m, 1), dtype=torch.int32, device=dev_)
+            vals = torch.empty(max(m, 1), dtype=torch.float32, device=dev_)
+            cursor = indptr[:n].clone()
+            for bptr, bcols, bvals in blocks[sc]:        # block order = ascending columns: rows come out sorted
+                _lib.check(lib.srg_csr_block_scatter_f32(n, _p(bptr), _p(bcols), _p(bvals), _p(cursor), _p(cols),
+                                                         _p(vals), s))
+            if normalize:
+                _lib.check(lib.srg_csr_row_normalize_l1_f32(n, _p(indptr), _p(vals), s))
+            out.append((indptr, cols, vals))
+        return out
+
     def normalize_matrices(self):
-        """L1 row normalisation (sklearn.preprocessing.normalize(norm='l1', axis=1), utils.py:106-112)."""
+        """L1 row normalisation of ``self.phi_matrices`` (utils.py:106-112) on the device."""
+        lib = _lib.load()
         out = []
         for phi in self.phi_matrices:
-            phi = phi.tocsr().astype(np.float32)
-            norms = np.abs(phi).sum(axis=1).A1
-            norms[norms == 0] = 1.0
-            phi.data = phi.data / np.repeat(norms, np.diff(phi.indptr)).astype(np.float32)
-            out.append(phi)
+            phi = sp.csr_matrix(phi, dtype=np.float32)
+            indptr = torch.from_numpy(phi.indptr.astype(np.int32)).to(self.device)
+            vals = torch.from_numpy(phi.data.copy()).to(self.device)
+            _lib.check(lib.srg_csr_row_normalize_l1_f32(self.n, _p(indptr), _p(vals), _stream_ptr(vals.device)))
+            out.append(sp.csr_matrix((vals.cpu().numpy(), phi.indices, phi.indptr), shape=phi.shape))
         self.phi_matrices = out

@@ -337,11 +337,23 @@ def test_wavelet_sparsifier_matches_oracle():
     lmax = oracle.estimate_lmax(lap_h)
     ws = spectral.WaveletSparsifier(w, scale=0.5, approximation_order=3, tolerance=1e-4, lmax=lmax, block=256)
     phis = ws.calculate_all_wavelets(normalize=False)
+    wants = []
     for tau, phi in zip((-0.5, 0.5), phis):
         c = oracle.cheby_coeff_heat(tau, lmax, 3)
         dense = oracle.cheby_op(lap_h, [c], np.eye(700), lmax)[0]
         want = oracle.wavelet_threshold(dense, 1e-4)
-        assert (phi != want).nnz == 0
+        want.sort_indices()
+        wants.append(want)
+        assert phi.dtype == np.float32 and phi.has_sorted_indices
+        np.testing.assert_array_equal(phi.indptr, want.indptr)       # device sparsification: exact pattern
+        np.testing.assert_array_equal(phi.indices, want.indices)
+        np.testing.assert_array_equal(phi.data, want.data)
+    # L1 row normalisation with sklearn's float32 arithmetic
+    normed = spectral.WaveletSparsifier(w, 0.5, 3, 1e-4, lmax=lmax, block=200).calculate_all_wavelets(normalize=True)
+    for phi, want in zip(normed, wants):
+        ref = oracle.l1_normalize_rows(want)
+        np.testing.assert_array_equal(phi.indices, ref.indices)
+        np.testing.assert_array_equal(phi.data, ref.data)
 
 
 # ---- power-law rows ------------------------------------------------------------------------------------

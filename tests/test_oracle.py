@@ -136,3 +136,16 @@ def test_cheby_matches_exact_heat_kernel():
         c3 = oracle.cheby_coeff_heat(tau, lmax, 3)
         got3 = oracle.cheby_op(lap, [c3], np.eye(60), lmax)[0]
         assert np.abs(got3 - exact).max() < 1e-3
+
+
+def test_l1_normalize_restatement_matches_sklearn():
+    """sklearn is installed here: pin the restated arithmetic of normalize(norm='l1') (wavelet/src/utils.py:112)."""
+    from sklearn.preprocessing import normalize
+    m = sp.random(300, 300, density=0.1, random_state=1, format="csr", dtype=np.float32)
+    m.data -= np.float32(0.3)
+    m[7, :] = 0
+    m.eliminate_zeros()
+    want = normalize(m, norm="l1", axis=1)
+    got = oracle.l1_normalize_rows(m)
+    np.testing.assert_array_equal(got.indices, want.indices)
+    np.testing.assert_array_equal(got.data, want.data)

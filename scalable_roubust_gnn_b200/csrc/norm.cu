@@ -479,7 +479,7 @@ expand_rows_kernel(const int *__restrict__ at_indptr, long long n_rows, SegPlan 
   }
 }
 
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 6)
 entry_values_kernel(long long n_rows, long long row0, long long n_cols, const int *__restrict__ at_indptr,
                     const int *__restrict__ at_indices, const int *__restrict__ at_rows,
                     const double *__restrict__ at_val, const double *__restrict__ degree,

@@ -495,7 +495,8 @@ int spmm_csr_f32_impl(const int32_t *indptr, const int32_t *indices, const float
                       int64_t ldy, int32_t F, bool accumulate, cudaStream_t s) {
   SRG_REQUIRE(n_rows >= 0 && F >= 0, "spmm: negative size (n_rows=%lld, F=%d)", (long long)n_rows, F);
   if (n_rows == 0 || F == 0) return SRG_OK;
-  SRG_REQUIRE(indptr && indices && vals && X && Y, "spmm: NULL pointer argument");
+  SRG_REQUIRE(indptr && X && Y, "spmm: NULL pointer argument");
+  SRG_REQUIRE((indices && vals) || nnz == 0, "spmm: indices / vals are NULL but nnz says the matrix has entries");
   SRG_REQUIRE(ldx >= F && ldy >= F, "spmm: leading dimension smaller than F (ldx=%lld ldy=%lld F=%d)",
               (long long)ldx, (long long)ldy, F);
   SRG_REQUIRE(X != Y, "spmm: in-place hop (X == Y) is not supported");
@@ -650,7 +651,8 @@ extern "C" int srg_spmm_csr_f32_push(const int32_t *indptr, const int32_t *indic
   SRG_REQUIRE(n_rows >= 0 && F >= 0 && dest_row0 >= 0, "spmm_push: negative size");
   SRG_REQUIRE(n_dests >= 1 && n_dests <= kMaxPeers, "spmm_push: n_dests must be 1..%d", kMaxPeers);
   if (n_rows == 0 || F == 0) return SRG_OK;
-  SRG_REQUIRE(indptr && indices && vals && X && dests, "spmm_push: NULL pointer");
+  SRG_REQUIRE(indptr && X && dests, "spmm_push: NULL pointer");
+  SRG_REQUIRE((indices && vals) || nnz == 0, "spmm_push: indices / vals are NULL but nnz says the matrix has entries");
   SRG_REQUIRE(ldx >= F && ldy >= F && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)X % 16 == 0,
               "spmm_push: needs ld %% 4 == 0 and 16-byte aligned matrices");
   const int nvec = (F + 3) / 4;

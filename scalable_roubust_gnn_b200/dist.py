@@ -24,7 +24,8 @@ import ctypes as C
 import numpy as np
 import scipy.sparse as sp
 
-__all__ = ["row_partition", "shard_rows", "propagate_sharded", "DeviceOps", "DistState", "dist_sym_norm"]
+__all__ = ["row_partition", "grid_coords", "feature_slice", "push_peers", "shard_rows", "propagate_sharded",
+           "DeviceOps", "DistState", "dist_sym_norm"]
 
 
 def row_partition(n: int, world: int):
@@ -32,6 +33,29 @@ def row_partition(n: int, world: int):
     rows_per = -(-int(n) // int(world)) if n > 0 else 0
     starts = np.minimum(np.arange(world + 1, dtype=np.int64) * rows_per, n)
     return rows_per, starts
+
+
+def grid_coords(rank: int, world: int, feat_groups: int = 1):
+    """rank -> (row block index, feature slice index) of the P_r x P_f grid, rank = ri * P_f + ci.
+    P_f = 1 is the plain row partition; P_f > 1 additionally splits the feature columns, which divides
+    the per-hop exchange volume by P_f (the exchange is NVLink-ingress bound at 8 GPUs)."""
+    if world % feat_groups:
+        raise ValueError("world size must be a multiple of feat_groups")
+    return rank // feat_groups, rank % feat_groups
+
+
+def feature_slice(f: int, feat_groups: int, ci: int):
+    """[f0, f1) of feature slice ci: contiguous blocks of ceil(F / P_f) columns."""
+    per = -(-int(f) // int(feat_groups))
+    f0 = min(ci * per, f)
+    return f0, min(f, f0 + per)
+
+
+def push_peers(rank: int, world: int, feat_groups: int = 1):
+    """Ranks that hold the same feature slice (one per row block, in row-block order): the
+    destinations of this rank's output rows."""
+    _, ci = grid_coords(rank, world, feat_groups)
+    return [r * feat_groups + ci for r in range(world // feat_groups)]
 
 
 def shard_rows(adj: sp.csr_matrix, start: int, end: int) -> sp.csr_matrix:
@@ -70,7 +94,7 @@ def propagate_sharded(ops, local_norm, x_local, k, rows_per, world):
 class DistState:
     """Per-rank device state: partition, the two full feature buffers (peer-mapped in push mode)."""
 
-    def __init__(self, n, f, world, rank, mode="push", group=None, device=None):
+    def __init__(self, n, f, world, rank, mode="push", group=None, device=None, feat_groups=1):
         import torch
         import torch.distributed as dist
 
@@ -79,16 +103,24 @@ class DistState:
         self.torch, self.dist, self._lib = torch, dist, _lib
         self.lib = _lib.load()
         self.n, self.f, self.world, self.rank, self.mode, self.group = n, f, world, rank, mode, group
-        self.rows_per, self.starts = row_partition(n, world)
-        self.row0 = int(self.starts[rank])
-        self.n_local = int(self.starts[rank + 1] - self.starts[rank])
-        self.ld = pad_ld(f)
+        self.feat_groups = int(feat_groups)
+        self.ri, self.ci = grid_coords(rank, world, self.feat_groups)
+        self.n_row_blocks = world // self.feat_groups
+        if mode != "push" and self.feat_groups != 1:
+            raise ValueError("the all-gather exchange supports the plain row partition only (feat_groups = 1)")
+        self.rows_per, self.starts = row_partition(n, self.n_row_blocks)
+        self.row0 = int(self.starts[self.ri])
+        self.n_local = int(self.starts[self.ri + 1] - self.starts[self.ri])
+        self.f0, self.f1 = feature_slice(f, self.feat_groups, self.ci)
+        self.f_loc = self.f1 - self.f0
+        self.ld = pad_ld(self.f_loc)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-        self.n_pad = self.rows_per * world
+        self.n_pad = self.rows_per * self.n_row_blocks
+        self.peers = push_peers(rank, world, self.feat_groups)
         self._raw = []          # (ptr) owned IPC allocations
         self._opened = []       # peer mappings
         self.full = []          # torch views of the two local full buffers
-        self.peer_ptrs = []     # per buffer: list of world device pointers (index = rank)
+        self.peer_ptrs = []     # per buffer: device pointers of the push peers (index = row block)
         self._tick = torch.zeros(1, dtype=torch.int32, device=self.device)
         # the input exchange runs on a side stream so that it overlaps the normalisation
         self.side = torch.cuda.Stream(device=self.device)
@@ -113,7 +145,7 @@ class DistState:
                 handles = [None] * world
                 dist.all_gather_object(handles, bytes(h), group=group)
                 ptrs = []
-                for r in range(world):
+                for r in self.peers:
                     if r == rank:
                         ptrs.append(self._raw[b].value)
                     else:
@@ -186,16 +218,16 @@ class DeviceOps:
         st = self.st
         xin = st.full[i_in]
         if st.mode == "push" and st.world > 1:
-            dests = (C.c_void_p * st.world)(*st.peer_ptrs[i_out])
+            dests = (C.c_void_p * len(st.peers))(*st.peer_ptrs[i_out])
             _lib.check(st.lib.srg_spmm_csr_f32_push(_p(local_norm.indptr), _p(local_norm.indices), _p(local_norm.data),
-                                                    st.n_local, local_norm.nnz_bound, _p(xin), st.ld, dests, st.world,
-                                                    st.row0, st.ld, st.f,
+                                                    st.n_local, local_norm.nnz_bound, _p(xin), st.ld, dests,
+                                                    len(st.peers), st.row0, st.ld, st.f_loc,
                                                     _stream_ptr(st.device)))
             self._pushed = True
         else:
             out = st.full[i_out][st.row0:st.row0 + st.n_local]
             _lib.check(st.lib.srg_spmm_csr_f32(_p(local_norm.indptr), _p(local_norm.indices), _p(local_norm.data),
-                                               st.n_local, local_norm.nnz_bound, _p(xin), st.ld, _p(out), st.ld, st.f,
+                                               st.n_local, local_norm.nnz_bound, _p(xin), st.ld, _p(out), st.ld, st.f_loc,
                                                _stream_ptr(st.device)))
             self._pushed = False
 
@@ -216,8 +248,8 @@ def start_input_exchange(st: DistState, x_local_padded):
     side.wait_stream(torch.cuda.current_stream(st.device))
     with torch.cuda.stream(side):
         if st.mode == "push" and st.world > 1:
-            dests = (C.c_void_p * st.world)(*st.peer_ptrs[0])
-            _lib.check(st.lib.srg_push_rows_f32(_p(x_local_padded), st.n_local, st.ld, dests, st.world, st.row0,
+            dests = (C.c_void_p * len(st.peers))(*st.peer_ptrs[0])
+            _lib.check(st.lib.srg_push_rows_f32(_p(x_local_padded), st.n_local, st.ld, dests, len(st.peers), st.row0,
                                                 C.c_void_p(side.cuda_stream)))
         else:
             st.full[0][st.row0:st.row0 + st.n_local].copy_(x_local_padded)
@@ -271,14 +303,20 @@ def dist_sym_norm(st: DistState, a_local, r, ppr_alpha=None):
     cap = max(nnz + n_loc, 1)
     at_indices = torch.empty(cap, dtype=torch.int32, device=dev)
     at_val = torch.empty(cap, dtype=torch.float64, device=dev) if a_local.data is not None else None
-    deg_all = torch.zeros(st.n_pad, dtype=torch.float64, device=dev)
-    deg_loc = deg_all[st.rank * st.rows_per: st.rank * st.rows_per + max(n_loc, 0)]
+    # degrees of every row block; with feature groups the gather runs over the whole world and the
+    # P_f duplicates of each block are dropped afterwards
+    gath = torch.zeros(st.world * st.rows_per, dtype=torch.float64, device=dev)
+    deg_loc = gath[st.rank * st.rows_per: st.rank * st.rows_per + max(n_loc, 0)]
     _lib.check(lib.srg_selfloop_fill_rows_csr(_p(a_local.indptr), _p(a_local.indices), _p(a_local.data),
                                               a_local.val_dtype, n_loc, nnz, st.row0, st.n, _p(at_indptr), _p(at_indices),
                                               _p(at_val), _p(deg_loc), _p(flags), s))
     if st.world > 1:
-        view = deg_all[st.rank * st.rows_per:(st.rank + 1) * st.rows_per]
-        st.dist.all_gather_into_tensor(deg_all, view, group=st.group)
+        view = gath[st.rank * st.rows_per:(st.rank + 1) * st.rows_per]
+        st.dist.all_gather_into_tensor(gath, view, group=st.group)
+    if st.feat_groups > 1:
+        deg_all = gath.view(st.n_row_blocks, st.feat_groups, st.rows_per)[:, st.ci, :].contiguous().view(-1)
+    else:
+        deg_all = gath
     dl = torch.empty(st.n_pad, dtype=torch.float64, device=dev)
     dr = torch.empty(st.n_pad, dtype=torch.float64, device=dev)
     _lib.check(lib.srg_pow_tables_f64(_p(deg_all), st.n_pad, float(r), _p(dl), _p(dr), s))

@@ -36,14 +36,18 @@ def run(args, workloads, metric, unit, emit):
 
     t0 = time.perf_counter()
     a = synth.uniform_graph(n, nnz)        # every rank regenerates the same graph (fixed seed) ...
-    st = sdist.DistState(n, f, world, rank, mode=mode)
+    # 8 GPUs are NVLink-ingress bound with a pure row partition (every rank receives 7/8 of X per hop):
+    # a 4 x 2 grid (row blocks x feature slices) halves the exchange volume
+    pf = int(os.environ.get("SRG_FEAT_GROUPS", "2" if (world >= 8 and mode == "push") else "1"))
+    st = sdist.DistState(n, f, world, rank, mode=mode, feat_groups=pf)
     s, e = st.row0, st.row0 + st.n_local
     a_loc_host = sdist.shard_rows(a, s, e)  # ... and keeps its row slice
-    x_loc_host = synth.features(n, f)[s:e]
+    x_loc_host = np.ascontiguousarray(synth.features(n, f)[s:e, st.f0:st.f1])
+    f_loc = st.f_loc
     nnz_hat = a.nnz + n
     del a
     if rank == 0:
-        print(f"[bench] world={world} mode={mode} N={n} nnz_hat={nnz_hat} F={f} K={k} rows/rank={st.rows_per} "
+        print(f"[bench] world={world} mode={mode} grid={st.n_row_blocks}x{pf} N={n} nnz_hat={nnz_hat} F={f} K={k} rows/rank={st.rows_per} "
               f"setup {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
     a_loc = dev.upload_csr(a_loc_host)
     x_loc = dev.pack_features(torch.from_numpy(np.ascontiguousarray(x_loc_host)).cuda())
@@ -85,14 +89,14 @@ def run(args, workloads, metric, unit, emit):
     ip = torch.from_numpy(a_loc_host.indptr).pin_memory()
     ii = torch.from_numpy(a_loc_host.indices).pin_memory()
     dd = torch.from_numpy(a_loc_host.data).pin_memory()
-    outs = [torch.empty((st.n_local, f), dtype=torch.float32).pin_memory() for _ in range(k)]
+    outs = [torch.empty((st.n_local, f_loc), dtype=torch.float32).pin_memory() for _ in range(k)]
 
     # device staging allocated once: the timed region is copies + kernels, not cudaMalloc
     d_ip = torch.empty_like(ip, device="cuda")
     d_ii = torch.empty_like(ii, device="cuda")
     d_dd = torch.empty_like(dd, device="cuda")
     d_x = torch.empty_like(x_pin, device="cuda")
-    d_flat = torch.empty((st.n_local, f), dtype=torch.float32, device="cuda")
+    d_flat = torch.empty((st.n_local, f_loc), dtype=torch.float32, device="cuda")
     copy_stream = torch.cuda.Stream()
 
     def e2e_step():
@@ -106,7 +110,7 @@ def run(args, workloads, metric, unit, emit):
         norm, _ = sdist.dist_sym_norm(st, a_d, 0.5)
         hops = sdist.propagate_device(st, norm, xp, k, keep_hops=True)
         for o, h in zip(outs, hops[1:]):
-            lib.srg_unpack_features_f32(h.data_ptr(), st.ld, d_flat.data_ptr(), f, st.n_local, f,
+            lib.srg_unpack_features_f32(h.data_ptr(), st.ld, d_flat.data_ptr(), f_loc, st.n_local, f_loc,
                                         torch.cuda.current_stream().cuda_stream)
             o.copy_(d_flat, non_blocking=True)
         torch.cuda.synchronize()
@@ -130,11 +134,12 @@ def run(args, workloads, metric, unit, emit):
         bg = gather_bytes(n, nnz_hat, f)
         # per-GPU roofline: each rank gathers nnz_hat/P rows; the exchange moves (P-1)/P * N*F*4 bytes in
         hop_s = t_step / k
-        nvlink_bytes = (world - 1) / world * n * f * 4
+        nvlink_bytes = (st.n_row_blocks - 1) / st.n_row_blocks * n * f_loc * 4
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(args, n, nnz_hat, f, k), exchange=mode, partition="contiguous rows"),
+                "config": dict(workload_config(args, n, nnz_hat, f, k), exchange=mode,
+                               partition=f"{st.n_row_blocks} contiguous row blocks x {pf} feature slices"),
                 "roofline": {"bound": "hbm", "kernel": "spmm_stream2_kernel (push epilogue)" if mode == "push" else "spmm_stream2_kernel + ncclAllGather",
                              "achieved": bg / world / hop_s / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": bg / world / hop_s / 1e9 / peak, "peak_source": peak_src, "traffic": None,
@@ -144,7 +149,7 @@ def run(args, workloads, metric, unit, emit):
                 "cpu_baseline": None,
                 "e2e": {"value": k * nnz_hat * f / t_e2e, "unit": unit, "ms_per_step": t_e2e * 1e3,
                         "h2d_bytes_per_step": int(ip.numel() * 4 + ii.numel() * 4 + dd.numel() * 8 + x_pin.numel() * 4),
-                        "d2h_bytes_per_step": int(k * st.n_local * f * 4), "note": "per-rank bytes; max over ranks time"},
+                        "d2h_bytes_per_step": int(k * st.n_local * f_loc * 4), "note": "per-rank bytes; max over ranks time"},
                 "gpu_launches": int(launches), "clocks": clocks}
         emit(line)
     st.close()

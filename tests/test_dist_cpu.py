@@ -95,3 +95,16 @@ def test_sharded_propagation_bitwise_equals_single_process(tmp_path, n):
     got = np.concatenate([np.load(tmp_path / f"hops_{r}.npy") for r in range(world)], axis=1)
     for h in range(k + 1):
         np.testing.assert_array_equal(got[h], want[h])
+
+
+def test_grid_coordinates_and_feature_slices():
+    """P_r x P_f grid used when the exchange is NVLink-bound: rank = ri * P_f + ci."""
+    assert [sdist.grid_coords(r, 8, 2) for r in range(8)] == [(0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1), (3, 0), (3, 1)]
+    assert sdist.push_peers(5, 8, 2) == [1, 3, 5, 7] and sdist.push_peers(2, 4, 1) == [0, 1, 2, 3]
+    assert [sdist.feature_slice(100, 2, c) for c in range(2)] == [(0, 50), (50, 100)]
+    assert [sdist.feature_slice(7, 3, c) for c in range(3)] == [(0, 3), (3, 6), (6, 7)]
+    assert sdist.feature_slice(2, 4, 3) == (2, 2)
+    cover = sorted(c for ci in range(4) for c in range(*sdist.feature_slice(129, 4, ci)))
+    assert cover == list(range(129))
+    with pytest.raises(ValueError):
+        sdist.grid_coords(0, 6, 4)

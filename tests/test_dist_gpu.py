@@ -24,7 +24,7 @@ def rank_overlap(mode, weighted):
     return mode == "push" or weighted
 
 
-def _worker(rank, world, port, n, f, k, mode, weighted, out_dir, rmat=False):
+def _worker(rank, world, port, n, f, k, mode, weighted, out_dir, rmat=False, feat_groups=1):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -34,10 +34,11 @@ def _worker(rank, world, port, n, f, k, mode, weighted, out_dir, rmat=False):
         from scalable_roubust_gnn_b200 import device as dev, dist as sdist
         adj = _graph(n, weighted, rmat)
         x = np.random.default_rng(1).random((n, f), dtype=np.float32)
-        st = sdist.DistState(n, f, world, rank, mode=mode)
+        st = sdist.DistState(n, f, world, rank, mode=mode, feat_groups=feat_groups)
         s, e = st.row0, st.row0 + st.n_local
         a_loc = dev.upload_csr(sdist.shard_rows(adj, s, e))
-        xp = dev.pack_features(torch.from_numpy(x[s:e]).cuda())
+        xp = dev.pack_features(torch.from_numpy(np.ascontiguousarray(x[s:e, st.f0:st.f1])).cuda())
+        f = st.f_loc
         if rank_overlap(mode, weighted):
             sdist.start_input_exchange(st, xp)            # overlapped input exchange variant
         norm, flags = sdist.dist_sym_norm(st, a_loc, 0.5)
@@ -93,3 +94,25 @@ def test_two_gpus_power_law_rows(tmp_path, mode):
     parts = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
     got = np.concatenate([p["hops"] for p in parts], axis=1)
     np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs 4 GPUs")
+@pytest.mark.parametrize("rmat", [False, True])
+def test_four_gpus_row_by_feature_grid(tmp_path, rmat):
+    """2 row blocks x 2 feature slices (the layout used at 8 GPUs to halve the exchange): every rank's
+    tile equals the corresponding tile of the single-GPU result bit for bit."""
+    from scalable_roubust_gnn_b200 import device as dev, dist as sdist
+    world, n, f, k, pf = 4, 40001, 100, 3, 2
+    port = 29800 + (os.getpid() % 150) + (1 if rmat else 0)
+    mp.spawn(_worker, args=(world, port, n, f, k, "push", False, str(tmp_path), rmat, pf), nprocs=world, join=True)
+    adj = _graph(n, False, rmat)
+    x = np.random.default_rng(1).random((n, f), dtype=np.float32)
+    norm, flags, _ = dev.sym_norm(dev.upload_csr(adj), 0.5)
+    hops = dev.propagate(norm, dev.pack_features(torch.from_numpy(x).cuda()), f, k)
+    want = np.stack([h[:, :f].cpu().numpy() for h in hops])
+    for r in range(world):
+        ri, ci = sdist.grid_coords(r, world, pf)
+        rows_per, starts = sdist.row_partition(n, world // pf)
+        f0, f1 = sdist.feature_slice(f, pf, ci)
+        got = np.load(tmp_path / f"r{r}.npz")["hops"]
+        np.testing.assert_array_equal(got, want[:, starts[ri]:starts[ri + 1], f0:f1])

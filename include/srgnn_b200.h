@@ -284,6 +284,7 @@ int srg_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out, void *str
 #define SRG_AGG_MIN 5
 #define SRG_AGG_CONCAT 6
 #define SRG_AGG_WEIGHTED 7
+#define SRG_AGG_NAFS 8 /* over_smooth_distance_op.py:11-33; srg_propagate_aggregate_host only */
 /* fold one hop matrix x (n x ld_x) into acc[:, col0:col0+F] (n x ld_acc).  first != 0 initialises acc
  * from x; mode -1 finalises a mean (acc / weight).  The arithmetic is the reference's torch
  * expression evaluated in hop order (sequential fp32 adds; weighted: product first). */
@@ -291,12 +292,24 @@ int srg_aggregate_update_f32(float *acc, int64_t ld_acc, int32_t col0, const flo
                              int64_t n, int32_t F, int32_t mode, float weight, int32_t first,
                              void *stream);
 /*
+ * NAFS over-smoothing-distance aggregation (OverSmoothDistanceWeightedOp.combine,
+ * SSRG/operators/message_operator/over_smooth_distance_op.py:11-33; aggregator of SSRG/models/nafs.py:12):
+ *   score[i][j] = ((x0[i] . xj[i]) / (||xj[i]|| + 1e-10)) / (||x0[i]|| + 1e-10),
+ *   weight[i]   = softmax_j(score[i]),   out[i] = sum_j weight[i][j] * xj[i]   (fp32, hop order).
+ * hops: HOST array of n_hops (<= 64) DEVICE pointers to n x ld matrices (hops[0] = the input
+ * features); out: device n x ld_out; weights_out: optional device n x n_hops (the softmax weights).
+ * The reference walks the rows in a Python loop; one warp per row here.
+ */
+int srg_nafs_combine_f32(const float *const *hops, int32_t n_hops, int64_t ld, int64_t n, int32_t F,
+                         float *out, int64_t ld_out, float *weights_out, void *stream);
+/*
  * srg_propagate_host + the aggregation, with ONLY the aggregate coming back:
  *   out_agg (host, n x F_out, F_out = F or (agg_end-agg_start)*F for CONCAT) =
  *       msg_op.aggregate(graph_op.propagate(adj, feature))  over the hop slice [agg_start, agg_end)
  *   agg_weights: host array of agg_end-agg_start floats (WEIGHTED only).
  * Two ping-pong hop buffers + the accumulator stay on the device; K-1 of the K device->host copies
- * of srg_propagate_host disappear.
+ * of srg_propagate_host disappear.  SRG_AGG_NAFS keeps all K+1 hop buffers (its weights need every
+ * hop) and takes the whole list (agg_start / agg_end are ignored).
  */
 int srg_propagate_aggregate_host(const int32_t *indptr, const int32_t *indices, const void *data,
                                  int val_dtype, int64_t n, int64_t nnz, const float *features,

@@ -15,6 +15,7 @@ What it restates (file:line in /root/reference, SSRG = "Scalable Spectral Robust
   cheby_*           pygsp 0.5.1 (PyPI "PyGSP", un-pinned and absent from /root/reference):
                     call sites wavelet/src/utils.py:83,95,131-133 and
                     SSRG/models/base_scalable/base_model.py:184-189,243  -- PARITY UNPINNED
+  nafs_combine      SSRG/operators/message_operator/over_smooth_distance_op.py:11-33
   row_partition     new functionality (no reference code): the bit-exact partition map
 
 Pinning: tests/test_oracle.py checks these against tests/golden/*.npz (outputs of the real
@@ -263,6 +264,30 @@ def l1_normalize_rows(m):
         if tot != 0.0:
             m.data[s:e] = (m.data[s:e].astype(np.float64) / tot).astype(np.float32)
     return m
+
+
+# ------------------------------------------------------------------------------------------------
+# NAFS over-smoothing-distance aggregator (SSRG/operators/message_operator/over_smooth_distance_op.py)
+# ------------------------------------------------------------------------------------------------
+def nafs_combine(feat_list, return_weights=False):
+    """OverSmoothDistanceWeightedOp.combine (:11-33) in float32 numpy: cosine score of every hop row
+    against the input row (:13-19), softmax over the hops (:22), weighted sum in hop order (:27-31;
+    the reference's per-row Python loop is the same arithmetic as these whole-array statements)."""
+    feats = [np.asarray(f, dtype=np.float32) for f in feat_list]
+    x0 = feats[0]
+    eps = np.float32(1e-10)
+    norm_fea = np.sqrt((x0 * x0).sum(1, dtype=np.float32)) + eps
+    scores = []
+    for fea in feats:
+        norm_cur = np.sqrt((fea * fea).sum(1, dtype=np.float32)) + eps
+        scores.append(((x0 * fea).sum(1, dtype=np.float32) / norm_cur) / norm_fea)
+    s = np.stack(scores, axis=1)
+    e = np.exp(s - s.max(1, keepdims=True), dtype=np.float32)
+    w = e / e.sum(1, keepdims=True, dtype=np.float32)
+    out = np.zeros_like(x0)
+    for j, fea in enumerate(feats):
+        out = out + w[:, j:j + 1] * fea
+    return (out, w) if return_weights else out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@ SRG_FLAG_UNSORTED, SRG_FLAG_ASYMMETRIC, SRG_FLAG_ZERO_PRODUCT, SRG_FLAG_BAD_INDE
 SRG_FLAG_EXPLICIT_ZERO = 32
 SRG_VAL_HAS_ZEROS = 0x100
 SRG_AGG_NONE, SRG_AGG_LAST, SRG_AGG_SUM, SRG_AGG_MEAN, SRG_AGG_MAX, SRG_AGG_MIN, SRG_AGG_CONCAT, SRG_AGG_WEIGHTED = range(8)
+SRG_AGG_NAFS = 8
 
 
 class SrgError(RuntimeError):
@@ -82,6 +83,7 @@ SIGNATURES = {
     "srg_csr_row_normalize_l1_f32": (C.c_int, [_i64, _vp, _vp, _vp]),
     "srg_exclusive_scan_i32": (C.c_int, [_vp, _i64, _vp, _vp]),
     "srg_aggregate_update_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i64, _i32, _i32, C.c_float, _i32, _vp]),
+    "srg_nafs_combine_f32": (C.c_int, [C.POINTER(_vp), _i32, _i64, _i64, _i32, _vp, _i64, _vp, _vp]),
     "srg_propagate_aggregate_host": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _i32, _vp, _i32, _f64, _f64,
                                                _i32, _i32, _i32, _vp, _vp, C.c_int]),
     "srg_propagate_host": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _i32, _vp, _i32, _f64, _f64,

@@ -376,7 +376,7 @@ static int propagate_attempt(const int32_t *indptr, const int32_t *indices, cons
     std::vector<float *> hops(K + 1, nullptr);
     const bool have_feat = (int64_t)F * n > 0;
     // with an aggregation only two hop buffers ping-pong and an accumulator collects the result
-    const int n_bufs = do_agg ? std::min(K + 1, 2) : K + 1;
+    const int n_bufs = (do_agg && agg->mode != SRG_AGG_NAFS) ? std::min(K + 1, 2) : K + 1;
     if (have_feat)
       for (int k = 0; k <= K; ++k) {
         if (k < n_bufs) {
@@ -457,7 +457,7 @@ static int propagate_attempt(const int32_t *indptr, const int32_t *indices, cons
         if (k > 0 &&
             (rc = spmm_csr_f32_impl(no.indptr, no.indices, no.val32, n, nnz + n, hops[k - 1], ld, hops[k], ld, F, false, s_c)))
           return rc;
-        if (agg->mode == SRG_AGG_LAST || k < agg->start || k >= agg->end) continue;
+        if (agg->mode == SRG_AGG_LAST || agg->mode == SRG_AGG_NAFS || k < agg->start || k >= agg->end) continue;
         const int slot = k - agg->start;
         const float wgt = (agg->mode == SRG_AGG_WEIGHTED) ? agg->weights[slot] : 1.0f;
         const int col0 = (agg->mode == SRG_AGG_CONCAT) ? slot * F : 0;
@@ -468,6 +468,9 @@ static int propagate_attempt(const int32_t *indptr, const int32_t *indices, cons
       }
       if (agg->mode == SRG_AGG_MEAN &&
           (rc = srg_aggregate_update_f32(d_acc, ld_acc, 0, nullptr, 0, n, F, -1, (float)agg_cnt, 0, s_c)))
+        return rc;
+      if (agg->mode == SRG_AGG_NAFS &&
+          (rc = srg_nafs_combine_f32(hops.data(), K + 1, ld, n, F, d_acc, ld_acc, nullptr, s_c)))
         return rc;
       const float *res = (agg->mode == SRG_AGG_LAST) ? hops[K] : d_acc;
       const int64_t ld_res = (agg->mode == SRG_AGG_LAST) ? ld : ld_acc;
@@ -529,11 +532,19 @@ extern "C" int srg_propagate_aggregate_host(const int32_t *indptr, const int32_t
                                             double ppr_alpha, int32_t agg_mode, int32_t agg_start,
                                             int32_t agg_end, const float *agg_weights, float *out_agg,
                                             int device) {
-  SRG_REQUIRE(agg_mode >= SRG_AGG_LAST && agg_mode <= SRG_AGG_WEIGHTED, "propagate_aggregate: bad agg_mode %d", agg_mode);
+  SRG_REQUIRE(agg_mode >= SRG_AGG_LAST && agg_mode <= SRG_AGG_NAFS, "propagate_aggregate: bad agg_mode %d", agg_mode);
   SRG_REQUIRE(K >= 0, "propagate_aggregate: K must be >= 0");
   if (agg_mode == SRG_AGG_LAST) {
     agg_start = K;
     agg_end = K + 1;
+  }
+  if (agg_mode == SRG_AGG_NAFS) {
+    agg_start = 0;
+    agg_end = K + 1;
+    if (K + 1 > 64) {
+      set_err("propagate_aggregate: NAFS aggregation supports at most 64 hop matrices (K = %d)", K);
+      return SRG_ERR_UNSUPPORTED;
+    }
   }
   SRG_REQUIRE(agg_start >= 0 && agg_start < agg_end && agg_end <= K + 1,
               "propagate_aggregate: hop slice [%d, %d) outside [0, %d]", agg_start, agg_end, K + 1);

@@ -81,3 +81,65 @@ def test_fused_aggregation_wide_features_and_masks():
     hops = gop.propagate(adj, x)
     for op in (LastMessageOp(), MeanMessageOp(0, 5), ConcatMessageOp(0, 5), SimMaxMessageOp(1, 4)):
         np.testing.assert_array_equal(gop.propagate_aggregate(adj, x, op).numpy(), op.aggregate(hops).numpy())
+
+
+# ---- NAFS aggregator (over_smooth_distance_op.py): golden outputs of the reference class ------------
+@pytest.fixture(scope="module")
+def golden_ext():
+    import os
+    from conftest import GOLDEN as GOLDEN_DIR
+    return np.load(os.path.join(GOLDEN_DIR, "reference_ext.npz"))
+
+
+def test_nafs_op_contract():
+    from scalable_roubust_gnn_b200.operators import OverSmoothDistanceWeightedOp
+    op = OverSmoothDistanceWeightedOp()
+    assert op.aggr_type == "over_smooth_dis_weighted"
+    with pytest.raises(TypeError, match="The feature matrices must be tensors!"):
+        op.aggregate([np.ones((2, 2), dtype=np.float32)])
+    assert op.fused_spec(4)[0] == 8
+
+
+@pytest.mark.gpu
+def test_nafs_combine_vs_reference_golden(golden_ext):
+    from scalable_roubust_gnn_b200.operators import OverSmoothDistanceWeightedOp
+    op = OverSmoothDistanceWeightedOp()
+    got = op.aggregate([torch.from_numpy(f) for f in golden_ext["nafs2_feats"]])
+    assert isinstance(got, torch.Tensor) and got.dtype == torch.float32 and not got.is_cuda
+    np.testing.assert_allclose(got.numpy(), golden_ext["nafs2_out"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_nafs_fused_vs_reference_golden_and_unfused(golden_ext):
+    from helpers import sym_graph
+    from scalable_roubust_gnn_b200.operators import OverSmoothDistanceWeightedOp
+    adj, x = sym_graph(300, 1500, 2), golden_ext["nafs_x"]
+    gop, op = SymLaplacianGraphOp(3, r=0.5), OverSmoothDistanceWeightedOp()
+    fused = gop.propagate_aggregate(adj, x, op)
+    np.testing.assert_allclose(fused.numpy(), golden_ext["nafs_out"], rtol=1e-5, atol=1e-6)
+    unfused = op.aggregate(gop.propagate(adj, x))
+    np.testing.assert_array_equal(fused.numpy(), unfused.numpy())      # same kernel, same hop values
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("f,k", [(100, 4), (7, 1), (257, 2), (64, 0)])
+def test_nafs_device_vs_oracle(f, k):
+    from helpers import sym_graph
+    from scalable_roubust_gnn_b200.operators.message_operator import nafs_combine_device
+    n = 2000
+    adj = sym_graph(n, 12000, 5)
+    x = (np.random.default_rng(3).random((n, f), dtype=np.float32) - 0.4)
+    x[11] = 0.0
+    hops, _ = oracle.propagate(adj, x, k, r=0.5)
+    want, w_want = oracle.nafs_combine(hops, return_weights=True)
+    dev = [torch.from_numpy(h).cuda() for h in hops]
+    out, w = nafs_combine_device(dev, want_weights=True)
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(w.cpu().numpy(), w_want, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(w.sum(1).cpu().numpy(), 1.0, atol=1e-6)
+    # padded device layout (ld = roundup(F, 8)): pad columns stay untouched
+    from scalable_roubust_gnn_b200 import device as sdev
+    padded = [sdev.pack_features(h) for h in dev]
+    outp = nafs_combine_device(padded, f=f)
+    np.testing.assert_array_equal(outp[:, :f].cpu().numpy(), out.cpu().numpy())
+    assert float(outp[:, f:].abs().sum()) == 0.0

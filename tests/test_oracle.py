@@ -1,6 +1,7 @@
 """CPU suite: the oracle against the golden vectors produced by the real reference, and against
 the reference's own matmul.c compiled in place (oracle/_ref)."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -8,6 +9,7 @@ import scipy.sparse as sp
 import torch
 
 import oracle
+from conftest import GOLDEN as GOLDEN_DIR
 from helpers import assert_same_structure, golden_csr, sym_graph, ulp_diff64
 
 GRAPHS = ["cora", "rand_unw", "rand_w", "loop_iso"]
@@ -149,3 +151,15 @@ def test_l1_normalize_restatement_matches_sklearn():
     got = oracle.l1_normalize_rows(m)
     np.testing.assert_array_equal(got.indices, want.indices)
     np.testing.assert_array_equal(got.data, want.data)
+
+
+# ---- NAFS aggregator: the restatement against the reference's own outputs ------------
+def test_nafs_combine_matches_reference_golden():
+    g = np.load(os.path.join(GOLDEN_DIR, "reference_ext.npz"))
+    out = oracle.nafs_combine(list(g["nafs2_feats"]))
+    np.testing.assert_allclose(out, g["nafs2_out"], rtol=1e-5, atol=1e-6)
+    # the propagated list: hops rebuilt with the (pinned) oracle hop
+    x = g["nafs_x"]
+    hops, _ = oracle.propagate(sym_graph(300, 1500, 2), x, 3, r=0.5)
+    np.testing.assert_array_equal(hops[3], g["nafs_hop3"])
+    np.testing.assert_allclose(oracle.nafs_combine(hops), g["nafs_out"], rtol=1e-5, atol=1e-6)

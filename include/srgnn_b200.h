@@ -158,6 +158,17 @@ int srg_sym_norm_csr_general(const int32_t *indptr, const int32_t *indices, cons
                              int32_t *out_flags, void *stream);
 
 /*
+ * Transpose of a float32 CSR (square, n x n): the matrix the backward pass of the per-epoch sparse
+ * product needs (torch.mm(self.adj, x) in Layer2GraphConvolution.forward,
+ * SSRG/models/base_scalable/simple_models.py:228,233: grad_x = adj^T grad_y).  Stable key sort, so a
+ * canonical input gives a canonical output; `nnz` is the capacity of the arrays, the live entry count
+ * is indptr[n] on the device.  vals NULL = all ones.  Outputs have capacity nnz (tail zero-filled).
+ */
+int srg_csr_transpose_f32(const int32_t *indptr, const int32_t *indices, const float *vals, int64_t n,
+                          int64_t nnz, int32_t *out_indptr, int32_t *out_indices, float *out_vals,
+                          int32_t *out_flags, void *stream);
+
+/*
  * Canonical form of a CSR with unsorted rows and/or duplicate entries (what scipy's
  * `adj.tocoo() + eye` does first, SSRG/operators/utils.py:82): rows sorted by column, duplicates
  * summed in stored order.  Outputs have capacity nnz; *out_nnz_dev (device int32) = entries kept.

@@ -61,6 +61,7 @@ SIGNATURES = {
     "srg_norm_values_rows_csr": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _f64, C.c_int, _vp, _vp, _vp, _vp]),
     "srg_sym_norm_csr_general": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "srg_csr_canonicalize": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "srg_csr_transpose_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "srg_edge_gather_i64": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "srg_edges_to_sym_csr": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "srg_apply_feature_mask_f32": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),

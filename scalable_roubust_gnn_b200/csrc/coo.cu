@@ -180,6 +180,40 @@ __global__ void finalize_general_kernel(const uint64_t *__restrict__ keys, const
 
 __global__ void set_int_kernel(int *p, const int *src) { *p = *src; }
 
+// transpose keys of a float32 CSR: entry (a, b) -> key (b << 32 | a), payload = value.  Slots past
+// indptr[n] (the arrays may be longer than the matrix) get a key that sorts behind every entry.
+__global__ void transpose_keys_f32_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
+                                          const float *__restrict__ vals, long long n, long long cap,
+                                          uint64_t *__restrict__ keys, float *__restrict__ pay,
+                                          int *__restrict__ flags) {
+  const long long a = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (a < n) {
+    for (int j = indptr[a] + lane; j < indptr[a + 1]; j += 32) {
+      const int b = indices[j];
+      const bool bad = (b < 0 || b >= n);
+      if (bad) atomicOr(flags, SRG_FLAG_BAD_INDEX);
+      keys[j] = bad ? ((uint64_t)n << 32) : (((uint64_t)b << 32) | (uint64_t)a);
+      pay[j] = vals ? vals[j] : 1.0f;
+    }
+  } else if (a == n) {
+    for (long long j = (long long)indptr[n] + lane; j < cap; j += 32) {
+      keys[j] = (uint64_t)n << 32;
+      pay[j] = 0.f;
+    }
+  }
+}
+
+__global__ void split_keys_f32_kernel(const uint64_t *__restrict__ keys, const float *__restrict__ pay,
+                                      long long n, long long cap, int *__restrict__ out_indices,
+                                      float *__restrict__ out_vals) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  const bool live = (long long)(keys[i] >> 32) < n;  // padding / bad-index keys carry row n
+  out_indices[i] = live ? (int)(keys[i] & 0xffffffffu) : 0;
+  out_vals[i] = live ? pay[i] : 0.f;
+}
+
 }  // namespace srg
 
 using namespace srg;
@@ -289,6 +323,42 @@ extern "C" int srg_csr_canonicalize(const int32_t *indptr, const int32_t *indice
   }
   if (!rc) rc = keys_to_csr(keys + m, vals + m, m, n, out_indptr, out_indices, out_vals, out_nnz_dev, s);
   cudaFreeAsync(vals, s);
+  cudaFreeAsync(keys, s);
+  return rc;
+}
+
+extern "C" int srg_csr_transpose_f32(const int32_t *indptr, const int32_t *indices, const float *vals, int64_t n,
+                                     int64_t nnz, int32_t *out_indptr, int32_t *out_indices, float *out_vals,
+                                     int32_t *out_flags, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n >= 0 && nnz >= 0, "csr_transpose: negative size");
+  SRG_REQUIRE(indptr && out_indptr && out_flags, "csr_transpose: NULL pointer");
+  SRG_REQUIRE(nnz == 0 || (indices && out_indices && out_vals), "csr_transpose: NULL pointer");
+  SRG_REQUIRE(n < 2147483647LL && nnz <= 2147483647LL, "csr_transpose: exceeds the int32 CSR range");
+  cudaStream_t s = as_stream(stream);
+  const int64_t m = nnz;  // capacity of the arrays; the live entry count is indptr[n] (device side)
+  uint64_t *keys = nullptr;
+  float *pay = nullptr;
+  SRG_CUDA(cudaMallocAsync(&keys, (size_t)(m > 0 ? 2 * m : 1) * sizeof(uint64_t), s));
+  SRG_CUDA(cudaMallocAsync(&pay, (size_t)(m > 0 ? 2 * m : 1) * sizeof(float), s));
+  if (m > 0) {
+    transpose_keys_f32_kernel<<<(unsigned)ceil_div64((n + 1) * 32, 256), 256, 0, s>>>(indptr, indices, vals, n, m, keys,
+                                                                                    pay, out_flags);
+    SRG_LAUNCHED();
+    // stable: equal columns keep their row order, so every transposed row comes out sorted
+    rc = sort_pairs<float>(keys, keys + m, pay, pay + m, m, 32 + bits_for(n + 1), s);
+  }
+  if (!rc) {
+    // rows of the transpose = columns of the input; padding keys (row n) sort last and are not counted
+    row_lower_bound_kernel<<<(unsigned)ceil_div64(n + 1, 256), 256, 0, s>>>(keys + m, indptr + n, n, out_indptr);
+    SRG_LAUNCHED();
+    if (m > 0) {
+      split_keys_f32_kernel<<<(unsigned)ceil_div64(m, 256), 256, 0, s>>>(keys + m, pay + m, n, m, out_indices, out_vals);
+      SRG_LAUNCHED();
+    }
+  }
+  cudaFreeAsync(pay, s);
   cudaFreeAsync(keys, s);
   return rc;
 }

@@ -6,6 +6,10 @@ Second batch of fixtures (the "next" rows of SURVEY.md §8f), same recipe as mak
 reference's own classes imported from /root/reference, run on small inputs, outputs recorded.
   * nafs_*   OverSmoothDistanceWeightedOp.aggregate on a reference hop list
              (SSRG/operators/message_operator/over_smooth_distance_op.py)
+  * gcn_*    one forward + backward of the reference's Layer2GraphConvolution
+             (SSRG/models/base_scalable/simple_models.py:214-240) on the adjacency produced by
+             SymLaplacianGraphOp.construct_adj + scipy_sparse_mat_to_torch_sparse_tensor
+             (SSRG/models/utils.py:5-15), dropout off: outputs, loss, parameter and input gradients
 """
 import os
 import sys
@@ -36,6 +40,35 @@ def main():
     import torch
     out["nafs2_feats"] = np.stack(feats)
     out["nafs2_out"] = OverSmoothDistanceWeightedOp().aggregate([torch.from_numpy(f) for f in feats]).numpy()
+
+    # ---- per-epoch sparse product of the GCN model (forward + backward) ---------------------------
+    sys.modules["torch_sparse"].spspmm = None
+    sys.modules["torch_sparse"].spmm = None
+    from models.base_scalable.simple_models import Layer2GraphConvolution
+    from models.utils import scipy_sparse_mat_to_torch_sparse_tensor
+    for tag, r in (("gcn", 0.5), ("gcn_r03", 0.3)):
+        torch.manual_seed(7)
+        a = sym_graph(400, 2400, 6)
+        xg = rng.random((400, 20), dtype=np.float32)
+        adj_n = Sym(None, r=r).construct_adj(a)
+        layer = Layer2GraphConvolution(feat_dim=20, hidden_dim=16, output_dim=5, dropout=0.5)
+        layer.eval()
+        layer.adj = scipy_sparse_mat_to_torch_sparse_tensor(adj_n)
+        xt = torch.from_numpy(xg).requires_grad_(True)
+        y = layer(xt)
+        target = torch.from_numpy(rng.integers(0, 5, 400))
+        loss = torch.nn.functional.cross_entropy(y, target)
+        loss.backward()
+        out[f"{tag}_x"] = xg
+        out[f"{tag}_target"] = target.numpy()
+        out[f"{tag}_y"] = y.detach().numpy()
+        out[f"{tag}_loss"] = np.array([loss.item()], dtype=np.float32)
+        out[f"{tag}_grad_x"] = xt.grad.numpy()
+        for k, v in layer.state_dict().items():
+            out[f"{tag}_w_{k}"] = v.numpy()
+        for k, v in layer.named_parameters():
+            if v.grad is not None:
+                out[f"{tag}_g_{k}"] = v.grad.numpy()
 
     np.savez_compressed(os.path.join(HERE, "reference_ext.npz"), **out)
     print("wrote", sorted(out))

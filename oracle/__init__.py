@@ -15,6 +15,7 @@ What it restates (file:line in /root/reference, SSRG = "Scalable Spectral Robust
   cheby_*           pygsp 0.5.1 (PyPI "PyGSP", un-pinned and absent from /root/reference):
                     call sites wavelet/src/utils.py:83,95,131-133 and
                     SSRG/models/base_scalable/base_model.py:184-189,243  -- PARITY UNPINNED
+  spectral_preprocess  SSRG/models/base_scalable/base_model.py:180-221 (on top of cheby_*: PARITY UNPINNED)
   nafs_combine      SSRG/operators/message_operator/over_smooth_distance_op.py:11-33
   row_partition     new functionality (no reference code): the bit-exact partition map
 
@@ -264,6 +265,23 @@ def l1_normalize_rows(m):
         if tot != 0.0:
             m.data[s:e] = (m.data[s:e].astype(np.float64) / tot).astype(np.float32)
     return m
+
+
+def spectral_preprocess(adj, feature, scale, order, tol, lmax, return_phis=False):
+    """SpectralModel.preprocess (SSRG/models/base_scalable/base_model.py:180-221): wavelets for the scales
+    (-scale, +scale) (:185-192, impulse blocks :236-265 are the same arithmetic as the full identity),
+    L1 normalisation (:287-290), then [X | relu((Psi_0 Psi_1) X)] with the sparse-sparse product formed
+    first in float32 (spspmm :208-214, spmm :215-219) and the concat of :221."""
+    lap = combinatorial_laplacian(adj)
+    n = lap.shape[0]
+    coeffs = [cheby_coeff_heat(t, lmax, order) for t in (-scale, scale)]
+    res = cheby_op(lap, coeffs, np.eye(n), lmax)
+    phis = [l1_normalize_rows(wavelet_threshold(r, tol)) for r in res]
+    x = np.asarray(feature, dtype=np.float32)
+    prod = (phis[0] @ phis[1]).astype(np.float32)
+    loc = np.maximum((prod @ x).astype(np.float32), np.float32(0))
+    out = np.concatenate([x, loc], axis=1)
+    return (out, phis) if return_phis else out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -20,7 +20,8 @@ import torch
 from . import _lib
 from .device import DeviceCSR, _p, _stream_ptr, upload_csr
 
-__all__ = ["laplacian", "heat_cheby_coeffs", "estimate_lmax", "cheby_filter", "WaveletSparsifier"]
+__all__ = ["laplacian", "heat_cheby_coeffs", "estimate_lmax", "cheby_filter", "WaveletSparsifier", "SpectralModel",
+           "wavelet_localize"]
 
 
 def laplacian(w: DeviceCSR):
@@ -186,3 +187,79 @@ class WaveletSparsifier:
             _lib.check(lib.srg_csr_row_normalize_l1_f32(self.n, _p(indptr), _p(vals), _stream_ptr(vals.device)))
             out.append(sp.csr_matrix((vals.cpu().numpy(), phi.indices, phi.indptr), shape=phi.shape))
         self.phi_matrices = out
+
+
+def wavelet_localize(phi, phi_inverse, x, theta=None):
+    """``Psi (theta * (Psi^-1 x))`` on the device, differentiable in ``x`` and ``theta``.
+
+    The reference forms the sparse product first — ``spspmm(Psi [diag(theta)], Psi^-1)`` followed by
+    ``spmm(product, x)`` (SSRG/models/base_scalable/base_model.py:208-219; wavelet/src/gwnn_layer.py:
+    59-85, 111-128) — whose pattern is the 2m-hop neighbourhood.  The same linear map is applied here
+    as two hops of the propagation kernel with the diagonal in between: no fill-in, no SpGEMM, and the
+    result differs from the reference's association order by fp32 rounding only.
+    ``phi`` / ``phi_inverse``: ``sparse_mm.DeviceAdj``; ``x``: cuda float32 n x F; ``theta``: n or n x 1.
+    """
+    y = phi_inverse.mm(x)
+    if theta is not None:
+        y = y * theta.reshape(-1, 1)
+    return phi.mm(y)
+
+
+class SpectralModel:
+    """Pre-processing of the reference's wavelet model on the device.
+
+    Mirror of ``SpectralModel.__init__`` / ``.preprocess``
+    (SSRG/models/base_scalable/base_model.py:171-221): heat-kernel wavelets Psi(-s), Psi(+s) by the
+    Chebyshev recurrence in 1000-column impulse blocks (:236-265), threshold, float32 CSR, L1 row
+    normalisation (:287-290), then ``processed_feature = [X | relu(Psi(-s) Psi(+s) X)]`` (:208-221).
+    Everything between the adjacency upload and the final feature matrix stays on the GPU.
+    ``lmax``: pygsp's ARPACK estimate is an input here (``estimate_lmax`` reproduces its call).
+    """
+
+    def __init__(self, scale, approximation_order, tolerance, lmax=None, block=1000, device="cuda"):
+        self.scales = [-scale, scale]
+        self.approximation_order = approximation_order
+        self.tolerance = tolerance
+        self.lmax = lmax
+        self.block = block
+        self.device = device
+        self.phi_device = []          # per scale: (indptr, cols, vals) on the device
+        self._phi_host = None
+        self.processed_feature = None
+        self.ncount = None
+
+    @property
+    def phi_matrices(self):
+        """The two normalised wavelet matrices as scipy CSR float32 (copied back on first use)."""
+        if self._phi_host is None:
+            self._phi_host = []
+            for indptr, cols, vals in self.phi_device:
+                m = int(indptr[-1].item())
+                self._phi_host.append(sp.csr_matrix((vals[:m].cpu().numpy(), cols[:m].cpu().numpy(),
+                                                     indptr.cpu().numpy()), shape=(self.ncount, self.ncount)))
+        return self._phi_host
+
+    def density(self):
+        """Fractions of stored entries (calculate_density, base_model.py:292-298)."""
+        return [int(p[0][-1].item()) / float(self.ncount) ** 2 for p in self.phi_device]
+
+    def preprocess(self, adj, feature):
+        from .sparse_mm import DeviceAdj
+        if isinstance(feature, torch.Tensor):
+            feature = feature.numpy()
+        feature = np.ascontiguousarray(feature, dtype=np.float32)
+        ws = WaveletSparsifier(adj, self.scales[1], self.approximation_order, self.tolerance, lmax=self.lmax,
+                               block=self.block, device=self.device)
+        if feature.ndim != 2 or feature.shape[0] != ws.n:
+            raise ValueError("Dimension mismatch detected for the adjacency and the feature matrix!")
+        self.lmax = ws.lmax
+        self.ncount = ws.n
+        self.phi_device = ws.calculate_all_wavelets_device(normalize=True)
+        self._phi_host = None
+        adjs = []
+        for indptr, cols, vals in self.phi_device:
+            adjs.append(DeviceAdj(DeviceCSR(indptr, cols, vals, ws.n, -1)))
+        x = torch.from_numpy(feature).to(self.device)
+        localized = torch.relu(wavelet_localize(adjs[0], adjs[1], x))
+        self.processed_feature = torch.cat((x, localized), dim=1).cpu()
+        return self.processed_feature

@@ -32,6 +32,8 @@ WORKLOADS = {
     "pubmed": (19717, 88648, 500, 5),
     "arxiv": (169343, 1166243, 128, 3),
     "products": (2449029, 61859140, 100, 3),
+    # config 5: power-law (scrambled R-MAT) graph built per rank on the device; multi-GPU runs only
+    "papers100M": (111059956, 1615685872, 128, 3),
 }
 METRIC = "K-hop SpMM propagation throughput (normalisation + K hops)"
 UNIT = "edge*feat/s"
@@ -200,7 +202,8 @@ def run_reference(args):
 
 
 def workload_config(args, n, nnz_hat, f, k):
-    return {"workload": f"{args.workload}-shaped synthetic uniform graph", "N": n, "nnz_hat": int(nnz_hat), "F": f,
+    kind = "power-law (scrambled R-MAT, device-generated)" if args.workload.startswith("papers100M") else "uniform"
+    return {"workload": f"{args.workload}-shaped synthetic {kind} graph", "N": n, "nnz_hat": int(nnz_hat), "F": f,
             "K": k, "r": 0.5, "scale": args.scale, "l2": "inputs (X, CSR) exceed L2; no flush needed" if n * f * 4 > 126e6
             else "flushed between steps"}
 

@@ -157,6 +157,22 @@ int srg_sym_norm_csr_general(const int32_t *indptr, const int32_t *indices, cons
                              double *out_degree, double *out_val_f64, float *out_val_f32,
                              int32_t *out_flags, void *stream);
 
+/* ---- synthetic inputs of the named shapes, generated on the device --------------------
+ * Not a reference interface: BASELINE.json's configs 4 (power-law variant) and 5 are synthetic R-MAT
+ * graphs too large to build on the host per rank.  Rows [row0, row1) of the symmetrised, duplicate-free,
+ * loop-free adjacency (pattern only; every value is 1) of an R-MAT(a, b, c, 1-a-b-c) graph with
+ * 2^scale ids scrambled by a fixed bijection, ids >= n rejected, m_draw edge ids drawn.  Counter-based:
+ * edge id e alone determines the pair, so every rank can produce its own shard and the union over
+ * the ranks is one well-defined graph.  out_indptr: row1-row0+1 entries (local rows, GLOBAL column ids),
+ * out_indices capacity `cap` (SRG_ERR_RANGE when the shard needs more); *out_nnz (host) = entries.
+ * Synchronises the stream (set-up path).  numpy restatement: scalable_roubust_gnn_b200/synth.py. */
+int srg_synth_rmat_shard_csr(uint64_t seed, int32_t scale, int64_t m_draw, double a, double b, double c,
+                             int64_t n, int64_t row0, int64_t row1, int64_t cap, int32_t *out_indptr,
+                             int32_t *out_indices, int64_t *out_nnz, void *stream);
+/* out[i, c] (n_rows x ld, pad columns zero) = U[0,1) float32 from hash(seed, row0 + i, col0 + c) */
+int srg_synth_hash_features_f32(uint64_t seed, int64_t row0, int64_t n_rows, int32_t col0, int32_t F,
+                                int32_t f_total, float *out, int64_t ld, void *stream);
+
 /*
  * Transpose of a float32 CSR (square, n x n): the matrix the backward pass of the per-epoch sparse
  * product needs (torch.mm(self.adj, x) in Layer2GraphConvolution.forward,

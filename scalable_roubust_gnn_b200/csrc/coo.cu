@@ -12,6 +12,7 @@
 // library calls a CUDA-toolkit primitive (cub::DeviceRadixSort, stable LSD radix sort); everything
 // else (key construction, duplicate segmentation, row pointer search, value arithmetic) is local
 // kernels.  None of this is on the per-hop path.
+#include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
@@ -180,6 +181,86 @@ __global__ void finalize_general_kernel(const uint64_t *__restrict__ keys, const
 
 __global__ void set_int_kernel(int *p, const int *src) { *p = *src; }
 
+// ---- synthetic power-law shards (R-MAT, counter-based RNG keyed by (seed, edge id)) -----
+// splitmix64: the whole generator is integer arithmetic, restated in numpy by synth.rmat_scrambled_host.
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// bijection of [0, 2^scale): hubs of the R-MAT recursion (small ids) are spread over the id range so
+// contiguous row blocks carry comparable numbers of entries (Graph500-style vertex scrambling)
+__host__ __device__ __forceinline__ uint64_t scramble_id(uint64_t x, int scale, uint64_t seed) {
+  const uint64_t mask = (scale >= 64) ? ~0ull : ((1ull << scale) - 1ull);
+  const int h = scale / 2 + 1;
+  x = (x * 0x9E3779B97F4A7C15ull + splitmix64(seed)) & mask;
+  x ^= x >> h;
+  x = (x * 0xD6E8FEB86659FD93ull) & mask;
+  x ^= x >> h;
+  x = (x * 0xCA5A826395121157ull) & mask;
+  x ^= x >> h;
+  return x;
+}
+
+// edge id e -> (u, v): `scale` quadrant draws, 32 random bits each (two per hash)
+__device__ __forceinline__ void rmat_edge(uint64_t seed, uint64_t e, int scale, uint64_t ta, uint64_t tab,
+                                          uint64_t tabc, uint64_t *u_out, uint64_t *v_out) {
+  const uint64_t base = splitmix64(seed ^ (e * 0xA24BAED4963EE407ull));
+  uint64_t u = 0, v = 0, bits = 0;
+  for (int l = 0; l < scale; ++l) {
+    if ((l & 1) == 0) bits = splitmix64(base + (uint64_t)(l >> 1));
+    const uint64_t r = (l & 1) ? (bits >> 32) : (bits & 0xffffffffull);
+    const uint64_t right = (r >= ta && r < tab) || (r >= tabc);   // quadrant b or d: column bit
+    const uint64_t down = (r >= tab);                             // quadrant c or d: row bit
+    u = (u << 1) | down;
+    v = (v << 1) | right;
+  }
+  *u_out = scramble_id(u, scale, seed);
+  *v_out = scramble_id(v, scale, seed);
+}
+
+// every thread walks edge ids e0 + tid, + stride, ...; an accepted pair lands in the shard of each endpoint
+// that falls into [row0, row1) as key ((row - row0) << 32 | col).  Emission order is irrelevant (the keys
+// are sorted and made unique afterwards), so a global cursor is enough.
+__global__ void __launch_bounds__(256)
+rmat_shard_keys_kernel(uint64_t seed, long long m_draw, int scale, uint64_t ta, uint64_t tab, uint64_t tabc,
+                       long long n, long long row0, long long row1, uint64_t *__restrict__ keys, long long cap,
+                       unsigned long long *__restrict__ cursor) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < m_draw; e += stride) {
+    uint64_t u, v;
+    rmat_edge(seed, (uint64_t)e, scale, ta, tab, tabc, &u, &v);
+    if (u >= (uint64_t)n || v >= (uint64_t)n || u == v) continue;
+    const bool mine_u = (long long)u >= row0 && (long long)u < row1;
+    const bool mine_v = (long long)v >= row0 && (long long)v < row1;
+    const int cnt = (mine_u ? 1 : 0) + (mine_v ? 1 : 0);
+    if (!cnt) continue;
+    const unsigned long long at = atomicAdd(cursor, (unsigned long long)cnt);
+    if (at + cnt > (unsigned long long)cap) continue;   // overflow: detected by the host from the cursor
+    unsigned long long w = at;
+    if (mine_u) keys[w++] = ((u - (uint64_t)row0) << 32) | v;
+    if (mine_v) keys[w] = ((v - (uint64_t)row0) << 32) | u;
+  }
+}
+
+// X[i, c] = U[0,1) float32 from hash(seed, global row, global column): shards of any layout agree
+__global__ void __launch_bounds__(256)
+hash_features_kernel(uint64_t seed, long long row0, long long n_rows, int col0, int F, int f_total,
+                     float *__restrict__ out, long long ld) {
+  const long long row = (long long)blockIdx.x * 8 + threadIdx.y;
+  if (row >= n_rows) return;
+  float *o = out + row * ld;
+  for (int c = threadIdx.x; c < ld; c += 32) {
+    float val = 0.f;
+    if (c < F) {
+      const uint64_t h = splitmix64(seed ^ (((uint64_t)(row0 + row) * (uint64_t)f_total + (uint64_t)(col0 + c)) * 0x9E3779B97F4A7C15ull));
+      val = (float)(h >> 40) * (1.0f / 16777216.0f);
+    }
+    o[c] = val;
+  }
+}
+
 // transpose keys of a float32 CSR: entry (a, b) -> key (b << 32 | a), payload = value.  Slots past
 // indptr[n] (the arrays may be longer than the matrix) get a key that sorts behind every entry.
 __global__ void transpose_keys_f32_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
@@ -325,6 +406,71 @@ extern "C" int srg_csr_canonicalize(const int32_t *indptr, const int32_t *indice
   cudaFreeAsync(vals, s);
   cudaFreeAsync(keys, s);
   return rc;
+}
+
+extern "C" int srg_synth_rmat_shard_csr(uint64_t seed, int32_t scale, int64_t m_draw, double a, double b, double c,
+                                        int64_t n, int64_t row0, int64_t row1, int64_t cap, int32_t *out_indptr,
+                                        int32_t *out_indices, int64_t *out_nnz, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(scale >= 1 && scale <= 31, "rmat_shard: scale must be in 1..31");
+  SRG_REQUIRE(n >= 1 && n <= (1LL << scale) && row0 >= 0 && row0 <= row1 && row1 <= n, "rmat_shard: bad row range");
+  SRG_REQUIRE(m_draw >= 0 && cap >= 0 && cap <= 2147483647LL, "rmat_shard: bad sizes");
+  SRG_REQUIRE(a > 0 && b >= 0 && c >= 0 && a + b + c < 1.0, "rmat_shard: bad quadrant probabilities");
+  SRG_REQUIRE(out_indptr && out_nnz && (cap == 0 || out_indices), "rmat_shard: NULL pointer");
+  cudaStream_t s = as_stream(stream);
+  const int64_t n_loc = row1 - row0;
+  const uint64_t ta = (uint64_t)(a * 4294967296.0), tab = (uint64_t)((a + b) * 4294967296.0),
+                 tabc = (uint64_t)((a + b + c) * 4294967296.0);
+  uint64_t *keys = nullptr;
+  unsigned long long *cursor = nullptr;
+  SRG_CUDA(cudaMallocAsync(&keys, (size_t)(cap > 0 ? 2 * cap : 1) * sizeof(uint64_t), s));
+  SRG_CUDA(cudaMallocAsync(&cursor, sizeof(unsigned long long), s));
+  SRG_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s));
+  if (m_draw > 0 && cap > 0) {
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(m_draw, 256), 148 * 16);
+    rmat_shard_keys_kernel<<<blocks, 256, 0, s>>>(seed, m_draw, scale, ta, tab, tabc, n, row0, row1, keys, cap, cursor);
+    SRG_LAUNCHED();
+  }
+  unsigned long long emitted = 0;
+  SRG_CUDA(cudaMemcpyAsync(&emitted, cursor, sizeof(emitted), cudaMemcpyDeviceToHost, s));
+  SRG_CUDA(cudaStreamSynchronize(s));  // set-up path: the key count sizes the sort
+  cudaFreeAsync(cursor, s);
+  if (emitted > (unsigned long long)cap) {
+    cudaFreeAsync(keys, s);
+    set_err("rmat_shard: %llu keys for rows [%lld, %lld) exceed the capacity %lld", emitted, (long long)row0,
+            (long long)row1, (long long)cap);
+    return SRG_ERR_RANGE;
+  }
+  const int64_t m = (int64_t)emitted;
+  if (m > 0) rc = sort_keys(keys, keys + cap, m, 32 + bits_for(n_loc > 1 ? n_loc : 2), s);
+  int32_t *nnz_dev = nullptr;
+  if (!rc) {
+    SRG_CUDA(cudaMallocAsync(&nnz_dev, sizeof(int32_t), s));
+    rc = keys_to_csr(keys + cap, nullptr, m, n_loc, out_indptr, out_indices, nullptr, nnz_dev, s);
+  }
+  if (!rc) {
+    int32_t h = 0;
+    SRG_CUDA(cudaMemcpyAsync(&h, nnz_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    SRG_CUDA(cudaStreamSynchronize(s));
+    *out_nnz = h;
+  }
+  if (nnz_dev) cudaFreeAsync(nnz_dev, s);
+  cudaFreeAsync(keys, s);
+  return rc;
+}
+
+extern "C" int srg_synth_hash_features_f32(uint64_t seed, int64_t row0, int64_t n_rows, int32_t col0, int32_t F,
+                                           int32_t f_total, float *out, int64_t ld, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n_rows >= 0 && F >= 0 && col0 >= 0 && f_total >= col0 + F && ld >= F, "hash_features: bad sizes");
+  if (n_rows == 0 || ld == 0) return SRG_OK;
+  SRG_REQUIRE(out, "hash_features: NULL pointer");
+  hash_features_kernel<<<(unsigned)ceil_div64(n_rows, 8), dim3(32, 8), 0, as_stream(stream)>>>(seed, row0, n_rows, col0, F,
+                                                                                           f_total, out, ld);
+  SRG_LAUNCHED();
+  return SRG_OK;
 }
 
 extern "C" int srg_csr_transpose_f32(const int32_t *indptr, const int32_t *indices, const float *vals, int64_t n,

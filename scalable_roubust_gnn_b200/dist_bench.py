@@ -35,22 +35,41 @@ def run(args, workloads, metric, unit, emit):
     n, nnz = int(n * args.scale), int(nnz * args.scale)
 
     t0 = time.perf_counter()
-    a = synth.uniform_graph(n, nnz)        # every rank regenerates the same graph (fixed seed) ...
     # 8 GPUs are NVLink-ingress bound with a pure row partition (every rank receives 7/8 of X per hop):
     # a 4 x 2 grid (row blocks x feature slices) halves the exchange volume
     pf = int(os.environ.get("SRG_FEAT_GROUPS", "2" if (world >= 8 and mode == "push") else "1"))
     st = sdist.DistState(n, f, world, rank, mode=mode, feat_groups=pf)
     s, e = st.row0, st.row0 + st.n_local
-    a_loc_host = sdist.shard_rows(a, s, e)  # ... and keeps its row slice
-    x_loc_host = np.ascontiguousarray(synth.features(n, f)[s:e, st.f0:st.f1])
     f_loc = st.f_loc
-    nnz_hat = a.nnz + n
-    del a
+    gen = os.environ.get("SRG_GEN", "device" if args.workload.startswith("papers100M") else "host")
+    a_loc_host = x_loc_host = None
+    if gen == "device":
+        # config 5: every rank builds ITS rows of the scrambled R-MAT graph on its GPU (counter-based
+        # generator, csrc/coo.cu) and its slice of the procedural features; nothing of this size ever
+        # exists on the host
+        m_draw = synth.rmat_draws(n, nnz)
+        a_loc = synth.rmat_shard_device(n, m_draw, s, e)
+        x_loc = synth.hash_features_device(st.n_local, f_loc, row0=s, col0=st.f0, f_total=f)
+        cnt = torch.tensor([a_loc.nnz if st.ci == 0 else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cnt)
+        nnz_hat = int(cnt.item()) + n
+        if st.ci == 0:
+            # column 0 := sqrt(degree): an eigenvector of D^-1/2 (A+I) D^-1/2 with eigenvalue 1, so every
+            # hop must hand it back unchanged (size-independent check of the hops and of the exchange)
+            deg = (a_loc.indptr[1:] - a_loc.indptr[:-1] + 1).to(torch.float32)
+            x_loc[:, 0] = torch.sqrt(deg)
+    else:
+        a = synth.uniform_graph(n, nnz)        # every rank regenerates the same graph (fixed seed) ...
+        a_loc_host = sdist.shard_rows(a, s, e)  # ... and keeps its row slice
+        x_loc_host = np.ascontiguousarray(synth.features(n, f)[s:e, st.f0:st.f1])
+        nnz_hat = a.nnz + n
+        del a
+        a_loc = dev.upload_csr(a_loc_host)
+        x_loc = dev.pack_features(torch.from_numpy(np.ascontiguousarray(x_loc_host)).cuda())
+    torch.cuda.synchronize()
     if rank == 0:
         print(f"[bench] world={world} mode={mode} grid={st.n_row_blocks}x{pf} N={n} nnz_hat={nnz_hat} F={f} K={k} rows/rank={st.rows_per} "
-              f"setup {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
-    a_loc = dev.upload_csr(a_loc_host)
-    x_loc = dev.pack_features(torch.from_numpy(np.ascontiguousarray(x_loc_host)).cuda())
+              f"gen={gen} setup {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
 
     def step():
         sdist.start_input_exchange(st, x_loc)          # overlaps the normalisation
@@ -84,6 +103,56 @@ def run(args, workloads, metric, unit, emit):
     t_step = float(ms.item()) * 1e-3 / args.steps
     launches = _lib.launch_count() - launches0
 
+    verify = None
+    if gen == "device":
+        verify = _verify_device_generated(st, a_loc, x_loc, k, f, sdist, synth, torch, dist)
+        e2e_line = None
+    else:
+        e2e_line = _e2e(args, st, a_loc_host, x_loc_host, k, f_loc, lib, dev, sdist, torch, dist)
+    clocks = sampler.stop() if rank == 0 else None
+    _emit_line(args, st, metric, unit, emit, mode, pf, world, rank, n, nnz_hat, f, f_loc, k, t_step, launches, e2e_line,
+               clocks, verify, gen)
+    st.close()
+    dist.destroy_process_group()
+
+
+def _verify_device_generated(st, a_loc, x_loc, k, f, sdist, synth, torch, dist):
+    """Checks for the device-generated workload (no host copy of the graph exists):
+      (1) 8 sampled local rows of hop 1 recomputed on the host from the procedural features of their
+          neighbour rows (rows owned by every rank: exercises the exchange) and the normalised weights;
+      (2) column 0 = sqrt(degree) must survive all K hops (eigenvalue 1).
+    Returns a dict (max errors) on rank 0."""
+    sdist.start_input_exchange(st, x_loc)
+    norm, _ = sdist.dist_sym_norm(st, a_loc, 0.5)
+    hops = sdist.propagate_device(st, norm, x_loc, k, keep_hops=True)
+    torch.cuda.synchronize()
+    errs = torch.zeros(2, dtype=torch.float64, device="cuda")
+    rows = np.linspace(0, st.n_local - 1, 8).astype(np.int64) if st.n_local > 0 else np.zeros(0, np.int64)
+    ip = norm.indptr.cpu().numpy()
+    for rl in rows:
+        lo, hi = int(ip[rl]), int(ip[rl + 1])
+        cols = norm.indices[lo:hi].cpu().numpy().astype(np.int64)
+        vals = norm.data[lo:hi].cpu().numpy().astype(np.float64)
+        if hi - lo > 200000:
+            continue                                   # a hub row: (2) covers it
+        xin = synth.hash_features_host(1, 0, 0, st.f0, st.f_loc, f, rows=cols).astype(np.float64)
+        if st.ci == 0:      # column 0 carries sqrt(degree) of the NEIGHBOUR: val = 1/sqrt(d_i d_j) gives it back
+            d_i = float(hi - lo)                       # row length of A+I = degree incl. the loop
+            xin[:, 0] = 1.0 / (vals * np.sqrt(d_i))    # sqrt(d_j) from the weight itself
+        want = (vals[:, None] * xin).sum(0)
+        got = hops[1][rl, :st.f_loc].double().cpu().numpy()
+        c0 = 1 if st.ci == 0 else 0                    # column 0 is checked by (2)
+        err = np.max(np.abs(got[c0:] - want[c0:]) / (np.abs(want[c0:]) + 1e-6))
+        errs[0] = max(float(errs[0]), float(err))
+    if st.ci == 0 and st.n_local > 0:
+        rel = ((hops[k][:, 0] - x_loc[:, 0]).abs() / x_loc[:, 0]).max()
+        errs[1] = rel.double()
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    del hops
+    return {"hop1_sampled_rows_max_rel_err": float(errs[0]), "sqrt_degree_eigenvector_max_rel_err_after_K_hops": float(errs[1])}
+
+
+def _e2e(args, st, a_loc_host, x_loc_host, k, f_loc, lib, dev, sdist, torch, dist):
     # end to end: host slices in (pinned), host slices of every hop out, per rank
     x_pin = torch.from_numpy(np.ascontiguousarray(x_loc_host)).pin_memory()
     ip = torch.from_numpy(a_loc_host.indptr).pin_memory()
@@ -125,8 +194,12 @@ def run(args, workloads, metric, unit, emit):
     t_e2e = torch.tensor([(time.perf_counter() - t0) / reps], device="cuda", dtype=torch.float64)
     dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     t_e2e = float(t_e2e.item())
-    clocks = sampler.stop() if rank == 0 else None
+    return {"t": t_e2e, "h2d": int(ip.numel() * 4 + ii.numel() * 4 + dd.numel() * 8 + x_pin.numel() * 4),
+            "d2h": int(k * st.n_local * f_loc * 4)}
 
+
+def _emit_line(args, st, metric, unit, emit, mode, pf, world, rank, n, nnz_hat, f, f_loc, k, t_step, launches, e2e_line,
+               clocks, verify, gen):
     if rank == 0:
         from bench import comp_bytes, gather_bytes, measured_peak, workload_config
         peak, peak_src = measured_peak()
@@ -147,10 +220,12 @@ def run(args, workloads, metric, unit, emit):
                              "nvlink_GBps_in_per_gpu": nvlink_bytes / hop_s / 1e9,
                              "compulsory_bytes_per_launch": comp_bytes(n, nnz_hat, f) / world},
                 "cpu_baseline": None,
-                "e2e": {"value": k * nnz_hat * f / t_e2e, "unit": unit, "ms_per_step": t_e2e * 1e3,
-                        "h2d_bytes_per_step": int(ip.numel() * 4 + ii.numel() * 4 + dd.numel() * 8 + x_pin.numel() * 4),
-                        "d2h_bytes_per_step": int(k * st.n_local * f_loc * 4), "note": "per-rank bytes; max over ranks time"},
+                "e2e": None if e2e_line is None else
+                {"value": k * nnz_hat * f / e2e_line["t"], "unit": unit, "ms_per_step": e2e_line["t"] * 1e3,
+                 "h2d_bytes_per_step": e2e_line["h2d"], "d2h_bytes_per_step": e2e_line["d2h"],
+                 "note": "per-rank bytes; max over ranks time"},
                 "gpu_launches": int(launches), "clocks": clocks}
+        if verify is not None:
+            line["verify"] = verify
+            line["data"] = "synthetic (device-generated shards; no host copy exists, so no host end-to-end leg)"
         emit(line)
-    st.close()
-    dist.destroy_process_group()

@@ -157,6 +157,22 @@ int srg_sym_norm_csr_general(const int32_t *indptr, const int32_t *indices, cons
                              double *out_degree, double *out_val_f64, float *out_val_f32,
                              int32_t *out_flags, void *stream);
 
+/* ---- 8f-2: magnetic-Laplacian normalisation of a directed graph ----------------------------------------
+ * adj_to_directed_symmetric_mag_norm (SSRG/operators/utils.py:95-138), the normaliser of
+ * SymDirMagLaplacianGraphOp / SymDirMagComPprGraphOp: symmetrised weights (A + A^T) / 2 with self loops,
+ * degrees, D^(r-1) A_s D^(-r), Hadamard exp(i * q_angle * (A - A^T)); q_angle = 2 pi q as the host
+ * evaluates it.  Outputs one CSR pattern (sorted, union of A, A^T and the diagonal; capacity 2 nnz + n)
+ * with the real and the imaginary values in fp64 (what the reference's scipy matrices hold) and/or
+ * rounded to fp32 (what the hops read, utils.py:39); any value output may be NULL.
+ * ppr_alpha >= 0 applies real = (1 - alpha) real + alpha I, imag = (1 - alpha) imag
+ * (symmetrical_directed_magnetic_comppr_operator.py:33-38); pass a negative value for none.
+ * nnz must equal indptr[n].  out_flags: SRG_FLAG_BAD_INDEX, SRG_FLAG_ZERO_PRODUCT (a blended real entry
+ * became exactly 0, which scipy would drop). */
+int srg_mag_norm_csr(const int32_t *indptr, const int32_t *indices, const void *data, int val_dtype,
+                     int64_t n, int64_t nnz, double r, double q_angle, double ppr_alpha, int32_t *out_indptr,
+                     int32_t *out_indices, double *out_degree, double *out_real_f64, double *out_imag_f64,
+                     float *out_real_f32, float *out_imag_f32, int32_t *out_flags, void *stream);
+
 /* ---- synthetic inputs of the named shapes, generated on the device --------------------
  * Not a reference interface: BASELINE.json's configs 4 (power-law variant) and 5 are synthetic R-MAT
  * graphs too large to build on the host per rank.  Rows [row0, row1) of the symmetrised, duplicate-free,

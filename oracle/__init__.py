@@ -15,6 +15,7 @@ What it restates (file:line in /root/reference, SSRG = "Scalable Spectral Robust
   cheby_*           pygsp 0.5.1 (PyPI "PyGSP", un-pinned and absent from /root/reference):
                     call sites wavelet/src/utils.py:83,95,131-133 and
                     SSRG/models/base_scalable/base_model.py:184-189,243  -- PARITY UNPINNED
+  mag_norm / com_propagate  SSRG/operators/utils.py:95-138, SSRG/operators/base_operator.py:152-208, :316-345
   spectral_preprocess  SSRG/models/base_scalable/base_model.py:180-221 (on top of cheby_*: PARITY UNPINNED)
   nafs_combine      SSRG/operators/message_operator/over_smooth_distance_op.py:11-33
   row_partition     new functionality (no reference code): the bit-exact partition map
@@ -165,6 +166,87 @@ def propagate(adj, feature, prop_steps, r=0.5, ppr_alpha=None, lib="oracle"):
     for _ in range(prop_steps):
         out.append(spmm_hop(adj_norm, out[-1], lib=lib))
     return out, adj_norm
+
+
+# ------------------------------------------------------------------------------------------------
+# magnetic-Laplacian operators of directed graphs
+# ------------------------------------------------------------------------------------------------
+def mag_norm(adj, r, q, ppr_alpha=None):
+    """adj_to_directed_symmetric_mag_norm (SSRG/operators/utils.py:95-138) in fp64 numpy, and the PPR blend
+    of SymDirMagComPprGraphOp.construct_adj (symmetrical_directed_magnetic_comppr_operator.py:33-38).
+    torch_sparse.coalesce(.., "add") = sum of equal (row, col) keys in stored order, output sorted by key;
+    torch_scatter.scatter_add = sequential sum in stored order (both packages absent from /root/reference:
+    their documented behaviour is restated).  Returns (real_csr, imag_csr) with float64 data."""
+    coo = sp.coo_matrix(adj)
+    n = coo.shape[0]
+    w = coo.data.astype(np.float64)
+    row = np.concatenate([coo.row, coo.col]).astype(np.int64)          # :100
+    col = np.concatenate([coo.col, coo.row]).astype(np.int64)
+    sym = np.concatenate([w, w])                                       # :102
+    theta = np.concatenate([w, -w])                                    # :103
+    uniq, inv = np.unique(row * n + col, return_inverse=True)          # coalesce :105
+    sym_c = np.zeros(len(uniq))
+    th_c = np.zeros(len(uniq))
+    np.add.at(sym_c, inv, sym)
+    np.add.at(th_c, inv, theta)
+    sym_c = sym_c / 2                                                  # :108
+    rows = np.concatenate([uniq // n, np.arange(n)])                   # loops appended :109-115
+    cols = np.concatenate([uniq % n, np.arange(n)])
+    sym_all = np.concatenate([sym_c, np.ones(n)])
+    th_all = np.concatenate([th_c, np.zeros(n)])                       # :117-119
+    deg = np.zeros(n)
+    np.add.at(deg, rows, sym_all)                                      # :122
+    with np.errstate(divide="ignore"):
+        dl = np.power(deg, r - 1)
+        dr = np.power(deg, -r)
+    dl[np.isinf(dl)] = 0
+    dr[np.isinf(dr)] = 0
+    angle = (1j * 2 * np.pi * q).imag * th_all                         # :124
+    x = dl[rows] * sym_all * dr[cols]                                  # :130
+    real = sp.csr_matrix((x * np.cos(angle), (rows, cols)), shape=(n, n))   # :133-136
+    imag = sp.csr_matrix((x * np.sin(angle), (rows, cols)), shape=(n, n))
+    if ppr_alpha is not None:
+        real = ((1 - ppr_alpha) * real + ppr_alpha * sp.eye(n)).tocsr()
+        imag = ((1 - ppr_alpha) * imag).tocsr()
+    for m in (real, imag):
+        m.sort_indices()
+    return real, imag
+
+
+def com_propagate(real_adj, imag_adj, feature, prop_steps, lib="oracle"):
+    """ComGraphOp.propagate (SSRG/operators/base_operator.py:152-208) including its aliasing: the
+    in-place `+=` of calculate_real_imag_feat (:316-345) turns the first real and the first imaginary
+    term of every step into the running totals, and those arrays are the inputs of the next step.
+    Returns (real_list, imag_list) of float32 arrays, prop_steps + 1 entries each."""
+    x = np.ascontiguousarray(feature, dtype=np.float32)
+    real_list, imag_list = [x], [x]
+    terms = []                                   # (value, r_step, i_step)
+    for step in range(prop_steps):
+        if step == 0:
+            tr = spmm_hop(real_adj, x, lib=lib)
+            ti = spmm_hop(imag_adj, x, lib=lib)
+            terms = [[tr, 1, 0], [ti, 0, 1]]
+            real_list.append(tr)
+            imag_list.append(ti)
+            continue
+        out = []
+        for val, rs, is_ in terms:
+            out.append([spmm_hop(real_adj, val, lib=lib), rs + 1, is_])
+        for val, rs, is_ in terms:
+            v = spmm_hop(imag_adj, val, lib=lib)
+            if (is_ + 1) & 1 == 0:               # reversal(): i_step even and non-zero
+                v = -v
+            out.append([v, rs, is_ + 1])
+        reals = [t for t in out if t[2] & 1 == 0]
+        imags = [t for t in out if t[2] & 1 == 1]
+        assert len(reals) == len(imags)
+        for k in range(1, len(reals)):
+            reals[0][0] += reals[k][0]           # in place: out[...] now holds the running total
+            imags[0][0] += imags[k][0]
+        real_list.append(reals[0][0])
+        imag_list.append(imags[0][0])
+        terms = out
+    return real_list, imag_list
 
 
 # ------------------------------------------------------------------------------------------------

@@ -109,6 +109,187 @@ class GraphOp:
         return out
 
 
+def _check_inputs(adj, feature):
+    """The reference's three checks (base_operator.py:22-30 and twins), run before any work."""
+    if not isinstance(adj, sp.csr_matrix):
+        raise TypeError("The adjacency matrix must be a scipy csr sparse matrix!")
+    if not isinstance(feature, np.ndarray):
+        if isinstance(feature, Tensor):
+            feature = feature.numpy()
+        else:
+            raise TypeError("The feature matrix must be a numpy.ndarray!")
+    if feature.ndim != 2 or adj.shape[1] != feature.shape[0]:
+        raise ValueError("Dimension mismatch detected for the adjacency and the feature matrix!")
+    if feature.dtype != np.float32:
+        raise ctypes.ArgumentError("The feature matrix must be float32!")
+    return feature
+
+
+class _MultiAdjGraphOp:
+    """Shared body of TwoOrderPprApproxGraphOp / TwoDirGraphOp: K independent hop chains, one per
+    normalised adjacency, features resident on the device."""
+
+    _adj_attrs = ()
+
+    def __init__(self, prop_steps):
+        self.prop_steps = prop_steps
+        for name in self._adj_attrs:
+            setattr(self, name, None)
+        self.device = 0
+
+    def construct_adj(self, adj):
+        raise NotImplementedError
+
+    def propagate(self, adj, feature):
+        feature = _check_inputs(adj, feature)
+        adjs = self.construct_adj(adj)
+        for name, a in zip(self._adj_attrs, adjs):
+            setattr(self, name, a)
+        run = _u.DeviceHopRunner(adjs, feature, device=self.device)
+        lists = []
+        for which in range(len(adjs)):
+            cur, hops = run.x0, [torch.FloatTensor(feature)]
+            for _ in range(self.prop_steps):
+                cur = run.hop(which, cur)
+                hops.append(run.to_host(cur))
+            lists.append(hops)
+        return tuple(lists)
+
+
+class TwoOrderPprApproxGraphOp(_MultiAdjGraphOp):
+    """SSRG/operators/base_operator.py:62-96: returns (one_prop_feat_list, two_prop_feat_list)."""
+    _adj_attrs = ("one_adj", "two_adj")
+
+
+class TwoDirGraphOp(_MultiAdjGraphOp):
+    """SSRG/operators/base_operator.py:244-284: returns (un_list, in_list, out_list)."""
+    _adj_attrs = ("un_adj", "in_adj", "out_adj")
+
+
+class ComGraphOp:
+    """Complex (magnetic) propagation, SSRG/operators/base_operator.py:145-208.
+
+    ``construct_adj`` yields the real and the imaginary part of the normalised operator; step k expands
+    ``(R + iI)`` applied to every term of step k-1 (2^k sparse products), negates a term whenever its
+    count of imaginary factors becomes even (``calculator.reversal``, :136-138) and sums the real /
+    imaginary terms (``calculate_real_imag_feat``, :316-345).  ``faithful=True`` (default) reproduces the
+    reference bit for bit, including the aliasing of its in-place ``+=``: the first real and the first
+    imaginary term of a step become the running totals and feed the next step.  ``faithful=False``
+    evaluates the recurrence the expansion stands for, ``Z_k = (R + iI) Z_{k-1}``, with 4 products per step.
+    """
+
+    def __init__(self, prop_steps, faithful=True):
+        self.prop_steps = prop_steps
+        self.real_adj = None
+        self.imag_adj = None
+        self.faithful = faithful
+        self.device = 0
+
+    def construct_adj(self, adj):
+        raise NotImplementedError
+
+    def propagate(self, adj, feature):
+        feature = _check_inputs(adj, feature)
+        self.real_adj, self.imag_adj = self.construct_adj(adj)
+        run = _u.DeviceHopRunner([self.real_adj, self.imag_adj], feature, device=self.device)
+        x0 = torch.FloatTensor(feature)
+        real_list, imag_list = [x0], [x0]
+        if not self.faithful:
+            re, im = run.x0, None
+            for step in range(self.prop_steps):
+                if im is None:                                   # Z_0 = x is real
+                    re, im = run.hop(0, re), run.hop(1, re)
+                else:
+                    re, im = run.add_(run.hop(0, re), run.neg(run.hop(1, im))), run.add_(run.hop(0, im), run.hop(1, re))
+                real_list.append(run.to_host(re))
+                imag_list.append(run.to_host(im))
+            return real_list, imag_list
+        terms = []                                               # [value, r_step, i_step]
+        for step in range(self.prop_steps):
+            if step == 0:
+                terms = [[run.hop(0, run.x0), 1, 0], [run.hop(1, run.x0), 0, 1]]
+                real_list.append(run.to_host(terms[0][0]))
+                imag_list.append(run.to_host(terms[1][0]))
+                continue
+            out = [[run.hop(0, v), rs + 1, is_] for v, rs, is_ in terms]
+            for v, rs, is_ in terms:
+                t = run.hop(1, v)
+                if (is_ + 1) & 1 == 0:
+                    t = run.neg(t)
+                out.append([t, rs, is_ + 1])
+            reals = [t for t in out if t[2] & 1 == 0]
+            imags = [t for t in out if t[2] & 1 == 1]
+            if len(reals) != len(imags):
+                raise RuntimeError("Something wrong!")
+            for k in range(1, len(reals)):
+                run.add_(reals[0][0], reals[k][0])
+                run.add_(imags[0][0], imags[k][0])
+            real_list.append(run.to_host(reals[0][0]))
+            imag_list.append(run.to_host(imags[0][0]))
+            terms = out
+        return real_list, imag_list
+
+
+def _typed_lists(names, lists):
+    for name, feats in zip(names, lists):
+        if any(not isinstance(feat, Tensor) for feat in feats):
+            raise TypeError(f"The {name} feature matrices must be tensors!")
+
+
+class ComMessageOp(torch.nn.Module):
+    """SSRG/operators/base_operator.py:212-241."""
+
+    def __init__(self, start=None, end=None):
+        super().__init__()
+        self.aggr_type = None
+        self.start, self.end = start, end
+
+    def combine(self, real_feat_list, imag_feat_list):
+        return NotImplementedError
+
+    def aggregate(self, real_feat_list, imag_feat_list):
+        if not isinstance(real_feat_list, list) or not isinstance(imag_feat_list, list):
+            return TypeError("The input must be a list consists of feature matrices!")
+        _typed_lists(("real", "imag"), (real_feat_list, imag_feat_list))
+        return self.combine(real_feat_list, imag_feat_list)
+
+
+class TwoOrderPprApproxMessageOp(torch.nn.Module):
+    """SSRG/operators/base_operator.py:99-124."""
+
+    def __init__(self, start=None, end=None):
+        super().__init__()
+        self.aggr_type = None
+        self.start, self.end = start, end
+
+    def combine(self, one_feat_list, two_feat_list):
+        return NotImplementedError
+
+    def aggregate(self, one_feat_list, two_feat_list):
+        if not isinstance(one_feat_list, list) or not isinstance(two_feat_list, list):
+            return TypeError("The input must be a list consists of feature matrices!")
+        _typed_lists(("one order", "two order"), (one_feat_list, two_feat_list))
+        return self.combine(one_feat_list, two_feat_list)
+
+
+class TwoDirMessageOp(torch.nn.Module):
+    """SSRG/operators/base_operator.py:288-306."""
+
+    def __init__(self, start=None, end=None):
+        super().__init__()
+        self.aggr_type = None
+        self.start, self.end = start, end
+
+    def combine(self, un_feat_list, in_feat_list, out_feat_list):
+        return NotImplementedError
+
+    def aggregate(self, un_feat_list, in_feat_list, out_feat_list):
+        if not all(isinstance(x, list) for x in (un_feat_list, in_feat_list, out_feat_list)):
+            return TypeError("The input must be a list consists of feature matrices!")
+        _typed_lists(("un direction", "in direction", "out direction"), (un_feat_list, in_feat_list, out_feat_list))
+        return self.combine(un_feat_list, in_feat_list, out_feat_list)
+
+
 def ada_platform_one_step_propagation(adj, x):
     """One hop ``adj @ x`` (SSRG/operators/base_operator.py:309-314).  The reference switches on
     the platform between its OpenMP library and scipy; here there is one path: the GPU."""

@@ -1,2 +1,4 @@
 from .symmetrical_simgraph_laplacian_operator import SymLaplacianGraphOp  # noqa: F401
 from .symmetrical_simgraph_ppr_operator import PprGraphOp  # noqa: F401
+from .symmetrical_directed_magnetic_laplacian_operator import SymDirMagLaplacianGraphOp  # noqa: F401
+from .symmetrical_directed_magnetic_comppr_operator import SymDirMagComPprGraphOp  # noqa: F401

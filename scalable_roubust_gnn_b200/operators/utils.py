@@ -6,6 +6,8 @@ Reference functions mirrored (same names, argument meaning and return layout):
     the GPU.
   * ``adj_to_symmetric_norm(adj, r)``          — SSRG/operators/utils.py:81-93 (scipy fp64).
     Here: CSR kernels on the GPU; the result comes back as a scipy matrix.
+  * ``adj_to_directed_symmetric_mag_norm(adj, r, q)`` — SSRG/operators/utils.py:95-138 (torch +
+    torch_sparse + torch_scatter on the CPU).  Here: one key sort + segment kernels (csrc/magnetic.cu).
   * ``propagate_host``                         — the body of GraphOp.propagate
     (SSRG/operators/base_operator.py:31-36) as ONE library call.
 
@@ -22,7 +24,7 @@ import torch
 from .. import _lib
 
 __all__ = ["csr_sparse_dense_matmul", "adj_to_symmetric_norm", "propagate_host", "propagate_aggregate_host",
-           "csr_host_parts"]
+           "csr_host_parts", "adj_to_directed_symmetric_mag_norm", "DeviceHopRunner"]
 
 
 def _ptr(a):
@@ -189,3 +191,117 @@ def propagate_aggregate_host(adj, feature, prop_steps, r, ppr_alpha, spec, featu
                                           _ptr(w), _ptr(out), int(device))
     _lib.check(rc)
     return out
+
+
+def adj_to_directed_symmetric_mag_norm(adj, r, q, ppr_alpha=None, device=0):
+    """Magnetic-Laplacian normalisation of a directed adjacency on the GPU (SSRG/operators/utils.py:95-138).
+
+    ``adj``: scipy sparse (the reference passes ``adj.tocoo()``).  Returns ``(real, imag)``: two
+    ``scipy.sparse.csr_matrix`` with float64 data sharing one sorted pattern (A, A^T and the diagonal).
+    ``ppr_alpha`` additionally applies the blend of SymDirMagComPprGraphOp.construct_adj."""
+    lib = _lib.load()
+    if lib.srg_device_count() <= 0:
+        raise _lib.SrgError(_lib.SRG_ERR_NODEV, "no CUDA device visible: libsrgnn_b200 has no CPU fallback")
+    if not sp.issparse(adj):
+        raise TypeError("The adjacency matrix must be a scipy sparse matrix!")
+    csr = adj.tocsr() if not isinstance(adj, sp.csr_matrix) else adj
+    indptr, indices, data, vt, n, nnz = csr_host_parts(csr)
+    if 2 * nnz + n > np.iinfo(np.int32).max:
+        raise _lib.SrgError(_lib.SRG_ERR_RANGE, "2 nnz + n exceeds the int32 CSR range")
+    dev = torch.device("cuda", int(device))
+    cap = max(2 * nnz + n, 1)
+    with torch.cuda.device(dev):
+        d_indptr = torch.from_numpy(indptr).to(dev)
+        d_indices = torch.from_numpy(indices).to(dev) if nnz else torch.zeros(1, dtype=torch.int32, device=dev)
+        d_data = torch.from_numpy(data).to(dev) if nnz else torch.zeros(1, dtype=torch.float64, device=dev)
+        o_indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        o_indices = torch.empty(cap, dtype=torch.int32, device=dev)
+        o_re = torch.empty(cap, dtype=torch.float64, device=dev)
+        o_im = torch.empty(cap, dtype=torch.float64, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        q_angle = (1j * 2 * np.pi * q).imag                 # the reference's own expression (utils.py:124)
+        alpha = -1.0 if ppr_alpha is None else float(ppr_alpha)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        rc = lib.srg_mag_norm_csr(_ptr(d_indptr), _ptr(d_indices), _ptr(d_data), vt, n, nnz, float(r), float(q_angle),
+                                  alpha, _ptr(o_indptr), _ptr(o_indices), None, _ptr(o_re), _ptr(o_im), None, None,
+                                  _ptr(flags), stream)
+        _lib.check(rc)
+        fl = int(flags.item())
+        if fl & _lib.SRG_FLAG_BAD_INDEX:
+            raise _lib.SrgError(_lib.SRG_ERR_INVALID, "column index out of range")
+        if fl & _lib.SRG_FLAG_ZERO_PRODUCT:
+            raise _lib.SrgUnsupported(_lib.SRG_ERR_UNSUPPORTED,
+                                      "a blended real entry is exactly zero (scipy would drop it from the pattern)")
+        h_indptr = o_indptr.cpu().numpy()
+        m = int(h_indptr[-1]) if n else 0
+        h_indices = o_indices[:m].cpu().numpy()
+        real = sp.csr_matrix((o_re[:m].cpu().numpy(), h_indices, h_indptr), shape=(n, n), copy=False)
+        imag = sp.csr_matrix((o_im[:m].cpu().numpy(), h_indices.copy(), h_indptr.copy()), shape=(n, n), copy=False)
+    real.has_sorted_indices = imag.has_sorted_indices = True
+    return real, imag
+
+
+class DeviceHopRunner:
+    """Hops with several (already normalised) adjacency matrices over device-resident features: the
+    per-hop body of ComGraphOp / TwoDirGraphOp / TwoOrderPprApproxGraphOp.propagate
+    (SSRG/operators/base_operator.py:62-306), each hop being ``csr_sparse_dense_matmul`` (utils.py:17-47:
+    weights rounded to float32, fp32 FMA chain in stored order) without the host round trip."""
+
+    def __init__(self, adjs, feature, device=0):
+        from .. import device as sdev
+        self.lib = _lib.load()
+        if self.lib.srg_device_count() <= 0:
+            raise _lib.SrgError(_lib.SRG_ERR_NODEV, "no CUDA device visible: libsrgnn_b200 has no CPU fallback")
+        self.dev = torch.device("cuda", int(device))
+        self.sdev = sdev
+        self.n, self.f = feature.shape
+        self.adjs = []
+        with torch.cuda.device(self.dev):
+            for a in adjs:
+                if not isinstance(a, sp.csr_matrix):
+                    a = sp.csr_matrix(a)
+                nnz = int(a.indptr[-1])
+                self.adjs.append(sdev.DeviceCSR(
+                    torch.from_numpy(np.ascontiguousarray(a.indptr, dtype=np.int32)).to(self.dev),
+                    torch.from_numpy(np.ascontiguousarray(a.indices[:nnz], dtype=np.int32)).to(self.dev)
+                    if nnz else torch.zeros(1, dtype=torch.int32, device=self.dev),
+                    torch.from_numpy(np.ascontiguousarray(a.data[:nnz]).astype(np.float32)).to(self.dev)
+                    if nnz else torch.zeros(1, dtype=torch.float32, device=self.dev),
+                    a.shape[0], nnz))
+            x = torch.from_numpy(np.ascontiguousarray(feature, dtype=np.float32)).to(self.dev)
+            self.x0 = sdev.pack_features(x) if self.n * self.f else x
+        self.ld = self.x0.shape[1] if self.n * self.f else self.f
+
+    def hop(self, which, x):
+        """A[which] @ x on the device (x and the result in the padded layout)."""
+        if self.n * self.f == 0:
+            return x.clone()
+        with torch.cuda.device(self.dev):
+            return self.sdev.spmm(self.adjs[which], x, self.f)
+
+    def _update(self, acc, x, mode, w, first):
+        stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        _lib.check(self.lib.srg_aggregate_update_f32(_ptr(acc), self.ld, 0, _ptr(x), self.ld, self.n, self.f, mode,
+                                                     C.c_float(w), first, stream))
+
+    def add_(self, acc, x):
+        """acc += x (elementwise fp32 add, numpy's in-place add)."""
+        if self.n * self.f:
+            with torch.cuda.device(self.dev):
+                self._update(acc, x, _lib.SRG_AGG_SUM, 1.0, 0)
+        return acc
+
+    def neg(self, x):
+        """-x as a fresh matrix."""
+        out = torch.empty_like(x)
+        if self.n * self.f:
+            with torch.cuda.device(self.dev):
+                self._update(out, x, _lib.SRG_AGG_WEIGHTED, -1.0, 1)
+        return out
+
+    def to_host(self, x):
+        """padded device matrix -> torch.FloatTensor n x F on the CPU."""
+        if self.n * self.f == 0:
+            return torch.zeros((self.n, self.f), dtype=torch.float32)
+        with torch.cuda.device(self.dev):
+            return self.sdev.unpack_features(x, self.f).cpu()

@@ -10,6 +10,11 @@ reference's own classes imported from /root/reference, run on small inputs, outp
              (SSRG/models/base_scalable/simple_models.py:214-240) on the adjacency produced by
              SymLaplacianGraphOp.construct_adj + scipy_sparse_mat_to_torch_sparse_tensor
              (SSRG/models/utils.py:5-15), dropout off: outputs, loss, parameter and input gradients
+  * mag_*    SymDirMagLaplacianGraphOp / SymDirMagComPprGraphOp (SSRG/operators/graph_operator/
+             symmetrical_directed_magnetic_*.py, ComGraphOp.propagate in base_operator.py:145-208) on small
+             directed graphs.  torch_sparse.coalesce / torch_scatter.scatter_add are absent from this image:
+             the script supplies pure-torch stand-ins with their documented semantics (sum of equal keys in
+             stored order, output sorted by key / sequential scatter sum) — everything else is reference code.
 """
 import os
 import sys
@@ -18,7 +23,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-from make_golden import import_reference, sym_graph  # noqa: E402
+from make_golden import csr_pack, import_reference, sym_graph  # noqa: E402
 
 
 def main():
@@ -69,6 +74,57 @@ def main():
         for k, v in layer.named_parameters():
             if v.grad is not None:
                 out[f"{tag}_g_{k}"] = v.grad.numpy()
+
+    # ---- magnetic operators of directed graphs ------------------------------------------------------
+    import scipy.sparse as sp
+    import operators.utils as U
+
+    def coalesce(index, value, m, n, op="add"):
+        key = index[0] * n + index[1]
+        uniq, inv = torch.unique(key, sorted=True, return_inverse=True)
+        acc = torch.zeros((uniq.numel(),) + tuple(value.shape[1:]), dtype=value.dtype)
+        acc.index_add_(0, inv, value)
+        return torch.stack([uniq // n, uniq % n]), acc
+
+    def scatter_add(src, index, dim=0, dim_size=None):
+        return torch.zeros(dim_size, dtype=src.dtype).index_add_(0, index, src)
+
+    U.coalesce, U.scatter_add = coalesce, scatter_add
+    from operators.graph_operator.symmetrical_directed_magnetic_comppr_operator import SymDirMagComPprGraphOp
+    from operators.graph_operator.symmetrical_directed_magnetic_laplacian_operator import SymDirMagLaplacianGraphOp
+    rg = np.random.default_rng(21)
+
+    def digraph(n, m, weighted=False, loops=False):
+        rows, cols = rg.integers(0, n, m), rg.integers(0, n, m)
+        if not loops:
+            keep = rows != cols
+            rows, cols = rows[keep], cols[keep]
+        a = sp.csr_matrix((np.ones(len(rows)), (rows, cols)), shape=(n, n))
+        a.data[:] = 1.0
+        if weighted:
+            a.data[:] = np.round(rg.random(a.nnz) + 0.25, 3)
+        a.sort_indices()
+        return a
+
+    mag_cases = {"mag_unw": (digraph(120, 700), 0.5, 0.25, 3), "mag_w": (digraph(90, 500, weighted=True, loops=True), 0.3, 0.1, 2),
+                 "mag_tiny": (digraph(7, 12, loops=True), 0.5, 0.25, 4)}
+    for tag, (a, r, q, k) in mag_cases.items():
+        xm = rg.random((a.shape[0], 6), dtype=np.float32) - 0.5
+        csr_pack(f"{tag}_adj", a, out)
+        out[f"{tag}_x"] = xm
+        out[f"{tag}_params"] = np.array([r, q, k])
+        op = SymDirMagLaplacianGraphOp(k, r=r, q=q)
+        re, im = op.propagate(a, xm)
+        csr_pack(f"{tag}_real", op.real_adj, out)
+        csr_pack(f"{tag}_imag", op.imag_adj, out)
+        out[f"{tag}_re_hops"] = np.stack([t.numpy() for t in re])
+        out[f"{tag}_im_hops"] = np.stack([t.numpy() for t in im])
+        op = SymDirMagComPprGraphOp(k, r=r, q=q, ppr_alpha=0.15)
+        re, im = op.propagate(a, xm)
+        csr_pack(f"{tag}_ppr_real", op.real_adj, out)
+        csr_pack(f"{tag}_ppr_imag", op.imag_adj, out)
+        out[f"{tag}_ppr_re_hops"] = np.stack([t.numpy() for t in re])
+        out[f"{tag}_ppr_im_hops"] = np.stack([t.numpy() for t in im])
 
     np.savez_compressed(os.path.join(HERE, "reference_ext.npz"), **out)
     print("wrote", sorted(out))

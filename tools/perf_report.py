@@ -27,11 +27,17 @@ report = {}
 for shape in args.shapes.split(","):
     name, _, kind = shape.partition("-")
     n, nnz, f, k = synth.SHAPES[name]
-    a = (synth.rmat_graph if kind == "rmat" else synth.uniform_graph)(n, nnz)
-    deg = np.diff(a.indptr)
-    x = torch.from_numpy(synth.features(n, f)).cuda()
-    a_dev = dev.upload_csr(a)
-    xp = dev.pack_features(x)
+    if kind == "rmatdev":      # counter-based scrambled R-MAT + procedural features, built on the device
+        a_dev = synth.rmat_shard_device(n, synth.rmat_draws(n, nnz), 0, n)
+        deg = (a_dev.indptr[1:] - a_dev.indptr[:-1]).cpu().numpy()
+        xp = synth.hash_features_device(n, f)
+        x = xp[:, :f].contiguous()
+    else:
+        a = (synth.rmat_graph if kind == "rmat" else synth.uniform_graph)(n, nnz)
+        deg = np.diff(a.indptr)
+        x = torch.from_numpy(synth.features(n, f)).cuda()
+        a_dev = dev.upload_csr(a)
+        xp = dev.pack_features(x)
     y = torch.empty_like(xp)
     norm, flags, _ = dev.sym_norm(a_dev, 0.5)
     torch.cuda.synchronize()

@@ -173,6 +173,31 @@ int srg_mag_norm_csr(const int32_t *indptr, const int32_t *indices, const void *
                      int32_t *out_indices, double *out_degree, double *out_real_f64, double *out_imag_f64,
                      float *out_real_f32, float *out_imag_f32, int32_t *out_flags, void *stream);
 
+/*
+ * Sparse x sparse product C = A B (float32 CSR; A: n_a x k_dim, B: k_dim x n_b) by expand / sort / compress.
+ * Replaces the DENSE N x N products of adj_to_un_in_out_dir_symmetric_norm (in_L = P^T P, out_L = P P^T,
+ * SSRG/operators/utils.py:216-227) and torch_sparse.spspmm(Psi, Psi^-1)
+ * (SSRG/models/base_scalable/base_model.py:208-214, wavelet/src/gwnn_layer.py:59-75).  c_ij is the sequential
+ * fp32 sum of a_ik * b_kj in ascending stored order of k; NaN results become 0 (utils.py:221); drop_zeros != 0
+ * removes exact zeros from the pattern (torch.nonzero, utils.py:223).  Rows of C come out sorted.
+ * a_vals / b_vals NULL = all ones.  out_* capacity `cap` entries (SRG_ERR_RANGE when the product holds more or
+ * when more than 2^31-1 intermediate products arise); *out_nnz (host) = entries.  Synchronises the stream.
+ */
+int srg_spgemm_csr_f32(const int32_t *a_indptr, const int32_t *a_indices, const float *a_vals, int64_t n_a,
+                       int64_t k_dim, const int32_t *b_indptr, const int32_t *b_indices, const float *b_vals,
+                       int64_t n_b, int32_t drop_zeros, int32_t *out_indptr, int32_t *out_indices,
+                       float *out_vals, int64_t cap, int64_t *out_nnz, int32_t *out_flags, void *stream);
+/* row i of the output = row i of the input + the entry (i, i) appended (torch_geometric add_self_loops as used
+ * at SSRG/operators/utils.py:199-201: one loop per node, duplicates are NOT merged here).  out_indices
+ * capacity indptr[n] + n. */
+int srg_csr_append_diagonal(const int32_t *indptr, const int32_t *indices, int64_t n, int32_t *out_indptr,
+                            int32_t *out_indices, void *stream);
+/* out_vals[p] = (deg[i]^(r-1) * vals[p]) * deg[col_p]^(-r) in float32, deg = row sums in stored order, inf -> 0:
+ * the float32 normalisation of SSRG/operators/utils.py:204-210, :229-237, :249-257.  vals NULL = all ones;
+ * out_degree optional. */
+int srg_csr_sym_scale_f32(const int32_t *indptr, const int32_t *indices, const float *vals, int64_t n, float r,
+                          float *out_vals, float *out_degree, void *stream);
+
 /* ---- synthetic inputs of the named shapes, generated on the device --------------------
  * Not a reference interface: BASELINE.json's configs 4 (power-law variant) and 5 are synthetic R-MAT
  * graphs too large to build on the host per rank.  Rows [row0, row1) of the symmetrised, duplicate-free,

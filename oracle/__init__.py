@@ -15,6 +15,7 @@ What it restates (file:line in /root/reference, SSRG = "Scalable Spectral Robust
   cheby_*           pygsp 0.5.1 (PyPI "PyGSP", un-pinned and absent from /root/reference):
                     call sites wavelet/src/utils.py:83,95,131-133 and
                     SSRG/models/base_scalable/base_model.py:184-189,243  -- PARITY UNPINNED
+  two_dir_norm      SSRG/operators/utils.py:195-260
   mag_norm / com_propagate  SSRG/operators/utils.py:95-138, SSRG/operators/base_operator.py:152-208, :316-345
   spectral_preprocess  SSRG/models/base_scalable/base_model.py:180-221 (on top of cheby_*: PARITY UNPINNED)
   nafs_combine      SSRG/operators/message_operator/over_smooth_distance_op.py:11-33
@@ -211,6 +212,42 @@ def mag_norm(adj, r, q, ppr_alpha=None):
     for m in (real, imag):
         m.sort_indices()
     return real, imag
+
+
+def two_dir_norm(adj, r):
+    """adj_to_un_in_out_dir_symmetric_norm (SSRG/operators/utils.py:195-260) in float32 numpy, dense products as
+    in the reference (small graphs only).  add_self_loops = one appended (i, i) entry per node.
+    Returns (un, in, out) float32 CSR matrices."""
+    coo = sp.coo_matrix(adj)
+    n = coo.shape[0]
+    f32 = np.float32
+    row = np.concatenate([coo.row, np.arange(n)]).astype(np.int64)
+    col = np.concatenate([coo.col, np.arange(n)]).astype(np.int64)
+    w = np.ones(len(row), dtype=f32)                                          # :197-201
+
+    def pw(d, e):
+        with np.errstate(divide="ignore"):
+            out = np.power(d, f32(e), dtype=f32)
+        out[np.isinf(out)] = 0
+        return out
+
+    def norm(rows, cols, vals):
+        deg = np.zeros(n, dtype=f32)
+        np.add.at(deg, rows, vals)                                            # scatter_add, stored order
+        return (pw(deg, r - 1)[rows] * vals * pw(deg, -r)[cols]).astype(f32), deg
+
+    un_w, deg = norm(row, col, w)                                             # :203-210
+    un = sp.csr_matrix((un_w, (row, col)), shape=(n, n))
+    p = pw(deg, -1)[row] * w                                                  # :212-214
+    p_dense = np.zeros((n, n), dtype=f32)
+    np.add.at(p_dense, (row, col), p)                                         # to_dense sums duplicates :215
+    res = []
+    for lmat in (p_dense.T @ p_dense, p_dense @ p_dense.T):                   # :216-217
+        lmat = np.where(np.isnan(lmat), f32(0), lmat).astype(f32)
+        rr, cc = np.nonzero(lmat)                                             # row-major, like torch.nonzero
+        vals, _ = norm(rr, cc, lmat[rr, cc])
+        res.append(sp.csr_matrix((vals, (rr, cc)), shape=(n, n)))
+    return un, res[0], res[1]
 
 
 def com_propagate(real_adj, imag_adj, feature, prop_steps, lib="oracle"):

@@ -72,6 +72,92 @@ nafs_combine_kernel(NafsHops hops, int n_hops, long long ld, long long n, int F,
   }
 }
 
+// Vector form for the device layout (ld % 4 == 0, <= 8 hop matrices, F <= 512): every lane keeps its
+// float4 columns of ALL hop rows in registers, so the row is read from HBM exactly once with every load
+// in flight at the same time, the softmax is evaluated redundantly per lane from registers, and the
+// weighted sum needs no second pass over memory.
+template <int VPL, int HMAX>
+__global__ void __launch_bounds__(256)
+nafs_combine_vec_kernel(NafsHops hops, int n_hops, long long ld4, long long n, int nvec, int F,
+                        float4 *__restrict__ out, long long ldo4, float *__restrict__ weights_out) {
+  const long long row = (long long)blockIdx.x * 8 + threadIdx.y;
+  if (row >= n) return;
+  const int lane = threadIdx.x;
+  float4 v[HMAX][VPL];
+#pragma unroll
+  for (int j = 0; j < HMAX; ++j) {
+#pragma unroll
+    for (int p = 0; p < VPL; ++p) {
+      const int c = lane + 32 * p;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < n_hops && c < nvec) {
+        t = __ldcs(reinterpret_cast<const float4 *>(hops.p[j]) + row * ld4 + c);
+        const int e = F - 4 * c;               // columns >= F (tail of the last float4) do not take part
+        if (e < 4) t.w = 0.f;
+        if (e < 3) t.z = 0.f;
+        if (e < 2) t.y = 0.f;
+      }
+      v[j][p] = t;
+    }
+  }
+  float score[HMAX];
+  float norm_fea = 0.f, smax = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < HMAX; ++j) {
+    if (j < n_hops) {
+      float dot = 0.f, sq = 0.f;
+#pragma unroll
+      for (int p = 0; p < VPL; ++p) {
+        const float4 a = v[0][p], b = v[j][p];
+        dot = __fadd_rn(dot, __fmul_rn(a.x, b.x));
+        dot = __fadd_rn(dot, __fmul_rn(a.y, b.y));
+        dot = __fadd_rn(dot, __fmul_rn(a.z, b.z));
+        dot = __fadd_rn(dot, __fmul_rn(a.w, b.w));
+        sq = __fadd_rn(sq, __fmul_rn(b.x, b.x));
+        sq = __fadd_rn(sq, __fmul_rn(b.y, b.y));
+        sq = __fadd_rn(sq, __fmul_rn(b.z, b.z));
+        sq = __fadd_rn(sq, __fmul_rn(b.w, b.w));
+      }
+      dot = warp_sum(dot);
+      sq = warp_sum(sq);
+      const float norm_cur = __fadd_rn(__fsqrt_rn(sq), 1e-10f);
+      if (j == 0) norm_fea = norm_cur;
+      score[j] = __fdiv_rn(__fdiv_rn(dot, norm_cur), norm_fea);
+      smax = fmaxf(smax, score[j]);
+    } else {
+      score[j] = 0.f;
+    }
+  }
+  float denom = 0.f;
+#pragma unroll
+  for (int j = 0; j < HMAX; ++j)
+    if (j < n_hops) {
+      score[j] = expf(__fsub_rn(score[j], smax));
+      denom = __fadd_rn(denom, score[j]);
+    }
+#pragma unroll
+  for (int j = 0; j < HMAX; ++j)
+    if (j < n_hops) {
+      score[j] = __fdiv_rn(score[j], denom);
+      if (weights_out && lane == j) weights_out[row * n_hops + j] = score[j];
+    }
+#pragma unroll
+  for (int p = 0; p < VPL; ++p) {
+    const int c = lane + 32 * p;
+    if (c >= nvec) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < HMAX; ++j)
+      if (j < n_hops) {
+        acc.x = __fadd_rn(acc.x, __fmul_rn(score[j], v[j][p].x));
+        acc.y = __fadd_rn(acc.y, __fmul_rn(score[j], v[j][p].y));
+        acc.z = __fadd_rn(acc.z, __fmul_rn(score[j], v[j][p].z));
+        acc.w = __fadd_rn(acc.w, __fmul_rn(score[j], v[j][p].w));
+      }
+    __stcs(out + row * ldo4 + c, acc);
+  }
+}
+
 }  // namespace srg
 
 using namespace srg;
@@ -97,6 +183,22 @@ extern "C" int srg_nafs_combine_f32(const float *const *hops, int32_t n_hops, in
   for (int j = n_hops; j < kNafsMaxHops; ++j) hp.p[j] = nullptr;
   const int64_t blocks = ceil_div64(n, 8);
   SRG_REQUIRE(blocks <= 2147483647LL, "nafs_combine: too many rows");
+  bool vec = (ld % 4 == 0) && (ld_out % 4 == 0) && ((uintptr_t)out % 16 == 0) && n_hops <= 8 && F <= 512;
+  for (int j = 0; j < n_hops && vec; ++j) vec = ((uintptr_t)hops[j] % 16 == 0);
+  if (vec) {
+    const int nvec = (F + 3) / 4;
+    float4 *o4 = reinterpret_cast<float4 *>(out);
+    const dim3 blk(32, 8);
+    cudaStream_t st = as_stream(stream);
+    if (nvec <= 32)
+      nafs_combine_vec_kernel<1, 8><<<(unsigned)blocks, blk, 0, st>>>(hp, n_hops, ld / 4, n, nvec, F, o4, ld_out / 4, weights_out);
+    else if (nvec <= 64)
+      nafs_combine_vec_kernel<2, 8><<<(unsigned)blocks, blk, 0, st>>>(hp, n_hops, ld / 4, n, nvec, F, o4, ld_out / 4, weights_out);
+    else
+      nafs_combine_vec_kernel<4, 8><<<(unsigned)blocks, blk, 0, st>>>(hp, n_hops, ld / 4, n, nvec, F, o4, ld_out / 4, weights_out);
+    SRG_LAUNCHED();
+    return SRG_OK;
+  }
   nafs_combine_kernel<<<(unsigned)blocks, dim3(32, 8), 0, as_stream(stream)>>>(hp, n_hops, ld, n, F, out, ld_out,
                                                                               weights_out);
   SRG_LAUNCHED();

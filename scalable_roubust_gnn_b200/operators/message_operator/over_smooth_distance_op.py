@@ -54,8 +54,13 @@ class OverSmoothDistanceWeightedOp(MessageOp):
         shape = feat_list[0].shape
         if any(f.shape != shape or f.dim() != 2 for f in feat_list):
             raise ValueError("The feature matrices must share one 2-d shape!")
-        dev = [f.to(device="cuda", dtype=torch.float32).contiguous() for f in feat_list]
-        return nafs_combine_device(dev).cpu()
+        from ...device import pack_features, unpack_features
+        width = shape[1]
+        if shape[0] * width == 0:
+            return torch.zeros(shape, dtype=torch.float32)
+        # the padded device layout (ld % 8 == 0): the same kernel path propagate_aggregate takes
+        dev = [pack_features(f.to(device="cuda", dtype=torch.float32).contiguous()) for f in feat_list]
+        return unpack_features(nafs_combine_device(dev, f=width), width).cpu()
 
     def fused_spec(self, n_hops):
         return _lib.SRG_AGG_NAFS, 0, n_hops, None

@@ -24,7 +24,7 @@ import torch
 from .. import _lib
 
 __all__ = ["csr_sparse_dense_matmul", "adj_to_symmetric_norm", "propagate_host", "propagate_aggregate_host",
-           "csr_host_parts", "adj_to_directed_symmetric_mag_norm", "DeviceHopRunner"]
+           "csr_host_parts", "adj_to_directed_symmetric_mag_norm", "adj_to_un_in_out_dir_symmetric_norm", "DeviceHopRunner"]
 
 
 def _ptr(a):
@@ -239,6 +239,56 @@ def adj_to_directed_symmetric_mag_norm(adj, r, q, ppr_alpha=None, device=0):
         imag = sp.csr_matrix((o_im[:m].cpu().numpy(), h_indices.copy(), h_indptr.copy()), shape=(n, n), copy=False)
     real.has_sorted_indices = imag.has_sorted_indices = True
     return real, imag
+
+
+def adj_to_un_in_out_dir_symmetric_norm(adj, r, device=0):
+    """Undirected / in / out normalised operators of a directed graph on the GPU
+    (SSRG/operators/utils.py:195-260, the normaliser of TwoDirLaplacianGraphOp).
+
+    The reference densifies: P = D^-1 (A + I) as an N x N float32 matrix, in_L = P^T P and out_L = P P^T by
+    dense products, then torch.nonzero.  Here P stays a CSR and the two products are sparse x sparse
+    (``srg_spgemm_csr_f32``); the float32 degree normalisation (row sums, pow, D^(r-1) L D^(-r)) follows the
+    reference's operation order.  Edge weights are ignored exactly as there (``torch.ones``, :197).
+    Returns three ``scipy.sparse.csr_matrix`` with float32 data: (un, in, out)."""
+    from .. import device as sdev
+    from ..sparse_mm import csr_sym_scale, csr_to_scipy, csr_transpose, spgemm
+    lib = _lib.load()
+    if lib.srg_device_count() <= 0:
+        raise _lib.SrgError(_lib.SRG_ERR_NODEV, "no CUDA device visible: libsrgnn_b200 has no CPU fallback")
+    if not sp.issparse(adj):
+        raise TypeError("The adjacency matrix must be a scipy sparse matrix!")
+    csr = adj.tocsr() if not isinstance(adj, sp.csr_matrix) else adj
+    indptr, indices, _, _, n, nnz = csr_host_parts(csr)
+    dev = torch.device("cuda", int(device))
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        d_indptr = torch.from_numpy(indptr).to(dev)
+        d_indices = torch.from_numpy(indices).to(dev) if nnz else torch.zeros(1, dtype=torch.int32, device=dev)
+        # A with one loop appended per node, then rows sorted and duplicates summed: the counts that
+        # torch.sparse(...).to_dense() (:215) and scatter_add (:203) see
+        cap = nnz + n
+        l_indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        l_indices = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+        _lib.check(lib.srg_csr_append_diagonal(_ptr(d_indptr), _ptr(d_indices), n, _ptr(l_indptr), _ptr(l_indices), stream))
+        c_indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        c_indices = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+        c_vals = torch.empty(max(cap, 1), dtype=torch.float64, device=dev)
+        c_nnz = torch.zeros(1, dtype=torch.int32, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.srg_csr_canonicalize(_ptr(l_indptr), _ptr(l_indices), None, _lib.SRG_VAL_ONES, n, cap,
+                                            _ptr(c_indptr), _ptr(c_indices), _ptr(c_vals), _ptr(c_nnz), _ptr(flags), stream))
+        if int(flags.item()) & _lib.SRG_FLAG_BAD_INDEX:
+            raise _lib.SrgError(_lib.SRG_ERR_INVALID, "column index out of range")
+        m = int(c_nnz.item())
+        a_tilde = sdev.DeviceCSR(c_indptr, c_indices[:max(m, 1)], c_vals[:max(m, 1)].to(torch.float32), n, m)
+        un = csr_sym_scale(a_tilde, float(r))                       # :204-210
+        p = csr_sym_scale(a_tilde, 0.0)                             # deg^-1 * count  (:212-214)
+        pt = csr_transpose(p)
+        in_l = spgemm(pt, p, drop_zeros=True)                       # P^T P  (:216, :220-227)
+        out_l = spgemm(p, pt, drop_zeros=True)                      # P P^T  (:217, :240-247)
+        in_n = csr_sym_scale(in_l, float(r))                        # :229-237
+        out_n = csr_sym_scale(out_l, float(r))                      # :249-257
+        return csr_to_scipy(un), csr_to_scipy(in_n), csr_to_scipy(out_n)
 
 
 class DeviceHopRunner:

@@ -24,7 +24,7 @@ import torch
 from . import _lib
 from .device import DeviceCSR, _p, _stream_ptr, spmm
 
-__all__ = ["DeviceAdj", "scipy_sparse_mat_to_device_adj", "csr_transpose"]
+__all__ = ["DeviceAdj", "scipy_sparse_mat_to_device_adj", "csr_transpose", "spgemm", "csr_sym_scale", "csr_to_scipy"]
 
 
 def csr_transpose(a: DeviceCSR) -> DeviceCSR:
@@ -143,3 +143,61 @@ def scipy_sparse_mat_to_device_adj(sparse_mx, device="cuda") -> DeviceAdj:
                     torch.from_numpy(np.ascontiguousarray(m.data[:nnz], dtype=np.float32)).to(device),
                     m.shape[0], nnz)
     return DeviceAdj(csr)
+
+
+def spgemm(a: DeviceCSR, b: DeviceCSR, drop_zeros: bool = False, cap: int | None = None) -> DeviceCSR:
+    """C = A B for square float32 DeviceCSR operands (``srg_spgemm_csr_f32``: expand / sort / compress, sequential
+    fp32 sums in ascending k).  ``data=None`` operands are all ones.  Rows of C are sorted; ``nnz`` is exact."""
+    lib = _lib.load()
+    dev = a.indptr.device
+    if a.n != b.n:
+        raise ValueError("spgemm: inner dimensions differ")
+    for m in (a, b):
+        if m.data is not None and m.data.dtype != torch.float32:
+            raise TypeError("spgemm: float32 values expected")
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = _stream_ptr(dev)
+    o_indptr = torch.empty(a.n + 1, dtype=torch.int32, device=dev)
+    nnz = C.c_int64(0)
+    if cap is None:
+        # count pass: capacity 0 reports the size in the error text; cheaper: bound by the product count
+        cap = int(_product_count(a, b))
+    o_indices = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    o_vals = torch.empty(max(cap, 1), dtype=torch.float32, device=dev)
+    _lib.check(lib.srg_spgemm_csr_f32(_p(a.indptr), _p(a.indices), _p(a.data), a.n, a.n, _p(b.indptr), _p(b.indices),
+                                      _p(b.data), b.n, 1 if drop_zeros else 0, _p(o_indptr), _p(o_indices), _p(o_vals),
+                                      cap, C.byref(nnz), _p(flags), stream))
+    if int(flags.item()) & _lib.SRG_FLAG_BAD_INDEX:
+        raise _lib.SrgError(_lib.SRG_ERR_INVALID, "spgemm: column index out of range")
+    m = int(nnz.value)
+    return DeviceCSR(o_indptr, o_indices[:max(m, 1)], o_vals[:max(m, 1)], a.n, m)
+
+
+def _product_count(a: DeviceCSR, b: DeviceCSR) -> int:
+    """Upper bound of nnz(A B): the number of intermediate products (index arithmetic on the row lengths)."""
+    m = int(a.indptr[-1].item())
+    if m == 0:
+        return 0
+    blen = (b.indptr[1:] - b.indptr[:-1]).to(torch.int64)
+    return int(blen[a.indices[:m].to(torch.int64)].sum().item())
+
+
+def csr_sym_scale(a: DeviceCSR, r: float, want_degree: bool = False):
+    """(deg^(r-1) * v) * deg_col^(-r) in float32 with deg = row sums of ``a`` (``srg_csr_sym_scale_f32``)."""
+    lib = _lib.load()
+    dev = a.indptr.device
+    out = torch.empty(max(int(a.indices.numel()), 1), dtype=torch.float32, device=dev)
+    deg = torch.empty(max(a.n, 1), dtype=torch.float32, device=dev) if want_degree else None
+    _lib.check(lib.srg_csr_sym_scale_f32(_p(a.indptr), _p(a.indices), _p(a.data), a.n, C.c_float(r), _p(out), _p(deg),
+                                         _stream_ptr(dev)))
+    res = DeviceCSR(a.indptr, a.indices, out, a.n, a.nnz)
+    return (res, deg) if want_degree else res
+
+
+def csr_to_scipy(a: DeviceCSR, dtype=np.float32):
+    indptr = a.indptr.cpu().numpy()
+    m = int(indptr[-1]) if a.n else 0
+    data = (a.data[:m].cpu().numpy() if a.data is not None else np.ones(m, dtype=dtype)).astype(dtype, copy=False)
+    out = sp.csr_matrix((data, a.indices[:m].cpu().numpy(), indptr), shape=(a.n, a.n), copy=False)
+    out.has_sorted_indices = True
+    return out

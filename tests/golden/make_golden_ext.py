@@ -126,6 +126,27 @@ def main():
         out[f"{tag}_ppr_re_hops"] = np.stack([t.numpy() for t in re])
         out[f"{tag}_ppr_im_hops"] = np.stack([t.numpy() for t in im])
 
+    # ---- undirected / in / out operators of a directed graph (TwoDirLaplacianGraphOp) ------------------
+    def add_self_loops(edge_index, edge_attr=None, fill_value=1.0, num_nodes=None):
+        # torch_geometric.utils.add_self_loops: one (i, i) entry appended per node, existing loops kept
+        loop = torch.arange(num_nodes, dtype=torch.long)      # as in PyG: the cat promotes int32 indices to int64
+        ei = torch.cat([edge_index, torch.stack([loop, loop])], dim=1)
+        ea = torch.cat([edge_attr, torch.full((num_nodes,), fill_value, dtype=edge_attr.dtype)])
+        return ei, ea
+
+    U.add_self_loops = add_self_loops
+    from operators.graph_operator.in_out_directed_laplacian_operator import TwoDirLaplacianGraphOp
+    for tag, (a, r, k) in {"twodir": (digraph(150, 600), 0.5, 2), "twodir_loops": (digraph(60, 260, loops=True), 0.3, 2)}.items():
+        xm = rg.random((a.shape[0], 5), dtype=np.float32)
+        csr_pack(f"{tag}_adj", a, out)
+        out[f"{tag}_x"] = xm
+        out[f"{tag}_params"] = np.array([r, k])
+        op = TwoDirLaplacianGraphOp(k, r=r)
+        lists = op.propagate(a, xm)
+        for nm, m, hops in zip(("un", "in", "out"), (op.un_adj, op.in_adj, op.out_adj), lists):
+            csr_pack(f"{tag}_{nm}", m, out)
+            out[f"{tag}_{nm}_hops"] = np.stack([t.numpy() for t in hops])
+
     np.savez_compressed(os.path.join(HERE, "reference_ext.npz"), **out)
     print("wrote", sorted(out))
 

@@ -282,6 +282,9 @@ int srg_spmm_csr_f32_push(const int32_t *indptr, const int32_t *indices, const f
  * destination buffer (own + peers) */
 int srg_push_rows_f32(const float *src, int64_t n_rows, int64_t ld, float *const *dests,
                       int32_t n_dests, int64_t dest_row0, void *stream);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on `stream`: copy-engine transfer between local and
+ * peer-mapped buffers (the per-hop exchange of the "copy" multi-GPU mode). */
+int srg_copy_async(void *dst, const void *src, int64_t bytes, void *stream);
 /* peer-mappable device buffers: plain cudaMalloc + CUDA IPC handles (64 bytes) */
 int srg_ipc_alloc(void **ptr, int64_t bytes);
 int srg_ipc_free(void *ptr);

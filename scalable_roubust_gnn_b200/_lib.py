@@ -77,6 +77,7 @@ SIGNATURES = {
     "srg_spmm_csr_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
     "srg_spmm_csr_f32_push": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, C.POINTER(_vp), _i32, _i64, _i64, _i32, _vp]),
     "srg_push_rows_f32": (C.c_int, [_vp, _i64, _i64, C.POINTER(_vp), _i32, _i64, _vp]),
+    "srg_copy_async": (C.c_int, [_vp, _vp, _i64, _vp]),
     "srg_ipc_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
     "srg_ipc_free": (C.c_int, [_vp]),
     "srg_ipc_get_handle": (C.c_int, [_vp, _vp]),

@@ -738,6 +738,18 @@ extern "C" int srg_push_rows_f32(const float *src, int64_t n_rows, int64_t ld, f
   return SRG_OK;
 }
 
+// DMA copy between (peer-mapped) device buffers on `stream`: the exchange of the "copy" multi-GPU mode runs
+// on the copy engines over NVLink, so it takes no SM, LSU or L1 bandwidth from the hop kernel it overlaps.
+extern "C" int srg_copy_async(void *dst, const void *src, int64_t bytes, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(bytes >= 0, "copy_async: negative size");
+  if (bytes == 0) return SRG_OK;
+  SRG_REQUIRE(dst && src, "copy_async: NULL pointer");
+  SRG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, as_stream(stream)));
+  return SRG_OK;
+}
+
 // ---- peer-mapped buffers (CUDA IPC) for the push hop ---------------------------------------------------
 extern "C" int srg_ipc_alloc(void **ptr, int64_t bytes) {
   int rc = require_device();

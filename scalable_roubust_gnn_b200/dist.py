@@ -12,6 +12,10 @@ The reference has no multi-GPU code; this is the scheme SURVEY.
       - ``"push"``: the SpMM epilogue stores every finished row into the next-hop buffer of every
         rank over NVLink peer mappings (CUDA IPC), one stream-ordered tiny all-reduce orders the
         hops across ranks.  No separate all-gather kernel runs.
+      - ``"copy"``: the hop runs in row chunks that write only the local buffer; as soon as a chunk is
+        done the copy engines move it to every peer's buffer (cudaMemcpyAsync on peer mappings, a second
+        stream), so the exchange costs no SM / load-store bandwidth and only the last chunk's copy is
+        exposed.
   * every output row is owned by one rank and reduced in CSR order => bitwise equal to 1 GPU.
 
 The orchestration is written against a small ``ops`` object so the CPU test-suite can drive the
@@ -106,7 +110,7 @@ class DistState:
         self.feat_groups = int(feat_groups)
         self.ri, self.ci = grid_coords(rank, world, self.feat_groups)
         self.n_row_blocks = world // self.feat_groups
-        if mode != "push" and self.feat_groups != 1:
+        if mode not in ("push", "copy") and self.feat_groups != 1:
             raise ValueError("the all-gather exchange supports the plain row partition only (feat_groups = 1)")
         self.rows_per, self.starts = row_partition(n, self.n_row_blocks)
         self.row0 = int(self.starts[self.ri])
@@ -125,9 +129,13 @@ class DistState:
         # the input exchange runs on a side stream so that it overlaps the normalisation
         self.side = torch.cuda.Stream(device=self.device)
         self._x_event = None
+        self.p2p = mode in ("push", "copy") and world > 1     # peer-mapped full buffers
+        self.comm = torch.cuda.Stream(device=self.device)     # copy mode: the DMA exchange stream
+        import os
+        self.n_chunks = int(os.environ.get("SRG_COPY_CHUNKS", "4"))   # copy mode: row chunks per hop
         nbytes = self.n_pad * self.ld * 4
         for _ in range(2):
-            if mode == "push" and world > 1:
+            if self.p2p:
                 p = C.c_void_p()
                 _lib.check(self.lib.srg_ipc_alloc(C.byref(p), max(nbytes, 256)))
                 self._raw.append(p)
@@ -135,7 +143,7 @@ class DistState:
             else:
                 t = torch.zeros((self.n_pad, self.ld), dtype=torch.float32, device=self.device)
             self.full.append(t)
-        if mode == "push" and world > 1:
+        if self.p2p:
             for b in range(2):
                 self.full[b].zero_()
             torch.cuda.synchronize()
@@ -217,7 +225,10 @@ class DeviceOps:
         from .device import _p, _stream_ptr
         st = self.st
         xin = st.full[i_in]
-        if st.mode == "push" and st.world > 1:
+        if st.mode == "copy" and st.world > 1:
+            self._hop_copy(local_norm, xin, i_out)
+            self._pushed = True
+        elif st.mode == "push" and st.world > 1:
             dests = (C.c_void_p * len(st.peers))(*st.peer_ptrs[i_out])
             _lib.check(st.lib.srg_spmm_csr_f32_push(_p(local_norm.indptr), _p(local_norm.indices), _p(local_norm.data),
                                                     st.n_local, local_norm.nnz_bound, _p(xin), st.ld, dests,
@@ -230,6 +241,41 @@ class DeviceOps:
                                                st.n_local, local_norm.nnz_bound, _p(xin), st.ld, _p(out), st.ld, st.f_loc,
                                                _stream_ptr(st.device)))
             self._pushed = False
+
+    def _hop_copy(self, local_norm, xin, i_out):
+        """Chunked local hop + copy-engine exchange: chunk c is copied to the peers while chunk c+1 computes."""
+        import torch
+
+        from . import _lib
+        from .device import _p, _stream_ptr
+        st = self.st
+        cur = torch.cuda.current_stream(st.device)
+        out_base = st.full[i_out].data_ptr()
+        row_bytes = st.ld * 4
+        n_chunks = max(1, min(st.n_chunks, st.n_local))
+        per = -(-st.n_local // n_chunks) if st.n_local else 0
+        per = (per + 3) // 4 * 4                                   # whole row groups of the stream kernel
+        ip = local_norm.indptr.data_ptr()
+        r0 = 0
+        while r0 < st.n_local:
+            r1 = min(st.n_local, r0 + per)
+            y = out_base + (st.row0 + r0) * row_bytes
+            _lib.check(st.lib.srg_spmm_csr_f32(C.c_void_p(ip + 4 * r0), _p(local_norm.indices), _p(local_norm.data),
+                                               r1 - r0, local_norm.nnz_bound, _p(xin), st.ld, C.c_void_p(y), st.ld,
+                                               st.f_loc, _stream_ptr(st.device)))
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            st.comm.wait_event(ev)
+            cs = C.c_void_p(st.comm.cuda_stream)
+            for blk, peer in enumerate(st.peers):
+                if peer == st.rank:
+                    continue
+                dst = st.peer_ptrs[i_out][blk] + (st.row0 + r0) * row_bytes
+                _lib.check(st.lib.srg_copy_async(C.c_void_p(dst), C.c_void_p(y), (r1 - r0) * row_bytes, cs))
+            r0 = r1
+        done = torch.cuda.Event()
+        done.record(st.comm)
+        cur.wait_event(done)
 
     def snapshot_local(self, i):
         st = self.st
@@ -247,7 +293,14 @@ def start_input_exchange(st: DistState, x_local_padded):
     side = st.side
     side.wait_stream(torch.cuda.current_stream(st.device))
     with torch.cuda.stream(side):
-        if st.mode == "push" and st.world > 1:
+        if st.mode == "copy" and st.world > 1:
+            st.full[0][st.row0:st.row0 + st.n_local].copy_(x_local_padded)
+            src = st.full[0].data_ptr() + st.row0 * st.ld * 4
+            for blk, peer in enumerate(st.peers):
+                if peer != st.rank:
+                    _lib.check(st.lib.srg_copy_async(C.c_void_p(st.peer_ptrs[0][blk] + st.row0 * st.ld * 4), C.c_void_p(src),
+                                                     st.n_local * st.ld * 4, C.c_void_p(side.cuda_stream)))
+        elif st.mode == "push" and st.world > 1:
             dests = (C.c_void_p * len(st.peers))(*st.peer_ptrs[0])
             _lib.check(st.lib.srg_push_rows_f32(_p(x_local_padded), st.n_local, st.ld, dests, len(st.peers), st.row0,
                                                 C.c_void_p(side.cuda_stream)))
@@ -270,14 +323,14 @@ def propagate_device(st: DistState, local_norm, x_local_padded, k, keep_hops=Tru
     torch.cuda.current_stream(st.device).wait_event(st._x_event)
     st._x_event = None
     if st.world > 1:
-        if st.mode == "push":
+        if st.mode in ("push", "copy"):
             st.dist.all_reduce(st._tick, group=st.group)      # every rank's rows have landed everywhere
         else:
             ops.exchange(cur)
     out = [ops.snapshot_local(cur)] if keep_hops else []
     for _ in range(k):
         ops.hop(local_norm, cur, nxt)
-        ops.exchange(nxt, pushed=(st.mode == "push" and st.world > 1))
+        ops.exchange(nxt, pushed=(st.mode in ("push", "copy") and st.world > 1))
         if keep_hops:
             out.append(ops.snapshot_local(nxt))
         cur, nxt = nxt, cur

@@ -74,12 +74,28 @@ nafs_combine_kernel(NafsHops hops, int n_hops, long long ld, long long n, int F,
 
 // Vector form for the device layout (ld % 4 == 0, <= 8 hop matrices, F <= 512): every lane keeps its
 // float4 columns of ALL hop rows in registers, so the row is read from HBM exactly once with every load
-// in flight at the same time, the softmax is evaluated redundantly per lane from registers, and the
-// weighted sum needs no second pass over memory.
+// in flight at the same time and the weighted sum needs no second pass over memory.  The 2 * hops partial
+// sums (dot_j, |x_j|^2) are reduced together by a halving butterfly (V values -> V/2 -> ... -> 1, then
+// plain xor steps): 9 shuffles instead of 40 for 4 hops, and each total lands in its own lane group, so
+// sqrt / divide / exp run ONCE for all hops (every hop in a different lane) instead of once per hop.
+template <int HALF>
+__device__ __forceinline__ void butterfly_step(float *a, bool up, int o) {
+#pragma unroll
+  for (int i = 0; i < HALF; ++i) {
+    const float send = up ? a[i] : a[i + HALF];
+    const float keep = up ? a[i + HALF] : a[i];
+    a[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, o));
+  }
+}
+
 template <int VPL, int HMAX>
 __global__ void __launch_bounds__(256)
 nafs_combine_vec_kernel(NafsHops hops, int n_hops, long long ld4, long long n, int nvec, int F,
                         float4 *__restrict__ out, long long ldo4, float *__restrict__ weights_out) {
+  static_assert(HMAX == 4 || HMAX == 8, "hop capacity");
+  constexpr int V = 2 * HMAX;              // values reduced together
+  constexpr int SH = (V == 8) ? 2 : 1;     // total of value i ends up in lanes [i << SH, (i + 1) << SH)
+  constexpr unsigned FULL = 0xffffffffu;
   const long long row = (long long)blockIdx.x * 8 + threadIdx.y;
   if (row >= n) return;
   const int lane = threadIdx.x;
@@ -100,47 +116,58 @@ nafs_combine_vec_kernel(NafsHops hops, int n_hops, long long ld4, long long n, i
       v[j][p] = t;
     }
   }
-  float score[HMAX];
-  float norm_fea = 0.f, smax = -INFINITY;
+  // per-lane partials: a[2j] = x0 . xj, a[2j + 1] = xj . xj
+  float a[V];
 #pragma unroll
   for (int j = 0; j < HMAX; ++j) {
-    if (j < n_hops) {
-      float dot = 0.f, sq = 0.f;
+    float dot = 0.f, sq = 0.f;
 #pragma unroll
-      for (int p = 0; p < VPL; ++p) {
-        const float4 a = v[0][p], b = v[j][p];
-        dot = __fadd_rn(dot, __fmul_rn(a.x, b.x));
-        dot = __fadd_rn(dot, __fmul_rn(a.y, b.y));
-        dot = __fadd_rn(dot, __fmul_rn(a.z, b.z));
-        dot = __fadd_rn(dot, __fmul_rn(a.w, b.w));
-        sq = __fadd_rn(sq, __fmul_rn(b.x, b.x));
-        sq = __fadd_rn(sq, __fmul_rn(b.y, b.y));
-        sq = __fadd_rn(sq, __fmul_rn(b.z, b.z));
-        sq = __fadd_rn(sq, __fmul_rn(b.w, b.w));
-      }
-      dot = warp_sum(dot);
-      sq = warp_sum(sq);
-      const float norm_cur = __fadd_rn(__fsqrt_rn(sq), 1e-10f);
-      if (j == 0) norm_fea = norm_cur;
-      score[j] = __fdiv_rn(__fdiv_rn(dot, norm_cur), norm_fea);
-      smax = fmaxf(smax, score[j]);
-    } else {
-      score[j] = 0.f;
+    for (int p = 0; p < VPL; ++p) {
+      const float4 x = v[0][p], b = v[j][p];
+      dot = __fadd_rn(dot, __fmul_rn(x.x, b.x));
+      dot = __fadd_rn(dot, __fmul_rn(x.y, b.y));
+      dot = __fadd_rn(dot, __fmul_rn(x.z, b.z));
+      dot = __fadd_rn(dot, __fmul_rn(x.w, b.w));
+      sq = __fadd_rn(sq, __fmul_rn(b.x, b.x));
+      sq = __fadd_rn(sq, __fmul_rn(b.y, b.y));
+      sq = __fadd_rn(sq, __fmul_rn(b.z, b.z));
+      sq = __fadd_rn(sq, __fmul_rn(b.w, b.w));
     }
+    a[2 * j] = dot;
+    a[2 * j + 1] = sq;
   }
+  if (V == 16) butterfly_step<V / 2>(a, lane & 16, 16);
+  butterfly_step<4>(a, lane & (V == 16 ? 8 : 16), V == 16 ? 8 : 16);
+  butterfly_step<2>(a, lane & (V == 16 ? 4 : 8), V == 16 ? 4 : 8);
+  butterfly_step<1>(a, lane & (V == 16 ? 2 : 4), V == 16 ? 2 : 4);
+  float tot = a[0];
+  if (V == 8) tot = __fadd_rn(tot, __shfl_xor_sync(FULL, tot, 2));
+  tot = __fadd_rn(tot, __shfl_xor_sync(FULL, tot, 1));
+  // lanes of group 2j hold dot_j; |x_j|^2 sits one group up, |x_0|^2 in group 1
+  const float sq_j = __shfl_sync(FULL, tot, (lane + (1 << SH)) & 31);
+  const float sq_0 = __shfl_sync(FULL, tot, 1 << SH);
+  const float norm_cur = __fadd_rn(__fsqrt_rn(sq_j), 1e-10f);
+  const float norm_fea = __fadd_rn(__fsqrt_rn(sq_0), 1e-10f);
+  const float score = __fdiv_rn(__fdiv_rn(tot, norm_cur), norm_fea);   // meaningful in the even groups
+  float smax = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < HMAX; ++j)
+    if (j < n_hops) smax = fmaxf(smax, __shfl_sync(FULL, score, (2 * j) << SH));
+  const float ex = expf(__fsub_rn(score, smax));
   float denom = 0.f;
 #pragma unroll
   for (int j = 0; j < HMAX; ++j)
-    if (j < n_hops) {
-      score[j] = expf(__fsub_rn(score[j], smax));
-      denom = __fadd_rn(denom, score[j]);
-    }
+    if (j < n_hops) denom = __fadd_rn(denom, __shfl_sync(FULL, ex, (2 * j) << SH));
+  const float wgt = __fdiv_rn(ex, denom);
+  float w[HMAX];
 #pragma unroll
-  for (int j = 0; j < HMAX; ++j)
+  for (int j = 0; j < HMAX; ++j) {
+    w[j] = 0.f;
     if (j < n_hops) {
-      score[j] = __fdiv_rn(score[j], denom);
-      if (weights_out && lane == j) weights_out[row * n_hops + j] = score[j];
+      w[j] = __shfl_sync(FULL, wgt, (2 * j) << SH);
+      if (weights_out && lane == ((2 * j) << SH)) weights_out[row * n_hops + j] = wgt;
     }
+  }
 #pragma unroll
   for (int p = 0; p < VPL; ++p) {
     const int c = lane + 32 * p;
@@ -149,10 +176,10 @@ nafs_combine_vec_kernel(NafsHops hops, int n_hops, long long ld4, long long n, i
 #pragma unroll
     for (int j = 0; j < HMAX; ++j)
       if (j < n_hops) {
-        acc.x = __fadd_rn(acc.x, __fmul_rn(score[j], v[j][p].x));
-        acc.y = __fadd_rn(acc.y, __fmul_rn(score[j], v[j][p].y));
-        acc.z = __fadd_rn(acc.z, __fmul_rn(score[j], v[j][p].z));
-        acc.w = __fadd_rn(acc.w, __fmul_rn(score[j], v[j][p].w));
+        acc.x = __fadd_rn(acc.x, __fmul_rn(w[j], v[j][p].x));
+        acc.y = __fadd_rn(acc.y, __fmul_rn(w[j], v[j][p].y));
+        acc.z = __fadd_rn(acc.z, __fmul_rn(w[j], v[j][p].z));
+        acc.w = __fadd_rn(acc.w, __fmul_rn(w[j], v[j][p].w));
       }
     __stcs(out + row * ldo4 + c, acc);
   }
@@ -190,12 +217,18 @@ extern "C" int srg_nafs_combine_f32(const float *const *hops, int32_t n_hops, in
     float4 *o4 = reinterpret_cast<float4 *>(out);
     const dim3 blk(32, 8);
     cudaStream_t st = as_stream(stream);
-    if (nvec <= 32)
-      nafs_combine_vec_kernel<1, 8><<<(unsigned)blocks, blk, 0, st>>>(hp, n_hops, ld / 4, n, nvec, F, o4, ld_out / 4, weights_out);
-    else if (nvec <= 64)
-      nafs_combine_vec_kernel<2, 8><<<(unsigned)blocks, blk, 0, st>>>(hp, n_hops, ld / 4, n, nvec, F, o4, ld_out / 4, weights_out);
-    else
-      nafs_combine_vec_kernel<4, 8><<<(unsigned)blocks, blk, 0, st>>>(hp, n_hops, ld / 4, n, nvec, F, o4, ld_out / 4, weights_out);
+#define SRG_NAFS_LAUNCH(VPL_, H_) \
+  nafs_combine_vec_kernel<VPL_, H_><<<(unsigned)blocks, blk, 0, st>>>(hp, n_hops, ld / 4, n, nvec, F, o4, ld_out / 4, weights_out)
+    if (n_hops <= 4) {
+      if (nvec <= 32) SRG_NAFS_LAUNCH(1, 4);
+      else if (nvec <= 64) SRG_NAFS_LAUNCH(2, 4);
+      else SRG_NAFS_LAUNCH(4, 4);
+    } else {
+      if (nvec <= 32) SRG_NAFS_LAUNCH(1, 8);
+      else if (nvec <= 64) SRG_NAFS_LAUNCH(2, 8);
+      else SRG_NAFS_LAUNCH(4, 8);
+    }
+#undef SRG_NAFS_LAUNCH
     SRG_LAUNCHED();
     return SRG_OK;
   }

@@ -282,7 +282,7 @@ def run_ours(args):
     hop_avg = float(np.mean(hop_ms)) * 1e-3
     bg = gather_bytes(n, nnz_hat, f)
     achieved = bg / hop_avg / 1e9
-    roofline = {"bound": "hbm", "kernel": "spmm_stream2_kernel<4,true> (one hop)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "spmm_stream_kernel<4,1,0> (one hop)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
                 "algorithmic_bytes_per_launch": bg, "compulsory_bytes_per_launch": comp_bytes(n, nnz_hat, f),
                 "hop_ms_avg": hop_avg * 1e3, "hop_ms_min": float(np.min(hop_ms)), "frac_of_8TBps_nominal": achieved / 8000.0}

@@ -213,7 +213,7 @@ def _emit_line(args, st, metric, unit, emit, mode, pf, world, rank, n, nnz_hat, 
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(args, n, nnz_hat, f, k), exchange=mode,
                                partition=f"{st.n_row_blocks} contiguous row blocks x {pf} feature slices"),
-                "roofline": {"bound": "hbm", "kernel": {"push": "spmm_stream2_kernel (push epilogue)", "copy": "spmm hop in row chunks + copy-engine exchange"}.get(mode, "spmm_stream2_kernel + ncclAllGather"),
+                "roofline": {"bound": "hbm", "kernel": {"push": "spmm_stream_kernel (push epilogue)", "copy": "spmm hop in row chunks + copy-engine exchange"}.get(mode, "spmm_stream_kernel + ncclAllGather"),
                              "achieved": bg / world / hop_s / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": bg / world / hop_s / 1e9 / peak, "peak_source": peak_src, "traffic": None,
                              "note": "per GPU, step time / K (includes the sharded normalisation and the exchange)",

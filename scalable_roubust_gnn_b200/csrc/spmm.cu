@@ -42,6 +42,7 @@ static int g_stream_rows = 4;    // rows per warp task (R)
 static int g_stream_batch = 4;   // B: 4 or 8
 static int g_gather_l2_64 = 1;   // gathers fetch 64-byte DRAM granules instead of whole 128-byte lines
 static int g_group_unroll = 4;   // U of the 32-lane group kernel (4 or 8)
+static int g_push_tma = 0;       // push hop: stage the block's rows in shared memory, one TMA bulk store per peer
 static int g_long_row = 1024;    // rows with more entries are split (0 = never split)
 
 // ---- vector abstraction for the group kernel: float4 fast path, float scalar path ------------------
@@ -195,12 +196,13 @@ __device__ __forceinline__ void store_row(const StreamArgs &a, float4 *yrow, con
   }
 }
 
-template <int B, bool L2_64, bool PUSH>
-__global__ void __launch_bounds__(kStreamWarps * 32) spmm_stream_kernel(const StreamArgs a) {
+// TMA = the push hop's bulk-store form: the warp writes its finished rows into the block's shared-memory tile
+// (`tile`, kStreamWarps * R rows of ldy float4) instead of global memory; the kernel's epilogue sends the tile.
+template <int B, bool L2_64, bool PUSH, bool TMA>
+__device__ __forceinline__ void stream_warp_task(const StreamArgs &a, float4 *smem4, float4 *tile, const int w,
+                                                 const int lane) {
   constexpr int S = 2 * B;
   constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ float4 smem4[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned ring = (unsigned)__cvta_generic_to_shared(smem4 + (size_t)w * S * 32 + lane);
 
   const long long n_rows = a.n_rows_dev ? min((long long)*a.n_rows_dev, a.n_rows) : a.n_rows;
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) spmm_stream_kernel(const St
   const int col = chunk * 32 + lane;
   const bool active = col < a.nvec;
   const float4 *Xc = a.X + col;
-  float4 *yrow = a.Y + r0 * a.ldy + col;
+  float4 *yrow = TMA ? (tile + (long long)(w * a.R) * a.ldy + col) : (a.Y + r0 * a.ldy + col);
   const unsigned ldx = a.ldx;
   const long long ldy = a.ldy;
 
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) spmm_stream_kernel(const St
           acc.w = fmaf(v, x.w, acc.w);
         }
       }
-      if (active) store_row<PUSH>(a, yrow + (long long)r * ldy, acc);
+      if (active) store_row<PUSH && !TMA>(a, yrow + (long long)r * ldy, acc);
     }
     return;
   }
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) spmm_stream_kernel(const St
             acc.w = fmaf(v, x.w, acc.w);
           }
           if ((((j < 0) ? prev_mask : endmask) >> jj) & 1u) {
-            if (active) store_row<PUSH>(a, yrow, acc);
+            if (active) store_row<PUSH && !TMA>(a, yrow, acc);
             yrow += ldy;
             acc = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -320,6 +322,41 @@ __global__ void __launch_bounds__(kStreamWarps * 32) spmm_stream_kernel(const St
     }
   }
   cp_async_wait<0>();
+}
+
+template <int B, bool L2_64, bool PUSH, bool TMA>
+__global__ void __launch_bounds__(kStreamWarps * 32) spmm_stream_kernel(const StreamArgs a) {
+  extern __shared__ float4 smem4[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 *tile = smem4 + (size_t)kStreamWarps * (2 * B) * 32;   // behind the gather rings
+  if (TMA) {
+    // rows this kernel leaves alone (hub rows go to the segment kernels) and the pad columns travel as zeros
+    const int tile_vec = kStreamWarps * a.R * (int)a.ldy;
+    for (int i = threadIdx.x; i < tile_vec; i += kStreamWarps * 32) tile[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+  }
+  stream_warp_task<B, L2_64, PUSH, TMA>(a, smem4, tile, w, lane);
+  if (TMA) {
+    // generic-proxy writes of the tile -> visible to the async proxy, then ONE bulk store per destination:
+    // the exchange leaves the SM through the TMA unit, not through the load/store path the gathers use
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const long long row0 = (long long)blockIdx.x * kStreamWarps * a.R;
+      const long long rows = min((long long)kStreamWarps * a.R, a.n_rows - row0);
+      if (rows > 0) {
+        const unsigned bytes = (unsigned)(rows * a.ldy * 16);
+        const unsigned src = (unsigned)__cvta_generic_to_shared(tile);
+        for (int d = 0; d < a.peers.count; ++d) {
+          float4 *dst = a.peers.p[d] + row0 * a.ldy;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    }
+  }
 }
 
 // ---- long rows: device-side plan, segment tasks, ordered combine ------------------------------------------
@@ -406,17 +443,18 @@ static int alloc_long_plan(int64_t nnz, int L, int64_t ldp, LongPlan *p, cudaStr
   return SRG_OK;
 }
 
-template <int B, bool L2_64, bool PUSH>
+template <int B, bool L2_64, bool PUSH, bool TMA>
 static int launch_stream_t(const StreamArgs &a, int64_t blocks, cudaStream_t s) {
-  const size_t smem = (size_t)kStreamWarps * (2 * B) * 32 * sizeof(float4);
-  SRG_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<B, L2_64, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  spmm_stream_kernel<B, L2_64, PUSH><<<(unsigned)blocks, kStreamWarps * 32, smem, s>>>(a);
+  size_t smem = (size_t)kStreamWarps * (2 * B) * 32 * sizeof(float4);
+  if (TMA) smem += (size_t)kStreamWarps * a.R * a.ldy * sizeof(float4);
+  SRG_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<B, L2_64, PUSH, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  spmm_stream_kernel<B, L2_64, PUSH, TMA><<<(unsigned)blocks, kStreamWarps * 32, smem, s>>>(a);
   SRG_LAUNCHED();
   return SRG_OK;
 }
 
 template <bool PUSH>
-static int launch_stream(const StreamArgs &a, int64_t max_rows, cudaStream_t s) {
+static int launch_stream(const StreamArgs &a, int64_t max_rows, cudaStream_t s, bool tma = false) {
   const int64_t tasks = ceil_div64(max_rows, a.R) * a.chunks;
   const int64_t blocks = ceil_div64(tasks, kStreamWarps);
   if (blocks > 2147483647LL) {
@@ -424,9 +462,14 @@ static int launch_stream(const StreamArgs &a, int64_t max_rows, cudaStream_t s) 
     return SRG_ERR_RANGE;
   }
   if (blocks == 0) return SRG_OK;
+  if (PUSH && tma) {
+    if (g_stream_batch == 8)
+      return g_gather_l2_64 ? launch_stream_t<8, true, PUSH, PUSH>(a, blocks, s) : launch_stream_t<8, false, PUSH, PUSH>(a, blocks, s);
+    return g_gather_l2_64 ? launch_stream_t<4, true, PUSH, PUSH>(a, blocks, s) : launch_stream_t<4, false, PUSH, PUSH>(a, blocks, s);
+  }
   if (g_stream_batch == 8)
-    return g_gather_l2_64 ? launch_stream_t<8, true, PUSH>(a, blocks, s) : launch_stream_t<8, false, PUSH>(a, blocks, s);
-  return g_gather_l2_64 ? launch_stream_t<4, true, PUSH>(a, blocks, s) : launch_stream_t<4, false, PUSH>(a, blocks, s);
+    return g_gather_l2_64 ? launch_stream_t<8, true, PUSH, false>(a, blocks, s) : launch_stream_t<8, false, PUSH, false>(a, blocks, s);
+  return g_gather_l2_64 ? launch_stream_t<4, true, PUSH, false>(a, blocks, s) : launch_stream_t<4, false, PUSH, false>(a, blocks, s);
 }
 
 // one hop through the stream kernel (+ the long-row pipeline when nnz is known)
@@ -466,7 +509,9 @@ static int stream_hop(const int *indptr, const int *indices, const float *vals, 
     plan_long_rows_kernel<<<(unsigned)ceil_div64(n_rows, 256), 256, 0, s>>>(indptr, n_rows, L, plan);
     SRG_LAUNCHED();
   }
-  rc = launch_stream<PUSH>(a, n_rows, s);
+  // bulk-store form of the push hop: one row chunk per task (nvec <= 32), whole rows of <= 32 float4, tile <= 32 KB
+  const bool tma = PUSH && g_push_tma && a.chunks == 1 && a.ldy <= 32 && a.R <= 8 && a.peers.count > 0;
+  rc = launch_stream<PUSH>(a, n_rows, s, tma);
   if (split && !rc) {
     // segments as single-row tasks into the partial buffer, then the ordered combine
     StreamArgs g = a;
@@ -613,6 +658,7 @@ extern "C" int srg_set_tuning(const char *key, int64_t value) {
   else if (k == "group_unroll") g_group_unroll = (int)value;
   else if (k == "gather_l2_64") g_gather_l2_64 = (int)value;
   else if (k == "long_row") g_long_row = (int)value;
+  else if (k == "push_tma") g_push_tma = (int)value;
   else {
     set_err("set_tuning: unknown key '%s'", key);
     return SRG_ERR_INVALID;

@@ -24,6 +24,7 @@ same code over gloo with the oracle as the local hop (tests/test_dist_cpu.py).
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import scipy.sparse as sp
@@ -106,6 +107,11 @@ class DistState:
         from .device import pad_ld
         self.torch, self.dist, self._lib = torch, dist, _lib
         self.lib = _lib.load()
+        if mode == "push_tma":      # push hop whose epilogue is one TMA bulk store per peer (csrc/spmm.cu)
+            mode = "push"
+            _lib.set_tuning("push_tma", 1)
+        elif mode == "push":
+            _lib.set_tuning("push_tma", int(os.environ.get("SRG_PUSH_TMA", "0")))
         self.n, self.f, self.world, self.rank, self.mode, self.group = n, f, world, rank, mode, group
         self.feat_groups = int(feat_groups)
         self.ri, self.ci = grid_coords(rank, world, self.feat_groups)
@@ -131,7 +137,6 @@ class DistState:
         self._x_event = None
         self.p2p = mode in ("push", "copy") and world > 1     # peer-mapped full buffers
         self.comm = torch.cuda.Stream(device=self.device)     # copy mode: the DMA exchange stream
-        import os
         self.n_chunks = int(os.environ.get("SRG_COPY_CHUNKS", "4"))   # copy mode: row chunks per hop
         nbytes = self.n_pad * self.ld * 4
         for _ in range(2):

@@ -37,7 +37,7 @@ def run(args, workloads, metric, unit, emit):
     t0 = time.perf_counter()
     # 8 GPUs are NVLink-ingress bound with a pure row partition (every rank receives 7/8 of X per hop):
     # a 4 x 2 grid (row blocks x feature slices) halves the exchange volume
-    pf = int(os.environ.get("SRG_FEAT_GROUPS", "2" if (world >= 8 and mode in ("push", "copy")) else "1"))
+    pf = int(os.environ.get("SRG_FEAT_GROUPS", "2" if (world >= 8 and mode in ("push", "copy", "push_tma")) else "1"))
     st = sdist.DistState(n, f, world, rank, mode=mode, feat_groups=pf)
     s, e = st.row0, st.row0 + st.n_local
     f_loc = st.f_loc
@@ -213,7 +213,7 @@ def _emit_line(args, st, metric, unit, emit, mode, pf, world, rank, n, nnz_hat, 
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(args, n, nnz_hat, f, k), exchange=mode,
                                partition=f"{st.n_row_blocks} contiguous row blocks x {pf} feature slices"),
-                "roofline": {"bound": "hbm", "kernel": {"push": "spmm_stream_kernel (push epilogue)", "copy": "spmm hop in row chunks + copy-engine exchange"}.get(mode, "spmm_stream_kernel + ncclAllGather"),
+                "roofline": {"bound": "hbm", "kernel": {"push": "spmm_stream_kernel (push epilogue)", "push_tma": "spmm_stream_kernel (TMA bulk-store push epilogue)", "copy": "spmm hop in row chunks + copy-engine exchange"}.get(mode, "spmm_stream_kernel + ncclAllGather"),
                              "achieved": bg / world / hop_s / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": bg / world / hop_s / 1e9 / peak, "peak_source": peak_src, "traffic": None,
                              "note": "per GPU, step time / K (includes the sharded normalisation and the exchange)",

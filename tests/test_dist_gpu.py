@@ -21,7 +21,7 @@ def _graph(n, weighted, rmat):
 
 def rank_overlap(mode, weighted):
     """exercise both the overlapped and the in-line input exchange across the parametrisations"""
-    return mode in ("push", "copy") or weighted
+    return mode in ("push", "copy", "push_tma") or weighted
 
 
 def _worker(rank, world, port, n, f, k, mode, weighted, out_dir, rmat=False, feat_groups=1):
@@ -54,12 +54,12 @@ def _worker(rank, world, port, n, f, k, mode, weighted, out_dir, rmat=False, fea
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("mode", ["allgather", "push", "copy"])
+@pytest.mark.parametrize("mode", ["allgather", "push", "copy", "push_tma"])
 @pytest.mark.parametrize("weighted", [False, True])
 def test_two_gpus_bitwise_equal_one_gpu(tmp_path, mode, weighted):
     from scalable_roubust_gnn_b200 import device as dev
     world, n, f, k = 2, 50001, 100, 3
-    port = 29600 + (os.getpid() % 300) + ["allgather", "push", "copy"].index(mode) + (3 if weighted else 0)
+    port = 29600 + (os.getpid() % 300) + ["allgather", "push", "copy", "push_tma"].index(mode) + (4 if weighted else 0)
     mp.spawn(_worker, args=(world, port, n, f, k, mode, weighted, str(tmp_path)), nprocs=world, join=True)
     adj = _graph(n, weighted, False)
     x = np.random.default_rng(1).random((n, f), dtype=np.float32)
@@ -77,13 +77,13 @@ def test_two_gpus_bitwise_equal_one_gpu(tmp_path, mode, weighted):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("mode", ["allgather", "push", "copy"])
+@pytest.mark.parametrize("mode", ["allgather", "push", "copy", "push_tma"])
 def test_two_gpus_power_law_rows(tmp_path, mode):
     """R-MAT graph with hub rows: the segment + combine path (and its push variant) across 2 GPUs equals
     the single-GPU result bit for bit (same segments, same order)."""
     from scalable_roubust_gnn_b200 import device as dev
     world, n, f, k = 2, 60000, 100, 2
-    port = 29700 + (os.getpid() % 200) + ["allgather", "push", "copy"].index(mode)
+    port = 29700 + (os.getpid() % 200) + ["allgather", "push", "copy", "push_tma"].index(mode)
     mp.spawn(_worker, args=(world, port, n, f, k, mode, False, str(tmp_path), True), nprocs=world, join=True)
     adj = _graph(n, False, True)
     assert np.diff(adj.indptr).max() > 1024
@@ -97,14 +97,14 @@ def test_two_gpus_power_law_rows(tmp_path, mode):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs 4 GPUs")
-@pytest.mark.parametrize("mode", ["push", "copy"])
+@pytest.mark.parametrize("mode", ["push", "copy", "push_tma"])
 @pytest.mark.parametrize("rmat", [False, True])
 def test_four_gpus_row_by_feature_grid(tmp_path, rmat, mode):
     """2 row blocks x 2 feature slices (the layout used at 8 GPUs to halve the exchange): every rank's
     tile equals the corresponding tile of the single-GPU result bit for bit."""
     from scalable_roubust_gnn_b200 import device as dev, dist as sdist
     world, n, f, k, pf = 4, 40001, 100, 3, 2
-    port = 29800 + (os.getpid() % 150) + (1 if rmat else 0) + (2 if mode == "copy" else 0)
+    port = 29800 + (os.getpid() % 150) + (1 if rmat else 0) + 2 * ["push", "copy", "push_tma"].index(mode)
     mp.spawn(_worker, args=(world, port, n, f, k, mode, False, str(tmp_path), rmat, pf), nprocs=world, join=True)
     adj = _graph(n, False, rmat)
     x = np.random.default_rng(1).random((n, f), dtype=np.float32)

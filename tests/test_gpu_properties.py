@@ -96,3 +96,97 @@ def test_propagate_matches_oracle(case, f, k):
     assert len(got) == k + 1
     for g, w in zip(got, want):
         np.testing.assert_allclose(g.numpy(), w, rtol=1e-5, atol=1e-6)
+
+
+# ---- the "next" rows: transpose, sparse product, magnetic normalisation, NAFS ------------------
+@st.composite
+def square_f32(draw):
+    n = draw(st.integers(1, 70))
+    seed = draw(st.integers(0, 2**31 - 1))
+    m = sp.random(n, n, density=draw(st.sampled_from([0.0, 0.03, 0.2, 0.6])), random_state=seed % (2**31), format="csr",
+                  dtype=np.float32)
+    m.data = np.random.default_rng(seed).standard_normal(len(m.data)).astype(np.float32)
+    m.sort_indices()
+    return m
+
+
+@settings(**SETTINGS)
+@given(square_f32())
+def test_transpose_exact_and_involutive(m):
+    from scalable_roubust_gnn_b200.sparse_mm import csr_to_scipy, csr_transpose, scipy_sparse_mat_to_device_adj
+    d = scipy_sparse_mat_to_device_adj(m).csr
+    t = csr_transpose(d)
+    want = m.T.tocsr()
+    want.sort_indices()
+    got = csr_to_scipy(t)
+    np.testing.assert_array_equal(got.indptr, want.indptr)
+    np.testing.assert_array_equal(got.indices, want.indices)
+    np.testing.assert_array_equal(got.data, want.data)
+    back = csr_to_scipy(csr_transpose(t))
+    np.testing.assert_array_equal(back.indices, m.indices)
+    np.testing.assert_array_equal(back.data, m.data)
+
+
+@settings(**SETTINGS)
+@given(square_f32(), st.integers(0, 2**31 - 1))
+def test_spgemm_matches_scipy_pattern_and_values(a, seed):
+    from scalable_roubust_gnn_b200.sparse_mm import csr_to_scipy, scipy_sparse_mat_to_device_adj, spgemm
+    n = a.shape[0]
+    b = sp.random(n, n, density=0.15, random_state=seed % (2**31), format="csr", dtype=np.float32)
+    b.sort_indices()
+    got = csr_to_scipy(spgemm(scipy_sparse_mat_to_device_adj(a).csr, scipy_sparse_mat_to_device_adj(b).csr))
+    # scipy keeps structural entries whose products cancel, exactly like the expand / sort / compress path
+    want = (a.astype(np.float64) @ b.astype(np.float64)).tocsr()
+    want.sort_indices()
+    np.testing.assert_array_equal(got.indptr, want.indptr)
+    np.testing.assert_array_equal(got.indices, want.indices)
+    np.testing.assert_allclose(got.data, want.data, rtol=2e-5, atol=1e-6)
+
+
+@st.composite
+def digraph(draw):
+    n = draw(st.integers(1, 60))
+    seed = draw(st.integers(0, 2**31 - 1))
+    m = sp.random(n, n, density=draw(st.sampled_from([0.0, 0.05, 0.3])), random_state=seed % (2**31), format="csr")
+    if draw(st.booleans()):
+        m.data[:] = 1.0                                        # unweighted: theta in {0, +-1}
+    else:
+        m.data = np.round(m.data + 0.25, 3)
+    m = sp.csr_matrix(m, dtype=np.float64)
+    m.sort_indices()
+    return m, draw(st.sampled_from([0.0, 0.3, 0.5, 1.0])), draw(st.sampled_from([0.0, 0.1, 0.25]))
+
+
+@settings(**SETTINGS)
+@given(digraph(), st.booleans())
+def test_magnetic_norm_matches_oracle_on_arbitrary_digraphs(case, ppr):
+    from scalable_roubust_gnn_b200.operators import adj_to_directed_symmetric_mag_norm
+    adj, r, q = case
+    alpha = 0.15 if ppr else None
+    want_re, want_im = oracle.mag_norm(adj, r, q, alpha)
+    got_re, got_im = adj_to_directed_symmetric_mag_norm(adj, r, q, ppr_alpha=alpha)
+    for got, want in ((got_re, want_re), (got_im, want_im)):
+        assert_same_structure(got, want)
+        if want.nnz:
+            np.testing.assert_allclose(got.data, want.data, rtol=4e-15, atol=1e-15)
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+@given(st.integers(1, 50), st.integers(1, 150), st.integers(1, 9), st.integers(0, 2**31 - 1))
+def test_nafs_properties(n, f, hops, seed):
+    """weights are a softmax (positive, sum 1), the output is their convex combination row by row, identical hop
+    matrices give uniform weights, and the result matches the restatement."""
+    from scalable_roubust_gnn_b200.operators.message_operator import nafs_combine_device
+    rng = np.random.default_rng(seed)
+    feats = [rng.standard_normal((n, f)).astype(np.float32) for _ in range(hops)]
+    devs = [dev.pack_features(torch.from_numpy(x).cuda()) for x in feats]
+    out, w = nafs_combine_device(devs, f=f, want_weights=True)
+    w = w.cpu().numpy()
+    assert (w > 0).all()
+    np.testing.assert_allclose(w.sum(1), 1.0, atol=2e-6)
+    want, w_want = oracle.nafs_combine(feats, return_weights=True)
+    np.testing.assert_allclose(w, w_want, rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(out[:, :f].cpu().numpy(), want, rtol=2e-5, atol=2e-6)
+    same = [devs[0]] * hops
+    _, wu = nafs_combine_device(same, f=f, want_weights=True)
+    np.testing.assert_allclose(wu.cpu().numpy(), 1.0 / hops, rtol=1e-6)

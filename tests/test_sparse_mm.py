@@ -126,3 +126,25 @@ def test_csr_transpose_exact_with_padding_and_empty_rows():
     np.testing.assert_array_equal(t.indices.cpu().numpy()[:m], want.indices)
     np.testing.assert_array_equal(t.data.cpu().numpy()[:m], want.data)
     assert float(t.data[m:].abs().sum()) == 0.0
+
+
+def test_device_adj_autograd_plumbing_on_cpu(monkeypatch):
+    """torch.mm / spmm / sparse.mm / matmul / @ reach DeviceAdj through __torch_function__ and backward uses the
+    transpose: checked on the CPU with the device hop replaced by a dense product (plumbing only)."""
+    from scalable_roubust_gnn_b200 import sparse_mm as sm
+    from scalable_roubust_gnn_b200.device import DeviceCSR
+    a = sp.random(6, 6, 0.5, format="csr", dtype=np.float32, random_state=0)
+    dense = torch.from_numpy(a.toarray())
+    csr = DeviceCSR(torch.from_numpy(a.indptr), torch.from_numpy(a.indices), torch.from_numpy(a.data), 6, a.nnz)
+    t_csr = DeviceCSR(csr.indptr, csr.indices, csr.data, 6, a.nnz)
+    monkeypatch.setattr(sm.DeviceAdj, "_hop", staticmethod(lambda c, x: (dense if c is csr else dense.t()) @ x.detach()))
+    adj = sm.DeviceAdj(csr)
+    adj._t = sm.DeviceAdj(t_csr, transpose=adj)
+    assert adj.t().t() is adj and tuple(adj.shape) == (6, 6) and adj.is_sparse
+    for fn in (torch.mm, torch.spmm, torch.sparse.mm, torch.matmul, lambda p, q: p @ q):
+        x = torch.rand(6, 3, requires_grad=True)
+        y = fn(adj, x)
+        y.sum().backward()
+        assert torch.allclose(y, dense @ x) and torch.allclose(x.grad, dense.t() @ torch.ones(6, 3))
+    with pytest.raises(TypeError):
+        torch.add(adj, torch.ones(6, 6))          # anything but the products is not intercepted

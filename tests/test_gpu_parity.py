@@ -506,3 +506,28 @@ def test_reference_style_ctypes_binding():
     answer2 = np.zeros(feat.shape).astype(np.float32).flatten()
     assert lib.FloatCSRMulDense(answer2, adj.nnz, adj.data.astype(np.float32), adj.indices, adj.indptr, feat.flatten(), 4000, 47) == 0
     np.testing.assert_array_equal(answer2, answer)
+
+
+@pytest.mark.gpu
+def test_propagate_device_output_equals_host_output(golden_prop):
+    """SURVEY §8b placement opt-in: the same K+1 matrices, left on the GPU."""
+    from scalable_roubust_gnn_b200.operators import MeanMessageOp, PprGraphOp, SymLaplacianGraphOp
+    adj = golden_csr(golden_prop, "rand_unw_adj")
+    x = golden_prop["rand_unw_x"]
+    for op in (SymLaplacianGraphOp(3, r=0.5), PprGraphOp(2, r=0.5, alpha=0.15)):
+        host = op.propagate(adj, x)
+        devl = op.propagate(adj, x, device_output=True)
+        assert len(devl) == len(host) and all(t.is_cuda and t.dtype == torch.float32 and tuple(t.shape) == x.shape for t in devl)
+        for h, d in zip(host, devl):
+            np.testing.assert_array_equal(d.cpu().numpy(), h.numpy())
+        idx = torch.tensor([3, 1, 7])
+        np.testing.assert_array_equal(devl[-1][idx].cpu().numpy(), host[-1][idx].numpy())       # base_model.py:84-87
+        assert isinstance(op.adj, sp.csr_matrix)
+    mean = MeanMessageOp(0, 4)
+    np.testing.assert_array_equal(mean.aggregate(SymLaplacianGraphOp(3).propagate(adj, x, device_output=True)).cpu().numpy(),
+                                  mean.aggregate(SymLaplacianGraphOp(3).propagate(adj, x)).numpy())
+    # a directed input takes the general normalisation through construct_adj
+    asym = golden_csr(golden_prop, "asym_adj")
+    xa = golden_prop["asym_x"]
+    got = SymLaplacianGraphOp(2, r=0.5).propagate(asym, xa, device_output=True)
+    np.testing.assert_allclose(got[2].cpu().numpy(), golden_prop["asym_r0.5_hop2"], rtol=1e-5, atol=1e-6)

@@ -103,6 +103,34 @@ def run(args, workloads, metric, unit, emit):
     t_step = float(ms.item()) * 1e-3 / args.steps
     launches = _lib.launch_count() - launches0
 
+    # ---- overlap probe (SURVEY 8d multi-GPU reporting): the local hop alone, the exchange alone, the fused hop ---
+    # collectives (normalisation all-gather, barrier, the hops' ticks) run unconditionally on every rank; only the
+    # purely local timing sits inside the try, so a failure cannot leave another rank waiting
+    sdist.start_input_exchange(st, x_loc)
+    norm_p, _ = sdist.dist_sym_norm(st, a_loc, 0.5)
+    sdist.propagate_device(st, norm_p, x_loc, 1, keep_hops=False)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    hop_reps = 3
+    for _ in range(hop_reps):
+        sdist.propagate_device(st, norm_p, x_loc, k, keep_hops=False)
+    e1.record()
+    torch.cuda.synchronize()
+    t_hops = torch.tensor([e0.elapsed_time(e1) / (hop_reps * k)], device="cuda")
+    dist.all_reduce(t_hops, op=dist.ReduceOp.MAX)
+    probe = {"hop_fused_ms": float(t_hops.item())}
+    dist.barrier()
+    try:
+        probe.update(_overlap_probe(st, norm_p, lib, torch))
+        probe["overlap_efficiency"] = max(probe["hop_local_only_ms"], probe["exchange_only_ms"]) / probe["hop_fused_ms"]
+    except Exception as exc:                      # auxiliary figures must not take the bench line down
+        probe["error"] = str(exc)
+    torch.cuda.synchronize()
+    dist.barrier()
+    del norm_p
+
     verify = None
     if gen == "device":
         verify = _verify_device_generated(st, a_loc, x_loc, k, f, sdist, synth, torch, dist)
@@ -111,9 +139,47 @@ def run(args, workloads, metric, unit, emit):
         e2e_line = _e2e(args, st, a_loc_host, x_loc_host, k, f_loc, lib, dev, sdist, torch, dist)
     clocks = sampler.stop() if rank == 0 else None
     _emit_line(args, st, metric, unit, emit, mode, pf, world, rank, n, nnz_hat, f, f_loc, k, t_step, launches, e2e_line,
-               clocks, verify, gen)
+               clocks, verify, gen, probe)
     st.close()
     dist.destroy_process_group()
+
+
+def _overlap_probe(st, norm, lib, torch):
+    """This rank's hop WITHOUT the exchange (rows written to the local buffer only) and the exchange WITHOUT the
+    hop (the finished slice pushed to every peer), CUDA events, no collectives.  All ranks run it at the same
+    time (a barrier precedes it), so the exchange figure sees the real NVLink contention."""
+    import ctypes as C
+
+    from . import _lib
+    from .device import _p, _stream_ptr
+    s = _stream_ptr(st.device)
+    xin, out = st.full[0], st.full[1][st.row0:st.row0 + st.n_local]
+
+    def timed(fn, reps=5):
+        fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    def local_hop():
+        _lib.check(lib.srg_spmm_csr_f32(_p(norm.indptr), _p(norm.indices), _p(norm.data), st.n_local, norm.nnz_bound,
+                                        _p(xin), st.ld, _p(out), st.ld, st.f_loc, s))
+
+    res = {"hop_local_only_ms": timed(local_hop)}
+    if st.p2p:
+        dests = (C.c_void_p * len(st.peers))(*st.peer_ptrs[1])
+
+        def exchange():
+            _lib.check(lib.srg_push_rows_f32(_p(out), st.n_local, st.ld, dests, len(st.peers), st.row0, s))
+        res["exchange_only_ms"] = timed(exchange)
+        res["exchange_GBps_out"] = (len(st.peers) - 1) * st.n_local * st.ld * 4 / res["exchange_only_ms"] / 1e6
+    else:
+        res["exchange_only_ms"] = 0.0
+    return res
 
 
 def _verify_device_generated(st, a_loc, x_loc, k, f, sdist, synth, torch, dist):
@@ -199,7 +265,7 @@ def _e2e(args, st, a_loc_host, x_loc_host, k, f_loc, lib, dev, sdist, torch, dis
 
 
 def _emit_line(args, st, metric, unit, emit, mode, pf, world, rank, n, nnz_hat, f, f_loc, k, t_step, launches, e2e_line,
-               clocks, verify, gen):
+               clocks, verify, gen, probe=None):
     if rank == 0:
         from bench import comp_bytes, gather_bytes, measured_peak, workload_config
         peak, peak_src = measured_peak()
@@ -225,6 +291,10 @@ def _emit_line(args, st, metric, unit, emit, mode, pf, world, rank, n, nnz_hat, 
                  "h2d_bytes_per_step": e2e_line["h2d"], "d2h_bytes_per_step": e2e_line["d2h"],
                  "note": "per-rank bytes; max over ranks time"},
                 "gpu_launches": int(launches), "clocks": clocks}
+        if probe is not None:
+            probe["note"] = ("rank 0: hop with the exchange fused (max over ranks), the same hop writing locally only, the "
+                             "exchange alone (all ranks pushing at once); overlap_efficiency = max(local, exchange) / fused")
+            line["overlap"] = probe
         if verify is not None:
             line["verify"] = verify
             line["data"] = "synthetic (device-generated shards; no host copy exists, so no host end-to-end leg)"

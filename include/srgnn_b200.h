@@ -282,6 +282,30 @@ int srg_spmm_csr_f32_push(const int32_t *indptr, const int32_t *indices, const f
  * destination buffer (own + peers) */
 int srg_push_rows_f32(const float *src, int64_t n_rows, int64_t ld, float *const *dests,
                       int32_t n_dests, int64_t dest_row0, void *stream);
+/* ---- e (7): native multi-GPU handle — row partition + one NCCL all-gather per hop -------
+ * The reference has no multi-GPU code.  One process per GPU; rank p owns rows [p * rows_per, (p + 1) * rows_per)
+ * with rows_per = ceil(n / world); the degree vector is all-gathered once for the normalisation
+ * (SSRG/operators/utils.py:81-93 applied to the local rows), every hop is an all-gather of the previous hop's
+ * slices followed by the local SpMM (SSRG/operators/base_operator.py:31-36).  Bitwise equal to 1 GPU.
+ * NCCL is bound at run time (dlopen libnccl.so.2); SRG_ERR_UNSUPPORTED when it cannot be loaded.
+ *   srg_dist_unique_id   rank 0: ncclGetUniqueId into 128 bytes, to be handed to every rank by the caller
+ *   srg_dist_init        collective: ncclCommInitRank + the two full n_pad x ld feature buffers (ld = roundup(F, 8))
+ *   srg_dist_init_comm   the same around an existing ncclComm_t (not destroyed by srg_dist_destroy)
+ *   srg_dist_partition   this rank's row0 / n_local / rows_per / ld
+ *   srg_dist_propagate   indptr / indices / data: the rank's rows of the RAW adjacency (device, global column
+ *                        ids, symmetric overall — the caller's promise, the mirror rows live elsewhere);
+ *                        x_local: device n_local x ld_x; out_hops: NULL or a HOST array of K + 1 device pointers
+ *                        (n_local x ld_out each, NULL entries skipped; [0] receives the input);
+ *                        flags: device int32 (caller zeroes it), SRG_FLAG_*.  Stream-ordered, no host sync. */
+int srg_dist_unique_id(void *id128);
+int srg_dist_init(const void *id128, int32_t world, int32_t rank, int64_t n, int32_t F, void **out_handle);
+int srg_dist_init_comm(void *nccl_comm, int32_t world, int32_t rank, int64_t n, int32_t F, void **out_handle);
+int srg_dist_partition(const void *handle, int64_t *row0, int64_t *n_local, int64_t *rows_per, int64_t *ld);
+int srg_dist_propagate(void *handle, const int32_t *indptr, const int32_t *indices, const void *data,
+                       int val_dtype, int64_t nnz, const float *x_local, int64_t ld_x, int32_t K, double r,
+                       double ppr_alpha, float *const *out_hops, int64_t ld_out, int32_t *flags, void *stream);
+int srg_dist_destroy(void *handle);
+
 /* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on `stream`: copy-engine transfer between local and
  * peer-mapped buffers (the per-hop exchange of the "copy" multi-GPU mode). */
 int srg_copy_async(void *dst, const void *src, int64_t bytes, void *stream);

@@ -77,6 +77,13 @@ SIGNATURES = {
     "srg_spmm_csr_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
     "srg_spmm_csr_f32_push": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, C.POINTER(_vp), _i32, _i64, _i64, _i32, _vp]),
     "srg_push_rows_f32": (C.c_int, [_vp, _i64, _i64, C.POINTER(_vp), _i32, _i64, _vp]),
+    "srg_dist_unique_id": (C.c_int, [_vp]),
+    "srg_dist_init": (C.c_int, [_vp, _i32, _i32, _i64, _i32, C.POINTER(_vp)]),
+    "srg_dist_init_comm": (C.c_int, [_vp, _i32, _i32, _i64, _i32, C.POINTER(_vp)]),
+    "srg_dist_partition": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "srg_dist_propagate": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _i64, _vp, _i64, _i32, _f64, _f64, C.POINTER(_vp), _i64,
+                                     _vp, _vp]),
+    "srg_dist_destroy": (C.c_int, [_vp]),
     "srg_copy_async": (C.c_int, [_vp, _vp, _i64, _vp]),
     "srg_ipc_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
     "srg_ipc_free": (C.c_int, [_vp]),

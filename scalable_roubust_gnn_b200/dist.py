@@ -383,3 +383,54 @@ def dist_sym_norm(st: DistState, a_local, r, ppr_alpha=None):
     _lib.check(lib.srg_norm_values_rows_csr(_p(at_indptr), _p(at_indices), _p(at_val), _p(deg_loc), n_loc, nnz + n_loc,
                                             st.row0, st.n_pad, _p(dl), _p(dr), alpha, 0, None, _p(val32), _p(flags), s))
     return DeviceCSR(at_indptr, at_indices, val32, n_loc, nnz + n_loc), flags
+
+
+# ------------------------------------------------------------------------------------------------
+# native handle (csrc/dist.cu): the all-gather scheme without torch.distributed
+# ------------------------------------------------------------------------------------------------
+def native_unique_id() -> bytes:
+    """128-byte NCCL unique id (rank 0 creates it, the caller hands it to every rank)."""
+    from . import _lib
+    buf = (C.c_ubyte * 128)()
+    _lib.check(_lib.load().srg_dist_unique_id(buf))
+    return bytes(buf)
+
+
+class NativeDist:
+    """``srg_dist_init`` / ``srg_dist_propagate``: NCCL communicator, partition and the two full
+    feature buffers live in libsrgnn_b200.so; one call = sharded normalisation (one degree all-gather) + K hops with
+    one ``ncclAllGather`` each.  torch only provides the device tensors and the stream."""
+
+    def __init__(self, unique_id: bytes, world: int, rank: int, n: int, f: int):
+        from . import _lib
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.world, self.rank, self.n, self.f = world, rank, n, f
+        self._h = C.c_void_p()
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        _lib.check(self.lib.srg_dist_init(idbuf, world, rank, n, f, C.byref(self._h)))
+        row0, n_local, rows_per, ld = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self.lib.srg_dist_partition(self._h, C.byref(row0), C.byref(n_local), C.byref(rows_per), C.byref(ld)))
+        self.row0, self.n_local, self.rows_per, self.ld = row0.value, n_local.value, rows_per.value, ld.value
+
+    def propagate(self, a_local, x_local, k, r=0.5, ppr_alpha=None):
+        """``a_local``: DeviceCSR of this rank's rows of the raw adjacency (global column ids); ``x_local``: cuda
+        float32 n_local x F.  Returns (list of K+1 cuda tensors n_local x F, flags tensor)."""
+        import torch
+
+        from .device import _p, _stream_ptr
+        dev = x_local.device
+        x_local = x_local.contiguous()
+        outs = [torch.empty((self.n_local, self.f), dtype=torch.float32, device=dev) for _ in range(k + 1)]
+        ptrs = (C.c_void_p * (k + 1))(*[o.data_ptr() for o in outs])
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        alpha = -1.0 if ppr_alpha is None else float(ppr_alpha)
+        self._lib.check(self.lib.srg_dist_propagate(self._h, _p(a_local.indptr), _p(a_local.indices), _p(a_local.data),
+                                                    a_local.val_dtype, a_local.nnz, _p(x_local), x_local.stride(0), int(k),
+                                                    float(r), alpha, ptrs, self.f, _p(flags), _stream_ptr(dev)))
+        return outs, flags
+
+    def close(self):
+        if self._h:
+            self.lib.srg_dist_destroy(self._h)
+            self._h = C.c_void_p()

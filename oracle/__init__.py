@@ -16,6 +16,7 @@ What it restates (file:line in /root/reference, SSRG = "Scalable Spectral Robust
                     call sites wavelet/src/utils.py:83,95,131-133 and
                     SSRG/models/base_scalable/base_model.py:184-189,243  -- PARITY UNPINNED
   two_dir_norm      SSRG/operators/utils.py:195-260
+  fast_ppr_norm / two_order_ppr_norm   SSRG/operators/utils.py:262-335, :337-424 (device paths not built yet)
   mag_norm / com_propagate  SSRG/operators/utils.py:95-138, SSRG/operators/base_operator.py:152-208, :316-345
   spectral_preprocess  SSRG/models/base_scalable/base_model.py:180-221 (on top of cheby_*: PARITY UNPINNED)
   nafs_combine      SSRG/operators/message_operator/over_smooth_distance_op.py:11-33
@@ -248,6 +249,110 @@ def two_dir_norm(adj, r):
         vals, _ = norm(rr, cc, lmat[rr, cc])
         res.append(sp.csr_matrix((vals, (rr, cc)), shape=(n, n)))
     return un, res[0], res[1]
+
+
+def _f32_sym_scale(rows, cols, vals, n, r):
+    """float32 `D^(r-1) L D^(-r)` with D = scatter_add row sums in stored order and inf -> 0
+    (the block repeated at SSRG/operators/utils.py:204-210, :229-237, :324-332, :392-400, :413-421)."""
+    f32 = np.float32
+    vals = np.asarray(vals, dtype=f32)
+    deg = np.zeros(n, dtype=f32)
+    np.add.at(deg, rows, vals)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dl = np.power(deg, f32(r - 1), dtype=f32)
+        dr = np.power(deg, f32(-r), dtype=f32)
+    dl[np.isinf(dl)] = 0
+    dr[np.isinf(dr)] = 0
+    return (dl[rows] * vals * dr[cols]).astype(f32)
+
+
+def _loops_appended(adj):
+    """(row, col) of the adjacency pattern with one (i, i) entry appended per node (add_self_loops)."""
+    coo = sp.coo_matrix(adj)
+    n = coo.shape[0]
+    return (np.concatenate([coo.row, np.arange(n)]).astype(np.int64),
+            np.concatenate([coo.col, np.arange(n)]).astype(np.int64), n)
+
+
+def fast_ppr_norm(adj, r, ppr_alpha, max_iter=100, tol=1e-6):
+    """adj_to_fast_ppr_approx_symmetric_norm (SSRG/operators/utils.py:262-335): stationary distribution of the
+    teleporting walk by fixed-point iteration (fp64, :278-296), L = (Pi^1/2 P Pi^-1/2 + Pi^-1/2 P^T Pi^1/2) / 2
+    (:297-301), values cast to float32 and degree-normalised (:304-334)."""
+    row, col, n = _loops_appended(adj)
+    a1 = sp.csr_matrix((np.ones(len(row)), (row, col)), shape=(n, n))            # duplicates (old loops) summed
+    deg = np.asarray(a1.sum(axis=1)).reshape(-1)
+    nz = deg.nonzero()[0]
+    d_inv = sp.csr_matrix((1 / deg[nz], (nz, nz)), shape=(n, n))
+    s = np.full((n, 1), 1 / (1 + ppr_alpha) / n)
+    z = ((ppr_alpha * (1 + ppr_alpha)) * (deg != 0)
+         + ((1 - ppr_alpha) / (1 + ppr_alpha) + ppr_alpha * (1 + ppr_alpha)) * (deg == 0))[None, :]
+    w = (1 - ppr_alpha) * a1.T @ d_inv
+    x, old, it = s, np.zeros((n, 1)), 0
+    while np.sqrt(((x - old) ** 2).sum()) > tol:
+        old = x
+        x = w @ x + s @ (z @ x)
+        it += 1
+        if it >= max_iter:
+            break
+    pi = (x / x.sum()).reshape(-1)
+    p = d_inv @ a1
+    with np.errstate(divide="ignore", invalid="ignore"):
+        half, inv_half = sp.diags(np.power(pi, 0.5)), sp.diags(np.power(pi, -0.5))
+        lap = ((half @ p @ inv_half + inv_half @ p.T @ half) / 2.0).tocsr()
+    lap.data[np.isnan(lap.data)] = 0.0
+    lap = lap.tocoo()
+    vals = _f32_sym_scale(lap.row.astype(np.int64), lap.col.astype(np.int64), lap.data.astype(np.float32), n, r)
+    out = sp.csr_matrix((vals, (lap.row, lap.col)), shape=(n, n))
+    out.sort_indices()
+    return out
+
+
+def two_order_ppr_norm(adj, r, ppr_alpha):
+    """adj_to_slow_first_second_ppr_approx_symmetric_norm (SSRG/operators/utils.py:337-424), dense as there:
+    P = D^-1 (A + I) in float32 (:345-352), stationary vector = left eigenvector of the (N+1) x (N+1) teleport
+    matrix by LAPACK (:353-369), first-order L from pi (:374-386), second-order L from P^T P and P P^T masked by each
+    other (:402-411), both degree-normalised in float32.  Returns (one_order, two_order) float32 CSR."""
+    import scipy.linalg
+    f32 = np.float32
+    row, col, n = _loops_appended(adj)
+    deg = np.zeros(n, dtype=f32)
+    np.add.at(deg, row, f32(1))
+    with np.errstate(divide="ignore"):
+        dinv = np.power(deg, f32(-1), dtype=f32)
+    dinv[np.isinf(dinv)] = 0
+    p = np.zeros((n, n), dtype=f32)
+    np.add.at(p, (row, col), dinv[row])
+    pv = np.zeros((n + 1, n + 1), dtype=f32)
+    pv[:n, :n] = f32(1 - ppr_alpha) * p
+    pv[n, :n] = f32(1.0 / n)
+    pv[:n, n] = f32(ppr_alpha)
+    ev, left = scipy.linalg.eig(pv, left=True, right=False)
+    pi = left.real[:, np.argsort(-ev.real, kind="stable")[0]][:n]
+    pi = pi / pi.sum()
+    assert not (pi < 0).any()
+    pi = pi.astype(f32)                       # sgeev on the float32 matrix: everything below stays float32
+    with np.errstate(divide="ignore"):
+        inv_half = np.power(pi, f32(-0.5), dtype=f32)
+        half = np.power(pi, f32(0.5), dtype=f32)
+    inv_half[np.isinf(inv_half)] = 0
+    half[np.isinf(half)] = 0
+    one = ((np.diag(half) @ p) @ np.diag(inv_half) + (np.diag(inv_half) @ p.T) @ np.diag(half)) / f32(2.0)
+    one[np.isnan(one)] = 0
+
+    def finish(lmat):
+        rr, cc = np.nonzero(lmat)
+        vals = _f32_sym_scale(rr, cc, lmat[rr, cc].astype(f32), n, r)
+        m = sp.csr_matrix((vals, (rr, cc)), shape=(n, n))
+        m.sort_indices()
+        return m
+
+    l_in, l_out = p.T @ p, p @ p.T
+    m_in, m_out = l_in == 0, l_out == 0       # the reference masks in place: L_in by (L_out == 0), then L_out by the
+    l_in[m_out] = 0                           # ALREADY MASKED L_in == 0 (:405-406, same arrays)
+    l_out[l_in == 0] = 0
+    two = (l_in + l_out) / f32(2.0)
+    two[np.isnan(two)] = 0
+    return finish(one), finish(two)
 
 
 def com_propagate(real_adj, imag_adj, feature, prop_steps, lib="oracle"):

@@ -15,6 +15,9 @@ reference's own classes imported from /root/reference, run on small inputs, outp
              directed graphs.  torch_sparse.coalesce / torch_scatter.scatter_add are absent from this image:
              the script supplies pure-torch stand-ins with their documented semantics (sum of equal keys in
              stored order, output sorted by key / sequential scatter sum) — everything else is reference code.
+  * twodir_* TwoDirLaplacianGraphOp (in_out_directed_laplacian_operator.py, utils.py:195-260), add_self_loops stand-in
+  * fastppr_* / twoorder_*  SymDirFastPprApproxGraphOp, SymDirTwoOrderPprApproxGraphOp (utils.py:262-424): fixtures for
+             the oracle restatement; the device implementations are not built yet
 """
 import os
 import sys
@@ -146,6 +149,28 @@ def main():
         for nm, m, hops in zip(("un", "in", "out"), (op.un_adj, op.in_adj, op.out_adj), lists):
             csr_pack(f"{tag}_{nm}", m, out)
             out[f"{tag}_{nm}_hops"] = np.stack([t.numpy() for t in hops])
+
+    # ---- the two PPR-approximation operators of directed graphs (oracle pinned now, device path next round) -----
+    import scipy
+    if not hasattr(scipy, "newaxis"):
+        scipy.newaxis = None            # utils.py:283 uses the alias of numpy.newaxis that newer scipy removed
+    from operators.graph_operator.symmetrical_directed_fast_ppr_approximate_operator import SymDirFastPprApproxGraphOp
+    from operators.graph_operator.symmetrical_directed_two_order_ppr_approximate_operator import \
+        SymDirTwoOrderPprApproxGraphOp
+    a = digraph(60, 300)
+    xm = rg.random((60, 4), dtype=np.float32)
+    csr_pack("ppr_adj", a, out)
+    out["ppr_x"] = xm
+    op = SymDirFastPprApproxGraphOp(2, r=0.5, ppr_alpha=0.1)
+    hops = op.propagate(a, xm)
+    csr_pack("fastppr_norm", op.adj, out)
+    out["fastppr_hops"] = np.stack([t.numpy() for t in hops])
+    op = SymDirTwoOrderPprApproxGraphOp(2, r=0.5, ppr_alpha=0.1)
+    h1, h2 = op.propagate(a, xm)
+    csr_pack("twoorder_one", op.one_adj, out)
+    csr_pack("twoorder_two", op.two_adj, out)
+    out["twoorder_one_hops"] = np.stack([t.numpy() for t in h1])
+    out["twoorder_two_hops"] = np.stack([t.numpy() for t in h2])
 
     np.savez_compressed(os.path.join(HERE, "reference_ext.npz"), **out)
     print("wrote", sorted(out))

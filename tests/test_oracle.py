@@ -163,3 +163,30 @@ def test_nafs_combine_matches_reference_golden():
     hops, _ = oracle.propagate(sym_graph(300, 1500, 2), x, 3, r=0.5)
     np.testing.assert_array_equal(hops[3], g["nafs_hop3"])
     np.testing.assert_allclose(oracle.nafs_combine(hops), g["nafs_out"], rtol=1e-5, atol=1e-6)
+
+
+# ---- the two PPR-approximation normalisers of directed graphs: oracle pinned, device path not built yet -----------
+def _csr_close(got, want, rtol=2e-6):
+    got = got.tocsr()
+    got.sort_indices()
+    np.testing.assert_array_equal(got.indptr, want.indptr)
+    np.testing.assert_array_equal(got.indices, want.indices)
+    np.testing.assert_allclose(got.data, want.data, rtol=rtol, atol=1e-9)
+
+
+def test_ppr_approx_normalisers_match_reference_golden():
+    g = np.load(os.path.join(GOLDEN_DIR, "reference_ext.npz"))
+    a = golden_csr(g, "ppr_adj")
+    x = g["ppr_x"]
+    _csr_close(oracle.fast_ppr_norm(a, 0.5, 0.1), golden_csr(g, "fastppr_norm"))
+    one, two = oracle.two_order_ppr_norm(a, 0.5, 0.1)
+    _csr_close(one, golden_csr(g, "twoorder_one"))
+    _csr_close(two, golden_csr(g, "twoorder_two"))
+    # the hop chains on the reference's own matrices are the pinned FMA chain: bit-exact
+    for adj_key, hops_key in (("fastppr_norm", "fastppr_hops"), ("twoorder_one", "twoorder_one_hops"),
+                              ("twoorder_two", "twoorder_two_hops")):
+        m = golden_csr(g, adj_key)
+        cur = x
+        for k in range(1, 3):
+            cur = oracle.spmm_hop(m, cur)
+            np.testing.assert_array_equal(cur, g[hops_key][k])

@@ -140,7 +140,7 @@ def test_spgemm_matches_scipy_pattern_and_values(a, seed):
     want.sort_indices()
     np.testing.assert_array_equal(got.indptr, want.indptr)
     np.testing.assert_array_equal(got.indices, want.indices)
-    np.testing.assert_allclose(got.data, want.data, rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(got.data, want.data, rtol=2e-5, atol=5e-6)      # signed terms may nearly cancel
 
 
 @st.composite

@@ -168,7 +168,7 @@ def test_magnetic_norm_matches_oracle_on_arbitrary_digraphs(case, ppr):
     for got, want in ((got_re, want_re), (got_im, want_im)):
         assert_same_structure(got, want)
         if want.nnz:
-            np.testing.assert_allclose(got.data, want.data, rtol=4e-15, atol=1e-15)
+            np.testing.assert_allclose(got.data, want.data, rtol=1e-14, atol=1e-15)   # pow / sincos: an ulp or two per factor
 
 
 @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))

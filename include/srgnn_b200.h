@@ -413,6 +413,13 @@ int srg_propagate_aggregate_host(const int32_t *indptr, const int32_t *indices, 
                                  int32_t agg_end, const float *agg_weights, float *out_agg,
                                  int device);
 
+/* Host utility: 1 when every stored value of a host array is exactly 1 (or val_dtype is SRG_VAL_ONES), else 0;
+ * `threads` worker threads scan it.  scipy holds an unweighted adjacency as float64 ones (`A.data`, what
+ * SSRG/operators/utils.py:82 receives); with SRG_ONES_SHORTCUT=1 in the environment srg_propagate_host starts
+ * without uploading that array while this check runs in the shadow of the transfers, and falls back to the
+ * regular path when the check fails.  Off by default. */
+int srg_host_all_ones(const void *data, int val_dtype, int64_t nnz, int32_t threads);
+
 /* layout helpers: host layout (ld == F) <-> padded device layout (ld % 8 == 0, pad = 0).
  * mask (optional, int32 n x F, SSRG/data_process.py:38-39) is applied as x * mask
  * (SSRG/data_augument.py:28) while repacking. */

@@ -52,6 +52,7 @@ SIGNATURES = {
     "srg_last_error": (C.c_char_p, []),
     "srg_device_count": (C.c_int, []),
     "srg_launch_count": (_i64, []),
+    "srg_host_all_ones": (C.c_int, [_vp, C.c_int, _i64, _i32]),
     "srg_set_tuning": (C.c_int, [C.c_char_p, _i64]),
     "srg_degree_selfloop_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp]),
     "srg_sym_norm_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),

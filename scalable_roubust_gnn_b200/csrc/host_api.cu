@@ -11,8 +11,11 @@
 //   copy-out stream: after hop k: unpack to the host layout and D2H, overlapping hop k+1
 // Device memory comes from the stream-ordered pool (cudaMallocAsync) whose release threshold is
 // raised so repeated calls reuse the same blocks.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -222,6 +225,77 @@ static bool next_attempt(int flags, int *mode) {
   return true;
 }
 
+// ---- "is the adjacency unweighted?" on the host --------------------------------------------------------------
+// scipy hands A.data as float64 even when every stored value is 1.0 (the usual unweighted graph): 8 bytes per
+// entry of PCIe traffic that carry no information (products shape: 495 MB of the 1.73 GB upload).  With
+// SRG_ONES_SHORTCUT=1 the host pipeline starts WITHOUT uploading the values (val_dtype ONES) while worker threads
+// verify, in the shadow of the transfers, that the array really is all ones; if not, the result is discarded and
+// the regular path runs.  The device arithmetic is identical either way (the kernels detect weightedness at run
+// time and use exact integer degrees for all-ones input).
+template <typename T>
+static bool range_all_ones(const T *p, int64_t lo, int64_t hi, const std::atomic<int> &stop) {
+  const T one = (T)1;
+  for (int64_t i = lo; i < hi; i += 8192) {
+    if (stop.load(std::memory_order_relaxed)) return false;
+    const int64_t e = std::min<int64_t>(hi, i + 8192);
+    int bad = 0;
+    for (int64_t j = i; j < e; ++j) bad |= (p[j] != one);
+    if (bad) return false;
+  }
+  return true;
+}
+
+struct OnesProbe {
+  std::vector<std::thread> workers;
+  std::atomic<int> bad{0};
+  void start(const void *data, int val_dtype, int64_t nnz, int threads) {
+    threads = std::max(1, std::min(threads, 64));
+    const int64_t per = (nnz + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+      const int64_t lo = std::min<int64_t>(nnz, t * per), hi = std::min<int64_t>(nnz, lo + per);
+      if (lo >= hi) break;
+      workers.emplace_back([this, data, val_dtype, lo, hi] {
+        const bool ok = (val_dtype == SRG_VAL_F64) ? range_all_ones(static_cast<const double *>(data), lo, hi, bad)
+                                                   : range_all_ones(static_cast<const float *>(data), lo, hi, bad);
+        if (!ok) bad.store(1, std::memory_order_relaxed);
+      });
+    }
+  }
+  bool finish() {
+    for (auto &w : workers) w.join();
+    workers.clear();
+    return bad.load() == 0;
+  }
+  ~OnesProbe() { finish(); }
+};
+
+// cheap pre-filter: the first entries and a strided sample
+static bool sampled_all_ones(const void *data, int val_dtype, int64_t nnz) {
+  std::atomic<int> never{0};
+  const int64_t head = std::min<int64_t>(nnz, 4096);
+  const bool f64 = val_dtype == SRG_VAL_F64;
+  if (f64 ? !range_all_ones(static_cast<const double *>(data), 0, head, never)
+          : !range_all_ones(static_cast<const float *>(data), 0, head, never))
+    return false;
+  const int64_t stride = std::max<int64_t>(1, nnz / 4096);
+  for (int64_t i = 0; i < nnz; i += stride)
+    if (f64 ? static_cast<const double *>(data)[i] != 1.0 : static_cast<const float *>(data)[i] != 1.0f) return false;
+  return true;
+}
+
+static bool ones_shortcut_enabled() {
+  static const int v = [] {
+    const char *e = getenv("SRG_ONES_SHORTCUT");
+    return e ? atoi(e) : 0;
+  }();
+  return v != 0;
+}
+
+static bool ones_shortcut_applies(const void *data, int val_dtype, int64_t nnz) {
+  return ones_shortcut_enabled() && data && (val_dtype == SRG_VAL_F64 || val_dtype == SRG_VAL_F32) && nnz >= (1 << 20) &&
+         sampled_all_ones(data, val_dtype, nnz);
+}
+
 }  // namespace srg
 
 using namespace srg;
@@ -237,6 +311,15 @@ extern "C" int srg_device_count(void) {
   return n;
 }
 extern "C" int64_t srg_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int srg_host_all_ones(const void *data, int val_dtype, int64_t nnz, int32_t threads) {
+  SRG_REQUIRE(val_dtype >= 0 && val_dtype <= 2 && nnz >= 0, "host_all_ones: bad arguments");
+  if (val_dtype == SRG_VAL_ONES || nnz == 0) return 1;
+  SRG_REQUIRE(data != nullptr, "host_all_ones: data is NULL");
+  OnesProbe probe;
+  probe.start(data, val_dtype, nnz, threads);
+  return probe.finish() ? 1 : 0;
+}
 
 extern "C" int srg_release_workspace(void) {
   std::lock_guard<std::mutex> lk(g_state_mu);
@@ -514,16 +597,25 @@ extern "C" int srg_propagate_host(const int32_t *indptr, const int32_t *indices,
                                   double ppr_alpha, float *const *out_hops,
                                   int32_t *out_norm_indptr, int32_t *out_norm_indices,
                                   double *out_norm_data, int64_t *out_nnz, int device) {
-  int mode = 0;
-  for (;;) {
-    int flags = 0;
-    int rc = propagate_attempt(indptr, indices, data, val_dtype, n, nnz, features, F, feature_mask, K, r, ppr_alpha,
-                               out_hops, out_norm_indptr, out_norm_indices, out_norm_data, out_nnz, device, mode,
-                               &flags);
-    if (rc) return rc;
-    if (!flags) return SRG_OK;
-    if (!next_attempt(flags, &mode)) return check_flags(flags);
+  auto run = [&](const void *vals, int vt) -> int {
+    int mode = 0;
+    for (;;) {
+      int flags = 0;
+      int rc = propagate_attempt(indptr, indices, vals, vt, n, nnz, features, F, feature_mask, K, r, ppr_alpha,
+                                 out_hops, out_norm_indptr, out_norm_indices, out_norm_data, out_nnz, device, mode,
+                                 &flags);
+      if (rc) return rc;
+      if (!flags) return SRG_OK;
+      if (!next_attempt(flags, &mode)) return check_flags(flags);
+    }
+  };
+  if (ones_shortcut_applies(data, val_dtype, nnz)) {
+    OnesProbe probe;
+    probe.start(data, val_dtype, nnz, 8);
+    const int rc = run(nullptr, SRG_VAL_ONES);
+    if (probe.finish()) return rc;   // really unweighted: the result (or the error) stands
   }
+  return run(data, val_dtype);
 }
 
 extern "C" int srg_propagate_aggregate_host(const int32_t *indptr, const int32_t *indices, const void *data,
@@ -556,15 +648,24 @@ extern "C" int srg_propagate_aggregate_host(const int32_t *indptr, const int32_t
   agg.end = agg_end;
   agg.weights = agg_weights;
   agg.out = out_agg;
-  int mode = 0;
-  for (;;) {
-    int flags = 0;
-    int rc = propagate_attempt(indptr, indices, data, val_dtype, n, nnz, features, F, feature_mask, K, r, ppr_alpha,
-                               nullptr, nullptr, nullptr, nullptr, nullptr, device, mode, &flags, &agg);
-    if (rc) return rc;
-    if (!flags) return SRG_OK;
-    if (!next_attempt(flags, &mode)) return check_flags(flags);
+  auto run = [&](const void *vals, int vt) -> int {
+    int mode = 0;
+    for (;;) {
+      int flags = 0;
+      int rc = propagate_attempt(indptr, indices, vals, vt, n, nnz, features, F, feature_mask, K, r, ppr_alpha,
+                                 nullptr, nullptr, nullptr, nullptr, nullptr, device, mode, &flags, &agg);
+      if (rc) return rc;
+      if (!flags) return SRG_OK;
+      if (!next_attempt(flags, &mode)) return check_flags(flags);
+    }
+  };
+  if (ones_shortcut_applies(data, val_dtype, nnz)) {
+    OnesProbe probe;
+    probe.start(data, val_dtype, nnz, 8);
+    const int rc = run(nullptr, SRG_VAL_ONES);
+    if (probe.finish()) return rc;
   }
+  return run(data, val_dtype);
 }
 
 // ---- literal reference ABI ------------------------------------------------------------------------

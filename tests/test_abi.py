@@ -85,3 +85,22 @@ def test_argument_validation_matches_reference_messages():
         PprGraphOp(2).construct_adj(sp.identity(4, format="csc"))
     assert SymLaplacianGraphOp(None).prop_steps is None       # gcn.py:8 builds the op without steps
     assert PprGraphOp(3).alpha == 0.15 and PprGraphOp(3).r == 0.5 and SymLaplacianGraphOp(3).r == 0.5
+
+
+def test_host_all_ones_check():
+    """Host utility of the (opt-in) unweighted-adjacency shortcut: multithreaded scan for values != 1."""
+    lib = _lib.load()
+    for dt, vt in ((np.float64, _lib.SRG_VAL_F64), (np.float32, _lib.SRG_VAL_F32)):
+        a = np.ones(300_001, dtype=dt)
+        assert lib.srg_host_all_ones(a.ctypes.data, vt, a.size, 8) == 1
+        assert lib.srg_host_all_ones(a.ctypes.data, vt, 0, 8) == 1
+        for pos in (0, 4095, 4096, a.size // 2, a.size - 1):
+            b = a.copy()
+            b[pos] = np.nextafter(dt(1), dt(2))
+            for threads in (1, 3, 8):
+                assert lib.srg_host_all_ones(b.ctypes.data, vt, b.size, threads) == 0, (pos, threads)
+        z = a.copy()
+        z[7] = 0                                   # an explicit zero is not "unweighted" either
+        assert lib.srg_host_all_ones(z.ctypes.data, vt, z.size, 4) == 0
+    assert lib.srg_host_all_ones(None, _lib.SRG_VAL_ONES, 10, 4) == 1
+    assert lib.srg_host_all_ones(None, _lib.SRG_VAL_F64, 10, 4) == _lib.SRG_ERR_INVALID

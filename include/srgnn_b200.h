@@ -198,6 +198,21 @@ int srg_csr_append_diagonal(const int32_t *indptr, const int32_t *indices, int64
 int srg_csr_sym_scale_f32(const int32_t *indptr, const int32_t *indices, const float *vals, int64_t n, float r,
                           float *out_vals, float *out_degree, void *stream);
 
+/* ---- 8f-2: fast PPR-approximation normaliser of a directed graph (SSRG/operators/utils.py:262-335) ---------
+ * Device stages; the host loop (convergence test, <= 100 sweeps) and the float32 degree normalisation
+ * (srg_csr_sym_scale_f32) are driven by the caller (operators/utils.py:adj_to_fast_ppr_approx_symmetric_norm).
+ *   srg_ppr_iterate_f64  y = (1 - a) A1^T (x / r) + s (z . x) over the CSR of A1^T (float32 duplicate counts), fp64;
+ *                        stats3 (device, 3 doubles) = { z . x, |y - x|^2, sum(y) }               (utils.py:284-293)
+ *   srg_ppr_symmetrize   L = (Pi^1/2 P Pi^-1/2 + Pi^-1/2 P^T Pi^1/2) / 2 with pi = x / stats3[2], P = D1 A1, NaN -> 0,
+ *                        values rounded to float32; outputs: sorted CSR, capacity 2 nnz              (utils.py:297-309)
+ * Not yet validated on hardware (round 1): exercised by an opt-in test only. */
+int srg_ppr_iterate_f64(const int32_t *t_indptr, const int32_t *t_indices, const float *t_counts,
+                        const double *degree, int64_t n, double ppr_alpha, const double *x, double *y,
+                        double *stats3, void *stream);
+int srg_ppr_symmetrize(const int32_t *indptr, const int32_t *indices, const float *counts, const double *degree,
+                       const double *x, const double *stats3, int64_t n, int64_t nnz, int32_t *out_indptr,
+                       int32_t *out_indices, float *out_vals, void *stream);
+
 /* ---- synthetic inputs of the named shapes, generated on the device --------------------
  * Not a reference interface: BASELINE.json's configs 4 (power-law variant) and 5 are synthetic R-MAT
  * graphs too large to build on the host per rank.  Rows [row0, row1) of the symmetrised, duplicate-free,

@@ -24,7 +24,7 @@ import torch
 from .. import _lib
 
 __all__ = ["csr_sparse_dense_matmul", "adj_to_symmetric_norm", "propagate_host", "propagate_aggregate_host",
-           "csr_host_parts", "adj_to_directed_symmetric_mag_norm", "adj_to_un_in_out_dir_symmetric_norm", "DeviceHopRunner"]
+           "csr_host_parts", "adj_to_directed_symmetric_mag_norm", "adj_to_un_in_out_dir_symmetric_norm", "adj_to_fast_ppr_approx_symmetric_norm", "DeviceHopRunner"]
 
 
 def _ptr(a):
@@ -289,6 +289,78 @@ def adj_to_un_in_out_dir_symmetric_norm(adj, r, device=0):
         in_n = csr_sym_scale(in_l, float(r))                        # :229-237
         out_n = csr_sym_scale(out_l, float(r))                      # :249-257
         return csr_to_scipy(un), csr_to_scipy(in_n), csr_to_scipy(out_n)
+
+
+def _pattern_plus_loops(lib, csr, dev, stream):
+    """DeviceCSR of the adjacency pattern with one loop appended per node, rows sorted, duplicates summed into
+    float32 counts (add_self_loops + the duplicate sum of the sparse constructor, utils.py:264-271)."""
+    from .. import device as sdev
+    indptr, indices, _, _, n, nnz = csr_host_parts(csr)
+    d_indptr = torch.from_numpy(indptr).to(dev)
+    d_indices = torch.from_numpy(indices).to(dev) if nnz else torch.zeros(1, dtype=torch.int32, device=dev)
+    cap = nnz + n
+    l_indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    l_indices = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    _lib.check(lib.srg_csr_append_diagonal(_ptr(d_indptr), _ptr(d_indices), n, _ptr(l_indptr), _ptr(l_indices), stream))
+    c_indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    c_indices = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    c_vals = torch.empty(max(cap, 1), dtype=torch.float64, device=dev)
+    c_nnz = torch.zeros(1, dtype=torch.int32, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(lib.srg_csr_canonicalize(_ptr(l_indptr), _ptr(l_indices), None, _lib.SRG_VAL_ONES, n, cap,
+                                        _ptr(c_indptr), _ptr(c_indices), _ptr(c_vals), _ptr(c_nnz), _ptr(flags), stream))
+    if int(flags.item()) & _lib.SRG_FLAG_BAD_INDEX:
+        raise _lib.SrgError(_lib.SRG_ERR_INVALID, "column index out of range")
+    m = int(c_nnz.item())
+    return sdev.DeviceCSR(c_indptr, c_indices[:max(m, 1)], c_vals[:max(m, 1)].to(torch.float32), n, m)
+
+
+def adj_to_fast_ppr_approx_symmetric_norm(adj, r, ppr_alpha, max_iter=100, device=0, tol=1e-6):
+    """Fast PPR-approximation normaliser of a directed graph on the GPU (SSRG/operators/utils.py:262-335, the
+    normaliser of SymDirFastPprApproxGraphOp): stationary distribution of the teleporting walk by fixed-point sweeps
+    (fp64, same stopping rule: |x - x_old|_2 <= 1e-6 or ``max_iter`` sweeps), the symmetrised Laplacian
+    ``(Pi^1/2 P Pi^-1/2 + Pi^-1/2 P^T Pi^1/2) / 2`` and the float32 degree normalisation.  Returns a
+    ``scipy.sparse.csr_matrix`` with float32 data.  Round-1 status: not yet run on hardware (opt-in test)."""
+    from ..sparse_mm import csr_sym_scale, csr_to_scipy, csr_transpose
+    from ..device import DeviceCSR
+    lib = _lib.load()
+    if lib.srg_device_count() <= 0:
+        raise _lib.SrgError(_lib.SRG_ERR_NODEV, "no CUDA device visible: libsrgnn_b200 has no CPU fallback")
+    if not sp.issparse(adj):
+        raise TypeError("The adjacency matrix must be a scipy sparse matrix!")
+    csr = adj.tocsr() if not isinstance(adj, sp.csr_matrix) else adj
+    dev = torch.device("cuda", int(device))
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        a1 = _pattern_plus_loops(lib, csr, dev, stream)
+        n = a1.n
+        _, deg32 = csr_sym_scale(a1, 0.0, want_degree=True)           # row sums of the counts (exact small integers)
+        deg = deg32.to(torch.float64)
+        a1t = csr_transpose(a1)
+        x = torch.full((n,), 1.0 / (1.0 + ppr_alpha) / n, dtype=torch.float64, device=dev)
+        y = torch.empty_like(x)
+        stats = torch.zeros(3, dtype=torch.float64, device=dev)
+        err = float(np.sqrt(n) * (1.0 / (1.0 + ppr_alpha) / n))         # |s - 0|_2 of the first loop test
+        sweeps = 0
+        while err > tol:
+            _lib.check(lib.srg_ppr_iterate_f64(_ptr(a1t.indptr), _ptr(a1t.indices), _ptr(a1t.data), _ptr(deg), n,
+                                               float(ppr_alpha), _ptr(x), _ptr(y), _ptr(stats), stream))
+            x, y = y, x
+            err = float(np.sqrt(stats[1].item()))
+            sweeps += 1
+            if sweeps >= max_iter:
+                break
+        if sweeps == 0:                                                # tol above the start norm: pi = uniform
+            stats[2] = x.sum()
+        cap = max(2 * a1.nnz, 1)
+        o_indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        o_indices = torch.empty(cap, dtype=torch.int32, device=dev)
+        o_vals = torch.empty(cap, dtype=torch.float32, device=dev)
+        _lib.check(lib.srg_ppr_symmetrize(_ptr(a1.indptr), _ptr(a1.indices), _ptr(a1.data), _ptr(deg), _ptr(x), _ptr(stats),
+                                          n, a1.nnz, _ptr(o_indptr), _ptr(o_indices), _ptr(o_vals), stream))
+        m = int(o_indptr[-1].item())
+        lap = DeviceCSR(o_indptr, o_indices[:max(m, 1)], o_vals[:max(m, 1)], n, m)
+        return csr_to_scipy(csr_sym_scale(lap, float(r)))
 
 
 class DeviceHopRunner:

@@ -213,6 +213,20 @@ int srg_ppr_symmetrize(const int32_t *indptr, const int32_t *indices, const floa
                        const double *x, const double *stats3, int64_t n, int64_t nnz, int32_t *out_indptr,
                        int32_t *out_indices, float *out_vals, void *stream);
 
+/* Two-order PPR approximation (adj_to_slow_first_second_ppr_approx_symmetric_norm, SSRG/operators/utils.py:337-424):
+ *   srg_teleport_iterate_f64    one power-iteration sweep for the left eigenvector of the (n + 1) x (n + 1) teleport
+ *                               matrix [[(1 - a) P, a], [1/n, 0]] (the reference: dense LAPACK eig, :353-369) over the CSR
+ *                               of P^T; x, y: n + 1 doubles; stats3 = { sum_{i<n} x_i, |y - x|_1 over the first n, sum_{j<n} y_j }
+ *   srg_csr_intersect_mean_f32  (A + B) / 2 on the entries where both sorted float32 CSR operands are non-zero: the
+ *                               in-place masking L_in[L_out == 0] = 0, L_out[L_in == 0] = 0 and the mean of :405-410;
+ *                               out_indices / out_vals capacity a_nnz, out_indptr[n] = entries.
+ * Not yet validated on hardware (round 1): exercised by an opt-in test only. */
+int srg_teleport_iterate_f64(const int32_t *t_indptr, const int32_t *t_indices, const float *t_vals, int64_t n,
+                             double ppr_alpha, const double *x, double *y, double *stats3, void *stream);
+int srg_csr_intersect_mean_f32(const int32_t *a_indptr, const int32_t *a_indices, const float *a_vals,
+                               const int32_t *b_indptr, const int32_t *b_indices, const float *b_vals, int64_t n,
+                               int64_t a_nnz, int32_t *out_indptr, int32_t *out_indices, float *out_vals, void *stream);
+
 /* ---- synthetic inputs of the named shapes, generated on the device --------------------
  * Not a reference interface: BASELINE.json's configs 4 (power-law variant) and 5 are synthetic R-MAT
  * graphs too large to build on the host per rank.  Rows [row0, row1) of the symmetrised, duplicate-free,

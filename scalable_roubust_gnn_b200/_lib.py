@@ -70,6 +70,8 @@ SIGNATURES = {
     "srg_csr_sym_scale_f32": (C.c_int, [_vp, _vp, _vp, _i64, C.c_float, _vp, _vp, _vp]),
     "srg_ppr_iterate_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f64, _vp, _vp, _vp, _vp]),
     "srg_ppr_symmetrize": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "srg_teleport_iterate_f64": (C.c_int, [_vp, _vp, _vp, _i64, _f64, _vp, _vp, _vp, _vp]),
+    "srg_csr_intersect_mean_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "srg_synth_rmat_shard_csr": (C.c_int, [C.c_uint64, _i32, _i64, _f64, _f64, _f64, _i64, _i64, _i64, _i64, _vp, _vp,
                                            C.POINTER(_i64), _vp]),
     "srg_synth_hash_features_f32": (C.c_int, [C.c_uint64, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp]),

@@ -12,6 +12,8 @@
 // fp64 throughout; the sums run in a fixed (deterministic) order, not scipy's internal one, so the stationary
 // vector agrees to rounding (1e-15) and the final float32 values to float32 rounding.
 // HARDWARE STATUS: written after the round-1 GPU budget was spent; its test is opt-in (SRG_TEST_UNVALIDATED=1).
+#include <algorithm>
+
 #include "common.cuh"
 #include "scan.cuh"
 #include "sortutil.cuh"
@@ -158,9 +160,139 @@ __global__ void ppr_row_lower_bound_kernel(const uint64_t *__restrict__ keys, co
   indptr[r] = lo;
 }
 
+// ---- two-order PPR approximation (SSRG/operators/utils.py:337-424) ------------------------------------------------
+// left eigenvector of the (n + 1) x (n + 1) teleport matrix [[(1 - a) P, a], [1/n, 0]] (the reference calls LAPACK on
+// the dense float32 matrix, :353-369): one sweep of the power iteration over the CSR of P^T,
+//   y_j = (1 - a) sum_i P_ij x_i + x_n / n   (j < n),      y_n = a sum_{i<n} x_i
+__global__ void __launch_bounds__(256)
+teleport_sweep_kernel(const int *__restrict__ t_ptr, const int *__restrict__ t_idx, const float *__restrict__ t_val,
+                      const double *__restrict__ x, long long n, double one_minus_a, double a,
+                      const double *__restrict__ sum_x, double *__restrict__ y, double *__restrict__ part) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double d1 = 0.0, sy = 0.0;
+  if (j < n) {
+    double acc = 0.0;
+    for (int p = t_ptr[j]; p < t_ptr[j + 1]; ++p) acc = __dadd_rn(acc, __dmul_rn((double)t_val[p], x[t_idx[p]]));
+    const double yj = __dadd_rn(__dmul_rn(one_minus_a, acc), __ddiv_rn(x[n], (double)n));
+    y[j] = yj;
+    d1 = fabs(__dsub_rn(yj, x[j]));
+    sy = yj;
+  } else if (j == n) {
+    y[n] = __dmul_rn(a, sum_x[0]);
+  }
+  __shared__ double sh_d[256], sh_s[256];
+  sh_d[threadIdx.x] = d1;
+  sh_s[threadIdx.x] = sy;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sh_d[threadIdx.x] = __dadd_rn(sh_d[threadIdx.x], sh_d[threadIdx.x + o]);
+      sh_s[threadIdx.x] = __dadd_rn(sh_s[threadIdx.x], sh_s[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    part[2 * (long long)blockIdx.x] = sh_d[0];
+    part[2 * (long long)blockIdx.x + 1] = sh_s[0];
+  }
+}
+
+// L = (L_in + L_out) / 2 on the entries where BOTH are non-zero: the in-place masking of :405-410
+// (L_in[L_out == 0] = 0, then L_out[L_in == 0] = 0 on the already masked L_in).  Rows of both inputs are sorted.
+__global__ void intersect_count_kernel(const int *__restrict__ a_ptr, const int *__restrict__ a_idx,
+                                       const float *__restrict__ a_val, const int *__restrict__ b_ptr,
+                                       const int *__restrict__ b_idx, const float *__restrict__ b_val, long long n,
+                                       int *__restrict__ cnt, int *__restrict__ match) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
+  int c = 0;
+  const int b0 = b_ptr[i], b1 = b_ptr[i + 1];
+  for (int p = a_ptr[i] + lane; p < a_ptr[i + 1]; p += 32) {
+    const int col = a_idx[p];
+    int lo = b0, hi = b1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (b_idx[mid] < col) lo = mid + 1; else hi = mid;
+    }
+    const bool hit = lo < b1 && b_idx[lo] == col && a_val[p] != 0.f && b_val[lo] != 0.f;
+    match[p] = hit ? lo : -1;
+    c += hit ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) cnt[i] = c;
+}
+
+__global__ void intersect_fill_kernel(const int *__restrict__ a_ptr, const int *__restrict__ a_idx,
+                                      const float *__restrict__ a_val, const float *__restrict__ b_val,
+                                      const int *__restrict__ match, const int *__restrict__ out_ptr, long long n,
+                                      int *__restrict__ out_idx, float *__restrict__ out_val) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per row keeps the order
+  if (i >= n) return;
+  int w = out_ptr[i];
+  for (int p = a_ptr[i]; p < a_ptr[i + 1]; ++p) {
+    const int q = match[p];
+    if (q < 0) continue;
+    out_idx[w] = a_idx[p];
+    out_val[w] = __fdiv_rn(__fadd_rn(a_val[p], b_val[q]), 2.0f);
+    ++w;
+  }
+}
+
 }  // namespace srg
 
 using namespace srg;
+
+extern "C" int srg_teleport_iterate_f64(const int32_t *t_indptr, const int32_t *t_indices, const float *t_vals, int64_t n,
+                                        double ppr_alpha, const double *x, double *y, double *stats3, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n >= 1 && t_indptr && t_indices && t_vals && x && y && stats3 && x != y, "teleport_iterate: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  const long long blocks = ceil_div64(n + 1, 256);
+  double *part = nullptr;
+  SRG_CUDA(cudaMallocAsync(&part, (size_t)(2 * blocks) * sizeof(double), s));
+  ppr_dot_kernel<<<1, 1024, 0, s>>>(x, x, n, 1.0, 1.0, stats3);   // stats3[0] = sum_{i<n} x_i
+  SRG_LAUNCHED();
+  teleport_sweep_kernel<<<(unsigned)blocks, 256, 0, s>>>(t_indptr, t_indices, t_vals, x, n, 1 - ppr_alpha, ppr_alpha, stats3,
+                                                        y, part);
+  SRG_LAUNCHED();
+  ppr_finish_kernel<<<1, 1024, 0, s>>>(part, blocks, stats3);     // stats3[1] = |y - x|_1 (first n), [2] = sum_{j<n} y_j
+  SRG_LAUNCHED();
+  cudaFreeAsync(part, s);
+  return SRG_OK;
+}
+
+extern "C" int srg_csr_intersect_mean_f32(const int32_t *a_indptr, const int32_t *a_indices, const float *a_vals,
+                                          const int32_t *b_indptr, const int32_t *b_indices, const float *b_vals,
+                                          int64_t n, int64_t a_nnz, int32_t *out_indptr, int32_t *out_indices,
+                                          float *out_vals, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n >= 0 && a_nnz >= 0 && a_indptr && b_indptr && out_indptr, "csr_intersect_mean: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  if (n == 0) {
+    SRG_CUDA(cudaMemsetAsync(out_indptr, 0, sizeof(int32_t), s));
+    return SRG_OK;
+  }
+  SRG_REQUIRE(a_nnz == 0 || (a_indices && a_vals && b_indices && b_vals && out_indices && out_vals),
+              "csr_intersect_mean: NULL pointer");
+  int *ints = nullptr;   // cnt (n) | match (a_nnz) | scratch
+  SRG_CUDA(cudaMallocAsync(&ints, (size_t)(n + std::max<int64_t>(a_nnz, 1) + scan_scratch_ints(n)) * sizeof(int), s));
+  int *cnt = ints, *match = ints + n, *scratch = match + std::max<int64_t>(a_nnz, 1);
+  intersect_count_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, s>>>(a_indptr, a_indices, a_vals, b_indptr, b_indices,
+                                                                        b_vals, n, cnt, match);
+  SRG_LAUNCHED();
+  rc = exclusive_scan_i32(cnt, n, out_indptr, scratch, s);
+  if (!rc && a_nnz > 0) {
+    intersect_fill_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(a_indptr, a_indices, a_vals, b_vals, match, out_indptr,
+                                                                     n, out_indices, out_vals);
+    SRG_LAUNCHED();
+  }
+  cudaFreeAsync(ints, s);
+  return rc;
+}
 
 extern "C" int srg_ppr_iterate_f64(const int32_t *t_indptr, const int32_t *t_indices, const float *t_counts,
                                    const double *degree, int64_t n, double ppr_alpha, const double *x, double *y,

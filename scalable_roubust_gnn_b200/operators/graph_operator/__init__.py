@@ -4,3 +4,4 @@ from .symmetrical_directed_magnetic_laplacian_operator import SymDirMagLaplacian
 from .symmetrical_directed_magnetic_comppr_operator import SymDirMagComPprGraphOp  # noqa: F401
 from .in_out_directed_laplacian_operator import TwoDirLaplacianGraphOp  # noqa: F401
 from .symmetrical_directed_fast_ppr_approximate_operator import SymDirFastPprApproxGraphOp  # noqa: F401
+from .symmetrical_directed_two_order_ppr_approximate_operator import SymDirTwoOrderPprApproxGraphOp  # noqa: F401

@@ -24,7 +24,7 @@ import torch
 from .. import _lib
 
 __all__ = ["csr_sparse_dense_matmul", "adj_to_symmetric_norm", "propagate_host", "propagate_aggregate_host",
-           "csr_host_parts", "adj_to_directed_symmetric_mag_norm", "adj_to_un_in_out_dir_symmetric_norm", "adj_to_fast_ppr_approx_symmetric_norm", "DeviceHopRunner"]
+           "csr_host_parts", "adj_to_directed_symmetric_mag_norm", "adj_to_un_in_out_dir_symmetric_norm", "adj_to_fast_ppr_approx_symmetric_norm", "adj_to_slow_first_second_ppr_approx_symmetric_norm", "DeviceHopRunner"]
 
 
 def _ptr(a):
@@ -361,6 +361,72 @@ def adj_to_fast_ppr_approx_symmetric_norm(adj, r, ppr_alpha, max_iter=100, devic
         m = int(o_indptr[-1].item())
         lap = DeviceCSR(o_indptr, o_indices[:max(m, 1)], o_vals[:max(m, 1)], n, m)
         return csr_to_scipy(csr_sym_scale(lap, float(r)))
+
+
+def adj_to_slow_first_second_ppr_approx_symmetric_norm(adj, r, ppr_alpha, device=0, max_sweeps=2000, tol=1e-13):
+    """First- and second-order PPR-approximation operators of a directed graph on the GPU
+    (SSRG/operators/utils.py:337-424, the normaliser of SymDirTwoOrderPprApproxGraphOp).
+
+    The reference works on dense N x N matrices and takes the stationary vector from a dense LAPACK eigen-
+    decomposition of the (N+1) x (N+1) teleport matrix in float32.  Here P = D^-1 (A + I) stays a CSR, the stationary
+    vector is the fixed point of the same matrix by power iteration in fp64 (it agrees with LAPACK's float32 result
+    to float32 accuracy), the first-order Laplacian is the pi-weighted symmetrisation, the second-order one is
+    ``(P^T P + P P^T) / 2`` on the entries where both products are non-zero (sparse x sparse products), both
+    degree-normalised in float32.  Returns two ``scipy.sparse.csr_matrix`` (float32).
+    Round-1 status: not yet run on hardware (opt-in test)."""
+    from ..device import DeviceCSR
+    from ..sparse_mm import csr_sym_scale, csr_to_scipy, csr_transpose, spgemm
+    lib = _lib.load()
+    if lib.srg_device_count() <= 0:
+        raise _lib.SrgError(_lib.SRG_ERR_NODEV, "no CUDA device visible: libsrgnn_b200 has no CPU fallback")
+    if not sp.issparse(adj):
+        raise TypeError("The adjacency matrix must be a scipy sparse matrix!")
+    csr = adj.tocsr() if not isinstance(adj, sp.csr_matrix) else adj
+    dev = torch.device("cuda", int(device))
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        a1 = _pattern_plus_loops(lib, csr, dev, stream)
+        n = a1.n
+        p, deg32 = csr_sym_scale(a1, 0.0, want_degree=True)           # P = D^-1 A1 (float32, :345-352)
+        pt = csr_transpose(p)
+        # stationary vector of the teleport chain (:353-369)
+        x = torch.full((n + 1,), 1.0 / (n + 1), dtype=torch.float64, device=dev)
+        y = torch.empty_like(x)
+        stats = torch.zeros(3, dtype=torch.float64, device=dev)
+        prev = None
+        for sweep in range(max_sweeps):
+            _lib.check(lib.srg_teleport_iterate_f64(_ptr(pt.indptr), _ptr(pt.indices), _ptr(pt.data), n, float(ppr_alpha),
+                                                    _ptr(x), _ptr(y), _ptr(stats), stream))
+            x, y = y, x
+            # the float32 rows of P do not sum to exactly 1, so the dominant eigenvalue is 1 + O(1e-8): keep the
+            # iterate on the simplex and test the DIRECTION for convergence (every 8 sweeps, one sync)
+            x.div_(x.sum())
+            if sweep % 8 == 7:
+                if prev is not None and float((x - prev).abs().sum().item()) <= tol:
+                    break
+                prev = x.clone()
+        stats[2] = x[:n].sum()                      # pi = x[:n] / sum(x[:n]) inside the symmetrisation
+        deg = deg32.to(torch.float64)
+        cap = max(2 * a1.nnz, 1)
+        o_indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        o_indices = torch.empty(cap, dtype=torch.int32, device=dev)
+        o_vals = torch.empty(cap, dtype=torch.float32, device=dev)
+        _lib.check(lib.srg_ppr_symmetrize(_ptr(a1.indptr), _ptr(a1.indices), _ptr(a1.data), _ptr(deg), _ptr(x), _ptr(stats),
+                                          n, a1.nnz, _ptr(o_indptr), _ptr(o_indices), _ptr(o_vals), stream))
+        m1 = int(o_indptr[-1].item())
+        one = csr_sym_scale(DeviceCSR(o_indptr, o_indices[:max(m1, 1)], o_vals[:max(m1, 1)], n, m1), float(r))   # :374-400
+        # second order (:402-421)
+        l_in = spgemm(pt, p, drop_zeros=True)
+        l_out = spgemm(p, pt, drop_zeros=True)
+        t_indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        t_indices = torch.empty(max(l_in.nnz, 1), dtype=torch.int32, device=dev)
+        t_vals = torch.empty(max(l_in.nnz, 1), dtype=torch.float32, device=dev)
+        _lib.check(lib.srg_csr_intersect_mean_f32(_ptr(l_in.indptr), _ptr(l_in.indices), _ptr(l_in.data), _ptr(l_out.indptr),
+                                                  _ptr(l_out.indices), _ptr(l_out.data), n, l_in.nnz, _ptr(t_indptr),
+                                                  _ptr(t_indices), _ptr(t_vals), stream))
+        m2 = int(t_indptr[-1].item())
+        two = csr_sym_scale(DeviceCSR(t_indptr, t_indices[:max(m2, 1)], t_vals[:max(m2, 1)], n, m2), float(r))
+        return csr_to_scipy(one), csr_to_scipy(two)
 
 
 class DeviceHopRunner:

@@ -54,3 +54,23 @@ def test_device_fast_ppr_vs_oracle_larger():
     got.sort_indices()
     np.testing.assert_array_equal(got.indices, want.indices)
     np.testing.assert_allclose(got.data, want.data, rtol=2e-6, atol=1e-9)
+
+
+@pytest.mark.gpu
+@_UNVALIDATED
+def test_device_two_order_ppr_vs_reference_golden():
+    from scalable_roubust_gnn_b200.operators.graph_operator import SymDirTwoOrderPprApproxGraphOp
+    g = np.load(os.path.join(GOLDEN_DIR, "reference_ext.npz"))
+    a, x = golden_csr(g, "ppr_adj"), g["ppr_x"]
+    op = SymDirTwoOrderPprApproxGraphOp(2, r=0.5, ppr_alpha=0.1)
+    h1, h2 = op.propagate(a, x)
+    for got, key in ((op.one_adj, "twoorder_one"), (op.two_adj, "twoorder_two")):
+        want = golden_csr(g, key)
+        got = got.tocsr()
+        got.sort_indices()
+        np.testing.assert_array_equal(got.indptr, want.indptr)
+        np.testing.assert_array_equal(got.indices, want.indices)
+        # the reference's stationary vector comes from a float32 LAPACK eigendecomposition
+        np.testing.assert_allclose(got.data, want.data, rtol=2e-5, atol=1e-8)
+    np.testing.assert_allclose(np.stack([h.numpy() for h in h1]), g["twoorder_one_hops"], rtol=5e-5, atol=1e-6)
+    np.testing.assert_allclose(np.stack([h.numpy() for h in h2]), g["twoorder_two_hops"], rtol=5e-5, atol=1e-6)

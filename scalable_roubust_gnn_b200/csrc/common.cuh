@@ -50,6 +50,34 @@ static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStre
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Stream-ordered scratch of ONE stream: every block is handed back with cudaFreeAsync on that stream when the
+// scope ends, on the success path and on every early error return alike (the frees are ordered after the work
+// already queued on the stream, so kernels in flight keep their memory).
+struct StreamScratch {
+  cudaStream_t s;
+  void *ptrs[16];
+  int count = 0;
+  explicit StreamScratch(cudaStream_t s_) : s(s_) {}
+  StreamScratch(const StreamScratch &) = delete;
+  StreamScratch &operator=(const StreamScratch &) = delete;
+  template <typename T> int alloc(T **p, size_t n_elems) {
+    *p = nullptr;
+    if (count >= 16) {
+      set_err("StreamScratch: too many blocks");
+      return SRG_ERR_INVALID;
+    }
+    void *q = nullptr;
+    cudaError_t e = cudaMallocAsync(&q, (n_elems ? n_elems : 1) * sizeof(T), s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
+    ptrs[count++] = q;
+    *p = static_cast<T *>(q);
+    return SRG_OK;
+  }
+  ~StreamScratch() {
+    for (int i = count - 1; i >= 0; --i) cudaFreeAsync(ptrs[i], s);
+  }
+};
+
 // ---- device helpers --------------------------------------------------------------------
 // streamed-once data (CSR arrays): read-only path, do not allocate in L1
 __device__ __forceinline__ int ld_stream_i32(const int *p) {

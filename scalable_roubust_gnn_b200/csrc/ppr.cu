@@ -11,7 +11,7 @@
 //   srg_ppr_symmetrize    the union pattern of A1 and A1^T with the two pi-weighted terms summed, / 2
 // fp64 throughout; the sums run in a fixed (deterministic) order, not scipy's internal one, so the stationary
 // vector agrees to rounding (1e-15) and the final float32 values to float32 rounding.
-// HARDWARE STATUS: written after the round-1 GPU budget was spent; its test is opt-in (SRG_TEST_UNVALIDATED=1).
+// Scratch is stream-ordered and scoped (StreamScratch): every return path hands its blocks back.
 #include <algorithm>
 
 #include "common.cuh"
@@ -251,8 +251,9 @@ extern "C" int srg_teleport_iterate_f64(const int32_t *t_indptr, const int32_t *
   SRG_REQUIRE(n >= 1 && t_indptr && t_indices && t_vals && x && y && stats3 && x != y, "teleport_iterate: bad arguments");
   cudaStream_t s = as_stream(stream);
   const long long blocks = ceil_div64(n + 1, 256);
+  StreamScratch scratch(s);
   double *part = nullptr;
-  SRG_CUDA(cudaMallocAsync(&part, (size_t)(2 * blocks) * sizeof(double), s));
+  if ((rc = scratch.alloc(&part, (size_t)(2 * blocks)))) return rc;
   ppr_dot_kernel<<<1, 1024, 0, s>>>(x, x, n, 1.0, 1.0, stats3);   // stats3[0] = sum_{i<n} x_i
   SRG_LAUNCHED();
   teleport_sweep_kernel<<<(unsigned)blocks, 256, 0, s>>>(t_indptr, t_indices, t_vals, x, n, 1 - ppr_alpha, ppr_alpha, stats3,
@@ -260,7 +261,6 @@ extern "C" int srg_teleport_iterate_f64(const int32_t *t_indptr, const int32_t *
   SRG_LAUNCHED();
   ppr_finish_kernel<<<1, 1024, 0, s>>>(part, blocks, stats3);     // stats3[1] = |y - x|_1 (first n), [2] = sum_{j<n} y_j
   SRG_LAUNCHED();
-  cudaFreeAsync(part, s);
   return SRG_OK;
 }
 
@@ -278,8 +278,9 @@ extern "C" int srg_csr_intersect_mean_f32(const int32_t *a_indptr, const int32_t
   }
   SRG_REQUIRE(a_nnz == 0 || (a_indices && a_vals && b_indices && b_vals && out_indices && out_vals),
               "csr_intersect_mean: NULL pointer");
+  StreamScratch pool(s);
   int *ints = nullptr;   // cnt (n) | match (a_nnz) | scratch
-  SRG_CUDA(cudaMallocAsync(&ints, (size_t)(n + std::max<int64_t>(a_nnz, 1) + scan_scratch_ints(n)) * sizeof(int), s));
+  if ((rc = pool.alloc(&ints, (size_t)(n + std::max<int64_t>(a_nnz, 1) + scan_scratch_ints(n))))) return rc;
   int *cnt = ints, *match = ints + n, *scratch = match + std::max<int64_t>(a_nnz, 1);
   intersect_count_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, s>>>(a_indptr, a_indices, a_vals, b_indptr, b_indices,
                                                                         b_vals, n, cnt, match);
@@ -290,7 +291,6 @@ extern "C" int srg_csr_intersect_mean_f32(const int32_t *a_indptr, const int32_t
                                                                      n, out_indices, out_vals);
     SRG_LAUNCHED();
   }
-  cudaFreeAsync(ints, s);
   return rc;
 }
 
@@ -306,15 +306,15 @@ extern "C" int srg_ppr_iterate_f64(const int32_t *t_indptr, const int32_t *t_ind
   const double c_nz = a * (1 + a), c_z = (1 - a) / (1 + a) + a * (1 + a);
   const double sv = 1 / (1 + a) / (double)n;
   const long long blocks = ceil_div64(n, 256);
+  StreamScratch scratch(s);
   double *part = nullptr;
-  SRG_CUDA(cudaMallocAsync(&part, (size_t)(2 * blocks) * sizeof(double), s));
+  if ((rc = scratch.alloc(&part, (size_t)(2 * blocks)))) return rc;
   ppr_dot_kernel<<<1, 1024, 0, s>>>(x, degree, n, c_nz, c_z, stats3);
   SRG_LAUNCHED();
   ppr_sweep_kernel<<<(unsigned)blocks, 256, 0, s>>>(t_indptr, t_indices, t_counts, x, degree, n, 1 - a, sv, stats3, y, part);
   SRG_LAUNCHED();
   ppr_finish_kernel<<<1, 1024, 0, s>>>(part, blocks, stats3);
   SRG_LAUNCHED();
-  cudaFreeAsync(part, s);
   return SRG_OK;
 }
 
@@ -333,10 +333,11 @@ extern "C" int srg_ppr_symmetrize(const int32_t *indptr, const int32_t *indices,
   unsigned *pos = nullptr;    // 2m
   double *val = nullptr;      // m
   int *ints = nullptr;        // head (m+1) | seg (m+1) | scratch
-  SRG_CUDA(cudaMallocAsync(&keys, (size_t)(3 * m) * sizeof(uint64_t), s));
-  SRG_CUDA(cudaMallocAsync(&pos, (size_t)(2 * m) * sizeof(unsigned), s));
-  SRG_CUDA(cudaMallocAsync(&val, (size_t)m * sizeof(double), s));
-  SRG_CUDA(cudaMallocAsync(&ints, (size_t)(2 * (m + 1) + scan_scratch_ints(m)) * sizeof(int), s));
+  StreamScratch pool(s);
+  if ((rc = pool.alloc(&keys, (size_t)(3 * m)))) return rc;
+  if ((rc = pool.alloc(&pos, (size_t)(2 * m)))) return rc;
+  if ((rc = pool.alloc(&val, (size_t)m))) return rc;
+  if ((rc = pool.alloc(&ints, (size_t)(2 * (m + 1) + scan_scratch_ints(m))))) return rc;
   int *head = ints, *seg = ints + (m + 1), *scratch = seg + (m + 1);
   ppr_pairs_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, s>>>(indptr, indices, counts, degree, x, stats3, n, nnz, keys,
                                                                   pos, val);
@@ -354,9 +355,5 @@ extern "C" int srg_ppr_symmetrize(const int32_t *indptr, const int32_t *indices,
     ppr_row_lower_bound_kernel<<<(unsigned)ceil_div64(n + 1, 256), 256, 0, s>>>(keys + 2 * m, seg + m, n, out_indptr);
     SRG_LAUNCHED();
   }
-  cudaFreeAsync(ints, s);
-  cudaFreeAsync(val, s);
-  cudaFreeAsync(pos, s);
-  cudaFreeAsync(keys, s);
   return rc;
 }

@@ -72,7 +72,10 @@ int64_t srg_launch_count(void);
 
 /* tuning / experiment knobs (profiles/ records which values the defaults come from):
  *   "spmm_variant" 0 group kernel | 1 stream kernel;  "stream_batch" 4|8;  "stream_rows" rows per
- *   warp task;  "group_unroll" 4|8;  "gather_l2_64" 0|1;  "long_row" split threshold (0 = never) */
+ *   warp task;  "group_unroll" 4|8;  "gather_l2_64" 0|1;  "long_row" split threshold (0 = never);
+ *   "bulk_gather" -1 auto | 0 never | 1 always (rows <= 512 B fetched by TMA bulk copies), "bulk_auto" / "bulk_min"
+ *   widest / narrowest padded row (floats) of the automatic choice, "bulk_stages" 2..4, "bulk_rows" rows per warp
+ *   task, "bulk_tile" 0|1 finished rows leave as one bulk store per destination;  "push_tma" 0|1 */
 int srg_set_tuning(const char *key, int64_t value);
 
 /* ---- a3: adjacency normalisation  (SSRG/operators/utils.py:81-93) ------------------------ */
@@ -307,6 +310,19 @@ int srg_spmm_csr_f32_push(const int32_t *indptr, const int32_t *indices, const f
                           int64_t n_rows, int64_t nnz, const float *X, int64_t ldx,
                           float *const *dests, int32_t n_dests, int64_t dest_row0, int64_t ldy,
                           int32_t F, void *stream);
+/* The same with one row offset per destination (dest_row0s, HOST array): the rank's own n_rows x ldy copy of the
+ * hop — element k of the K+1 matrices GraphOp.propagate returns (SSRG/operators/base_operator.py:31-36) — is one
+ * more destination with offset 0, so keeping every hop costs no extra pass.  n_dests <= 9. */
+int srg_spmm_csr_f32_push2(const int32_t *indptr, const int32_t *indices, const float *vals,
+                           int64_t n_rows, int64_t nnz, const float *X, int64_t ldx,
+                           float *const *dests, const int64_t *dest_row0s, int32_t n_dests, int64_t ldy,
+                           int32_t F, void *stream);
+/* Orders consecutive push hops across ranks without a collective: publishes `epoch` into slot `my_slot` of every
+ * peer's flag array (peer_flags: HOST array of n_peers device pointers to >= 32 uint32 each, peer-mapped) and waits
+ * until every peer's epoch has arrived in local_flags[0..n_peers).  Stream-ordered; a peer that does not show up
+ * within 2 s sets *timeout_flag (device int32, may be NULL) instead of hanging the GPU. */
+int srg_peer_barrier(void *local_flags, void *const *peer_flags, int32_t n_peers, int32_t my_slot,
+                     uint32_t epoch, int32_t *timeout_flag, void *stream);
 /* input exchange without a collective: copy n_rows x ld floats into rows dest_row0.. of every
  * destination buffer (own + peers) */
 int srg_push_rows_f32(const float *src, int64_t n_rows, int64_t ld, float *const *dests,

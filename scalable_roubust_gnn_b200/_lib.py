@@ -81,6 +81,9 @@ SIGNATURES = {
     "srg_apply_feature_mask_f32": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
     "srg_spmm_csr_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
     "srg_spmm_csr_f32_push": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, C.POINTER(_vp), _i32, _i64, _i64, _i32, _vp]),
+    "srg_spmm_csr_f32_push2": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, C.POINTER(_vp), C.POINTER(_i64), _i32, _i64,
+                                         _i32, _vp]),
+    "srg_peer_barrier": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i32, C.c_uint32, _vp, _vp]),
     "srg_push_rows_f32": (C.c_int, [_vp, _i64, _i64, C.POINTER(_vp), _i32, _i64, _vp]),
     "srg_dist_unique_id": (C.c_int, [_vp]),
     "srg_dist_init": (C.c_int, [_vp, _i32, _i32, _i64, _i32, C.POINTER(_vp)]),
@@ -153,6 +156,11 @@ def load() -> C.CDLL:
                 fn.argtypes = args
             if lib.srg_abi_version() != 1:
                 raise RuntimeError("libsrgnn_b200.so ABI version mismatch")
+            # experiment knobs from the environment: SRG_TUNE="bulk_tile=1,bulk_rows=8" (srg_set_tuning keys)
+            for item in filter(None, os.environ.get("SRG_TUNE", "").split(",")):
+                key, _, val = item.partition("=")
+                if lib.srg_set_tuning(key.strip().encode(), int(val)) != SRG_OK:
+                    raise RuntimeError(f"SRG_TUNE: {lib.srg_last_error().decode()}")
             _lib = lib
     return _lib
 

@@ -44,6 +44,12 @@ static int g_gather_l2_64 = 1;   // gathers fetch 64-byte DRAM granules instead 
 static int g_group_unroll = 4;   // U of the 32-lane group kernel (4 or 8)
 static int g_push_tma = 0;       // push hop: stage the block's rows in shared memory, one TMA bulk store per peer
 static int g_long_row = 1024;    // rows with more entries are split (0 = never split)
+static int g_bulk_gather = -1;   // -1: bulk (TMA) row gathers for rows of <= g_bulk_auto floats; 0 never; 1 whenever a row is <= 512 B
+static int g_bulk_auto = 64;     // widest row (floats, padded) the automatic choice hands to the bulk kernel
+static int g_bulk_min = 32;      // ... and the narrowest (a bulk copy of < 128 bytes is not worth a TMA request)
+static int g_bulk_stages = 2;    // chunks of 32 neighbour rows in flight per warp (2..4)
+static int g_bulk_rows = 32;     // rows per warp task of the bulk kernel (1..32)
+static int g_bulk_tile = 0;      // 1: finished rows are staged in shared memory and leave as ONE bulk store per destination
 
 // ---- vector abstraction for the group kernel: float4 fast path, float scalar path ------------------
 template <typename VT> struct VecOps;
@@ -64,6 +70,13 @@ template <> struct VecOps<float> {
 };
 
 constexpr int kSpmmThreads = 256;
+
+// rows of <= 512 bytes can be fetched whole by the TMA unit (bulk-gather kernel below)
+static inline bool use_bulk_gather(int nvec, int64_t ld_floats) {
+  if (nvec > 32 || nvec < 1) return false;
+  if (g_bulk_gather > 0) return true;
+  return g_bulk_gather < 0 && ld_floats <= g_bulk_auto && ld_floats >= g_bulk_min;
+}
 
 template <typename VT, int G, int U, bool ACCUM>
 __global__ void __launch_bounds__(kSpmmThreads)
@@ -161,7 +174,7 @@ __device__ __forceinline__ float4 lds_f4(unsigned smem_addr) {
 }
 
 constexpr int kStreamWarps = 8;
-constexpr int kMaxPeers = 8;
+constexpr int kMaxPeers = 9;      // 8 row blocks + the rank's own copy of the hop (the K+1 matrices of the API)
 
 struct PeerDests {
   float4 *p[kMaxPeers];
@@ -359,6 +372,288 @@ __global__ void __launch_bounds__(kStreamWarps * 32) spmm_stream_kernel(const St
   }
 }
 
+// ---- bulk-gather stream kernel: neighbour rows of <= 512 bytes fetched by the TMA unit -----------------------------
+// Same task shape and the same arithmetic as the stream kernel (one warp walks the neighbours of R consecutive rows
+// as ONE stream and applies the FMAs in CSR order, so the result is bit-identical), but a neighbour row is moved by
+// ONE 1-D bulk copy (cp.async.bulk.shared.global, SASS UBLKCP) issued by the lane that holds its index instead of
+// one 16-byte cp.async per lane: the warp spends its issue slots on the FMA chain, not on addressing.  The narrow
+// rows of the multi-GPU grid (F/2 = 50 floats -> 224 bytes) were bound by issued instructions per gathered row
+// (~56) in the LDGSTS form; here a gathered row costs ~6 instructions to fetch and ~8 to consume.
+//   per warp: S stages of 32 row slots (+ the 32 edge weights of the chunk), one mbarrier per stage; the lane that
+//   owns position i of a chunk issues the copy of X[indices[i]] into slot i with complete_tx on the stage barrier;
+//   the warp waits for the stage, consumes its 32 positions in order and refills the stage.
+//   TILE: finished rows are staged in a shared-memory tile (R x ldy) and leave as one bulk store per destination
+//   (own buffer, peers over NVLink, the caller's copy of the hop) - the exchange never touches the load/store path.
+__device__ __forceinline__ void mbar_init(unsigned mb, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mb, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mb, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(mb), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mb) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mb)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, unsigned src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float lds_f1(unsigned smem_addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f1(unsigned smem_addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f4(unsigned smem_addr, const float4 &v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(smem_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+static inline size_t bulk_warp_smem(int S, int nvec, int R, long long ldy, bool tile) {
+  size_t b = (size_t)S * 32 * nvec * 16 + (size_t)S * 128 + (tile ? (size_t)R * ldy * 16 : 0) + (size_t)S * 8;
+  return (b + 127) / 128 * 128;
+}
+
+template <int S, bool PUSH, bool TILE>
+__global__ void __launch_bounds__(128) spmm_bulk_kernel(const StreamArgs a, const unsigned warp_smem) {
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  constexpr unsigned FULL = 0xffffffffu;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const unsigned rowbytes = (unsigned)a.nvec * 16u;
+  const unsigned slots = (unsigned)__cvta_generic_to_shared(bulk_smem) + (unsigned)w * warp_smem;
+  const unsigned sv = slots + (unsigned)S * 32u * rowbytes;
+  const unsigned tile = sv + (unsigned)S * 128u;
+  const unsigned mb = tile + (TILE ? (unsigned)a.R * (unsigned)a.ldy * 16u : 0u);
+
+  const long long n_rows = a.n_rows_dev ? min((long long)*a.n_rows_dev, a.n_rows) : a.n_rows;
+  const long long task = (long long)blockIdx.x * wpb + w;
+  const long long r0 = task * a.R;
+  if (r0 >= n_rows) return;
+  const int nr = (int)min((long long)a.R, n_rows - r0);
+  const bool active = lane < a.nvec;
+  const float4 *Xc = a.X + lane;
+  const unsigned ldx = a.ldx;
+  const long long ldy = a.ldy;
+  float4 *yrow = a.Y + r0 * ldy + lane;   // !TILE
+  unsigned trow = tile + (unsigned)lane * 16u;   // TILE: the lane's float4 of the current tile row
+
+  const int my_end = (lane < nr) ? __ldg(a.row_hi + r0 + lane) : 0;
+  const int e0 = __ldg(a.row_lo + r0);
+  const int e1 = __shfl_sync(FULL, my_end, nr - 1);
+  int prev_end = __shfl_up_sync(FULL, my_end, 1);
+  if (lane == 0) prev_end = e0;
+  const int my_len = my_end - prev_end;
+  const bool odd_row = lane < nr && (my_len == 0 || (a.long_len > 0 && my_len > a.long_len));
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc = zero4;
+
+#define SRG_BULK_ROW_DONE()                                                    \
+  do {                                                                         \
+    if (TILE) {                                                                \
+      if (lane < (int)ldy) sts_f4(trow, active ? acc : zero4);                 \
+      trow += (unsigned)ldy * 16u;                                             \
+    } else {                                                                   \
+      if (active) store_row<PUSH>(a, yrow, acc);                               \
+      yrow += ldy;                                                             \
+    }                                                                          \
+    acc = zero4;                                                               \
+  } while (0)
+
+  if (__any_sync(FULL, odd_row)) {
+    // an empty or an over-long row in this task: rows one by one with direct loads (A^ has a full diagonal, so
+    // empty rows only occur for caller-supplied matrices; over-long rows are left to the segment kernels and
+    // travel as zeros here - the combine kernel, later in stream order, writes them)
+    for (int r = 0; r < nr; ++r) {
+      const int st = __shfl_sync(FULL, prev_end, r), ed = __shfl_sync(FULL, my_end, r);
+      const bool skip = a.long_len > 0 && ed - st > a.long_len;
+      if (!skip) {
+        for (int j = st; j < ed; ++j) {
+          const int c = __ldg(a.indices + j);
+          const float v = __ldg(a.vals + j);
+          if (active) {
+            const float4 x = ld_gather_f4(Xc + (unsigned long long)(unsigned)c * ldx);
+            acc.x = fmaf(v, x.x, acc.x);
+            acc.y = fmaf(v, x.y, acc.y);
+            acc.z = fmaf(v, x.z, acc.z);
+            acc.w = fmaf(v, x.w, acc.w);
+          }
+        }
+      }
+      if (TILE || !skip) {
+        SRG_BULK_ROW_DONE();
+      } else {
+        yrow += ldy;
+      }
+    }
+  } else {
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) mbar_init(mb + 8u * s, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int n_chunks = (e1 - e0 + 31) >> 5;
+    int nx_c = 0;
+    float nx_v = 0.f;
+    if (e0 + lane < e1) {
+      nx_c = ld_stream_i32(a.indices + e0 + lane);
+      nx_v = ld_stream_f32(a.vals + e0 + lane);
+    }
+    int issued = 0, ist = 0;   // chunks issued so far, stage of the next issue
+
+#define SRG_BULK_ISSUE()                                                                                    \
+  do {                                                                                                      \
+    const int cb_ = e0 + (issued << 5);                                                                     \
+    const int cnt_ = min(32, e1 - cb_);                                                                     \
+    const int c_ = nx_c;                                                                                    \
+    sts_f1(sv + (unsigned)ist * 128u + (unsigned)lane * 4u, nx_v);                                          \
+    if (cb_ + 32 + lane < e1) {                                                                             \
+      nx_c = ld_stream_i32(a.indices + cb_ + 32 + lane);                                                    \
+      nx_v = ld_stream_f32(a.vals + cb_ + 32 + lane);                                                       \
+    }                                                                                                       \
+    if (lane == 0) mbar_expect_tx(mb + 8u * ist, (unsigned)cnt_ * rowbytes);                                \
+    __syncwarp();                                                                                           \
+    if (lane < cnt_)                                                                                        \
+      bulk_g2s(slots + ((unsigned)ist * 32u + (unsigned)lane) * rowbytes, a.X + (unsigned long long)(unsigned)c_ * ldx, \
+               rowbytes, mb + 8u * ist);                                                                    \
+    ++issued;                                                                                               \
+    if (++ist == S) ist = 0;                                                                                \
+  } while (0)
+
+    for (int k = 0; k < S && k < n_chunks; ++k) SRG_BULK_ISSUE();
+    int cst = 0;
+    unsigned par = 0;
+    for (int k = 0; k < n_chunks; ++k) {
+      const int cb = e0 + (k << 5);
+      const int cnt = min(32, e1 - cb);
+      unsigned bit = 0;
+      {
+        const int d = my_end - cb - 1;
+        if (lane < nr && d >= 0 && d < 32) bit = 1u << d;
+      }
+      const unsigned endmask = __reduce_or_sync(FULL, bit);
+      const unsigned sl = slots + (unsigned)cst * 32u * rowbytes + (unsigned)lane * 16u;
+      const unsigned svp = sv + (unsigned)cst * 128u;
+      mbar_wait(mb + 8u * cst, par);
+      if (cnt == 32) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v4 = lds_f4(svp + q * 16);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = q * 4 + u;
+            const float v = (u == 0) ? v4.x : (u == 1) ? v4.y : (u == 2) ? v4.z : v4.w;
+            if (active) {
+              const float4 x = lds_f4(sl + (unsigned)j * rowbytes);
+              acc.x = fmaf(v, x.x, acc.x);
+              acc.y = fmaf(v, x.y, acc.y);
+              acc.z = fmaf(v, x.z, acc.z);
+              acc.w = fmaf(v, x.w, acc.w);
+            }
+            if ((endmask >> j) & 1u) SRG_BULK_ROW_DONE();
+          }
+        }
+      } else {
+        for (int j = 0; j < cnt; ++j) {
+          const float v = lds_f1(svp + j * 4);
+          if (active) {
+            const float4 x = lds_f4(sl + (unsigned)j * rowbytes);
+            acc.x = fmaf(v, x.x, acc.x);
+            acc.y = fmaf(v, x.y, acc.y);
+            acc.z = fmaf(v, x.z, acc.z);
+            acc.w = fmaf(v, x.w, acc.w);
+          }
+          if ((endmask >> j) & 1u) SRG_BULK_ROW_DONE();
+        }
+      }
+      if (++cst == S) {
+        cst = 0;
+        par ^= 1u;
+      }
+      __syncwarp();   // every lane has read the stage before it is refilled
+      if (issued < n_chunks) SRG_BULK_ISSUE();
+    }
+#undef SRG_BULK_ISSUE
+  }
+#undef SRG_BULK_ROW_DONE
+
+  if (TILE) {
+    // generic-proxy writes of the tile -> visible to the async proxy, then ONE bulk store per destination
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const unsigned bytes = (unsigned)nr * (unsigned)ldy * 16u;
+    const long long off = r0 * ldy;
+    bool sent = false;
+    if (PUSH) {
+#pragma unroll
+      for (int d = 0; d < kMaxPeers; ++d)
+        if (d < a.peers.count && lane == d) {
+          bulk_s2g(a.peers.p[d] + off, tile, bytes);
+          sent = true;
+        }
+    } else if (lane == 0) {
+      bulk_s2g(a.Y + off, tile, bytes);
+      sent = true;
+    }
+    if (sent) {
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  }
+}
+
+template <int S, bool PUSH, bool TILE>
+static int launch_bulk_t(const StreamArgs &a, int64_t max_rows, cudaStream_t s) {
+  const size_t per_warp = bulk_warp_smem(S, a.nvec, a.R, a.ldy, TILE);
+  int wpb = 4;
+  while (wpb > 1 && per_warp * wpb > 113 * 1024) wpb >>= 1;   // at least two blocks per SM when a warp's share allows it
+  const size_t smem = per_warp * wpb;
+  if (smem > 227 * 1024) {
+    set_err("spmm: bulk-gather kernel needs %zu bytes of shared memory", smem);
+    return SRG_ERR_RANGE;
+  }
+  const int64_t tasks = ceil_div64(max_rows, a.R);
+  const int64_t blocks = ceil_div64(tasks, wpb);
+  if (blocks > 2147483647LL) {
+    set_err("spmm: grid too large (%lld blocks)", (long long)blocks);
+    return SRG_ERR_RANGE;
+  }
+  if (blocks == 0) return SRG_OK;
+  SRG_CUDA(cudaFuncSetAttribute(spmm_bulk_kernel<S, PUSH, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  spmm_bulk_kernel<S, PUSH, TILE><<<(unsigned)blocks, wpb * 32, smem, s>>>(a, (unsigned)per_warp);
+  SRG_LAUNCHED();
+  return SRG_OK;
+}
+
+template <bool PUSH>
+static int launch_bulk(const StreamArgs &a, int64_t max_rows, bool tile, cudaStream_t s) {
+  const int S = g_bulk_stages < 2 ? 2 : (g_bulk_stages > 4 ? 4 : g_bulk_stages);
+#define SRG_CASE(SS)                                                     \
+  if (S == SS)                                                           \
+    return tile ? launch_bulk_t<SS, PUSH, true>(a, max_rows, s) : launch_bulk_t<SS, PUSH, false>(a, max_rows, s)
+  SRG_CASE(2);
+  SRG_CASE(3);
+  SRG_CASE(4);
+#undef SRG_CASE
+  return SRG_ERR_INVALID;
+}
+
 // ---- long rows: device-side plan, segment tasks, ordered combine ------------------------------------------
 struct LongPlan {
   int *counts;     // [0] number of long rows, [1] number of segments
@@ -511,7 +806,16 @@ static int stream_hop(const int *indptr, const int *indices, const float *vals, 
   }
   // bulk-store form of the push hop: one row chunk per task (nvec <= 32), whole rows of <= 32 float4, tile <= 32 KB
   const bool tma = PUSH && g_push_tma && a.chunks == 1 && a.ldy <= 32 && a.R <= 8 && a.peers.count > 0;
-  rc = launch_stream<PUSH>(a, n_rows, s, tma);
+  // rows of <= 512 bytes: the TMA unit fetches whole neighbour rows (bulk-gather kernel)
+  const bool bulk = use_bulk_gather(nvec, ldx4 * 4);
+  if (bulk) {
+    StreamArgs b = a;
+    b.R = g_bulk_rows < 1 ? 1 : (g_bulk_rows > 32 ? 32 : g_bulk_rows);
+    const bool tile = g_bulk_tile && b.ldy <= 32;
+    rc = launch_bulk<PUSH>(b, n_rows, tile, s);
+  } else {
+    rc = launch_stream<PUSH>(a, n_rows, s, tma);
+  }
   if (split && !rc) {
     // segments as single-row tasks into the partial buffer, then the ordered combine
     StreamArgs g = a;
@@ -524,7 +828,7 @@ static int stream_hop(const int *indptr, const int *indices, const float *vals, 
     g.R = 1;
     g.long_len = 0;
     g.peers.count = 0;
-    rc = launch_stream<false>(g, plan.cap_segs, s);
+    rc = bulk ? launch_bulk<false>(g, plan.cap_segs, false, s) : launch_stream<false>(g, plan.cap_segs, s);
     if (!rc) {
       const int blocks = (int)std::min<int64_t>(ceil_div64((int64_t)plan.cap_rows * 32, 256), 148 * 8);
       combine_long_rows_kernel<PUSH><<<blocks, 256, 0, s>>>(plan, (long long)a.chunks * 32, Y, ldy4, nvec, a.peers);
@@ -550,7 +854,7 @@ int spmm_csr_f32_impl(const int32_t *indptr, const int32_t *indices, const float
     const int nvec = (F + 3) / 4;
     const float4 *X4 = reinterpret_cast<const float4 *>(X);
     float4 *Y4 = reinterpret_cast<float4 *>(Y);
-    if (!accumulate && g_spmm_variant == 1 && nvec > 16)
+    if (!accumulate && g_spmm_variant == 1 && (nvec > 16 || use_bulk_gather(nvec, ldx)))
       return stream_hop<false>(indptr, indices, vals, n_rows, nnz, X4, ldx / 4, Y4, ldy / 4, nvec, nullptr, s);
     return accumulate ? dispatch_group<float4, true>(indptr, indices, vals, n_rows, X4, ldx / 4, Y4, ldy / 4, nvec, s)
                       : dispatch_group<float4, false>(indptr, indices, vals, n_rows, X4, ldx / 4, Y4, ldy / 4, nvec, s);
@@ -659,6 +963,12 @@ extern "C" int srg_set_tuning(const char *key, int64_t value) {
   else if (k == "gather_l2_64") g_gather_l2_64 = (int)value;
   else if (k == "long_row") g_long_row = (int)value;
   else if (k == "push_tma") g_push_tma = (int)value;
+  else if (k == "bulk_gather") g_bulk_gather = (int)value;
+  else if (k == "bulk_auto") g_bulk_auto = (int)value;
+  else if (k == "bulk_min") g_bulk_min = (int)value;
+  else if (k == "bulk_stages") g_bulk_stages = (int)value;
+  else if (k == "bulk_rows") g_bulk_rows = (int)value;
+  else if (k == "bulk_tile") g_bulk_tile = (int)value;
   else {
     set_err("set_tuning: unknown key '%s'", key);
     return SRG_ERR_INVALID;
@@ -711,6 +1021,35 @@ extern "C" int srg_spmm_csr_f32_push(const int32_t *indptr, const int32_t *indic
     pd.p[d] = reinterpret_cast<float4 *>(dests[d]) + dest_row0 * (ldy / 4);
   }
   // Y is only the origin the kernel measures row offsets from
+  return stream_hop<true>(indptr, indices, vals, n_rows, nnz, reinterpret_cast<const float4 *>(X), ldx / 4, pd.p[0],
+                          ldy / 4, nvec, &pd, as_stream(stream));
+}
+
+// the same with one row offset per destination: the peers' full buffers take the rows at dest_row0s[d] = the
+// rank's first global row, the caller's own n_rows x ldy copy of the hop (element k of the API's K+1 list) is
+// simply one more destination with offset 0 - no clone of the slice after the hop
+extern "C" int srg_spmm_csr_f32_push2(const int32_t *indptr, const int32_t *indices, const float *vals,
+                                      int64_t n_rows, int64_t nnz, const float *X, int64_t ldx,
+                                      float *const *dests, const int64_t *dest_row0s, int32_t n_dests, int64_t ldy,
+                                      int32_t F, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n_rows >= 0 && F >= 0, "spmm_push2: negative size");
+  SRG_REQUIRE(n_dests >= 1 && n_dests <= kMaxPeers, "spmm_push2: n_dests must be 1..%d", kMaxPeers);
+  if (n_rows == 0 || F == 0) return SRG_OK;
+  SRG_REQUIRE(indptr && X && dests && dest_row0s, "spmm_push2: NULL pointer");
+  SRG_REQUIRE((indices && vals) || nnz == 0, "spmm_push2: indices / vals are NULL but nnz says the matrix has entries");
+  SRG_REQUIRE(ldx >= F && ldy >= F && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)X % 16 == 0,
+              "spmm_push2: needs ld %% 4 == 0 and 16-byte aligned matrices");
+  const int nvec = (F + 3) / 4;
+  PeerDests pd;
+  pd.count = n_dests;
+  for (int d = 0; d < kMaxPeers; ++d) pd.p[d] = nullptr;
+  for (int d = 0; d < n_dests; ++d) {
+    SRG_REQUIRE(dests[d] && (uintptr_t)dests[d] % 16 == 0 && dest_row0s[d] >= 0, "spmm_push2: dests[%d] NULL, unaligned or negative offset", d);
+    SRG_REQUIRE((const float *)dests[d] != X, "spmm_push2: destination aliases the input");
+    pd.p[d] = reinterpret_cast<float4 *>(dests[d]) + dest_row0s[d] * (ldy / 4);
+  }
   return stream_hop<true>(indptr, indices, vals, n_rows, nnz, reinterpret_cast<const float4 *>(X), ldx / 4, pd.p[0],
                           ldy / 4, nvec, &pd, as_stream(stream));
 }
@@ -780,6 +1119,53 @@ extern "C" int srg_push_rows_f32(const float *src, int64_t n_rows, int64_t ld, f
   const long long n_vec = n_rows * (ld / 4);
   const int blocks = (int)std::min<int64_t>(ceil_div64(n_vec, 256), 148 * 4);
   push_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4 *>(src), n_vec, pd);
+  SRG_LAUNCHED();
+  return SRG_OK;
+}
+
+// ---- cross-rank ordering of the push hops without a collective ------------------------------------------------------
+// Every rank owns a small flag array in peer-mapped memory, one 32-bit slot per peer.  After a hop (stream order)
+// thread q of this one-block kernel publishes the hop's epoch into slot `my_slot` of peer q's array with a
+// system-scope release (the hop kernel's remote stores were performed before this kernel started) and then waits,
+// with system-scope acquires, until peer q's epoch shows up in the local array: when the kernel ends every peer has
+// finished writing this rank's next-hop buffer AND has finished reading the buffer the next hop overwrites.
+// A bounded wait (2 s of %globaltimer) turns a lost peer into an error flag instead of a hung GPU.
+__global__ void __launch_bounds__(32)
+peer_barrier_kernel(unsigned *local_flags, PeerDests peer_flags, int my_slot, unsigned epoch, int *timeout_flag) {
+  const int q = threadIdx.x;
+  if (q >= peer_flags.count) return;
+  unsigned *remote = reinterpret_cast<unsigned *>(peer_flags.p[q]) + my_slot;
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local_flags + q) : "memory");
+    if ((int)(v - epoch) >= 0) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) {
+      if (timeout_flag) atomicExch(timeout_flag, 1);
+      break;
+    }
+    __nanosleep(64);
+  }
+}
+
+extern "C" int srg_peer_barrier(void *local_flags, void *const *peer_flags, int32_t n_peers, int32_t my_slot,
+                                uint32_t epoch, int32_t *timeout_flag, void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(local_flags && peer_flags && n_peers >= 1 && n_peers <= kMaxPeers && my_slot >= 0 && my_slot < 32,
+              "peer_barrier: bad arguments");
+  PeerDests pd;
+  pd.count = n_peers;
+  for (int d = 0; d < kMaxPeers; ++d) pd.p[d] = nullptr;
+  for (int d = 0; d < n_peers; ++d) {
+    SRG_REQUIRE(peer_flags[d] != nullptr, "peer_barrier: peer_flags[%d] is NULL", d);
+    pd.p[d] = reinterpret_cast<float4 *>(peer_flags[d]);
+  }
+  peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(static_cast<unsigned *>(local_flags), pd, my_slot, epoch, timeout_flag);
   SRG_LAUNCHED();
   return SRG_OK;
 }

@@ -148,10 +148,39 @@ class DistState:
             else:
                 t = torch.zeros((self.n_pad, self.ld), dtype=torch.float32, device=self.device)
             self.full.append(t)
+        # cross-rank ordering of the push hops: "flags" = peer-mapped epoch slots + one tiny kernel per hop
+        # (srg_peer_barrier); "nccl" = a 4-byte all-reduce per hop (the round-1 form, kept for comparison)
+        self.fence = os.environ.get("SRG_DIST_FENCE", "flags") if self.p2p else "nccl"
+        self._epoch = 0
+        self._flag_ptrs = None
+        self._timeout = torch.zeros(1, dtype=torch.int32, device=self.device)
         if self.p2p:
             for b in range(2):
                 self.full[b].zero_()
+            fl = C.c_void_p()
+            _lib.check(self.lib.srg_ipc_alloc(C.byref(fl), 256))
+            self._raw.append(fl)
+            self._flags_local = fl
             torch.cuda.synchronize()
+            # zero the epoch slots before anybody can see the mapping
+            tmp = torch.zeros(64, dtype=torch.int32, device=self.device)
+            _lib.check(self.lib.srg_copy_async(fl, C.c_void_p(tmp.data_ptr()), 256, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+            torch.cuda.synchronize()
+            h = (C.c_ubyte * 64)()
+            _lib.check(self.lib.srg_ipc_get_handle(fl, h))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(h), group=group)
+            fptrs = []
+            for r in self.peers:
+                if r == rank:
+                    fptrs.append(fl.value)
+                else:
+                    q = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                    _lib.check(self.lib.srg_ipc_open(hb, C.byref(q)))
+                    self._opened.append(q)
+                    fptrs.append(q.value)
+            self._flag_ptrs = fptrs
             for b in range(2):
                 h = (C.c_ubyte * 64)()
                 _lib.check(self.lib.srg_ipc_get_handle(self._raw[b], h))
@@ -179,6 +208,24 @@ class DistState:
         h.__cuda_array_interface__ = {"shape": (self.n_pad, self.ld), "typestr": "<f4", "data": (int(ptr), False),
                                       "version": 2, "strides": None}
         return torch.as_tensor(h, device=self.device)
+
+    def peer_fence(self):
+        """Stream-ordered barrier among the ranks that exchange rows with this one (same feature slice)."""
+        from .device import _p, _stream_ptr
+        if self.world == 1:
+            return
+        if self.fence == "flags" and self._flag_ptrs is not None:
+            self._epoch += 1
+            ptrs = (C.c_void_p * len(self._flag_ptrs))(*self._flag_ptrs)
+            self._lib.check(self.lib.srg_peer_barrier(self._flags_local, ptrs, len(self._flag_ptrs), self.ri, self._epoch,
+                                                      _p(self._timeout), _stream_ptr(self.device)))
+        else:
+            self.dist.all_reduce(self._tick, group=self.group)
+
+    def check_fence(self):
+        """Host-side check (synchronises): a peer that never showed up at a flag barrier raises instead of hanging."""
+        if int(self._timeout.item()):
+            raise RuntimeError("multi-GPU hop: a peer did not reach the flag barrier within 2 s")
 
     def close(self):
         self.torch.cuda.synchronize()
@@ -220,12 +267,14 @@ class DeviceOps:
             return
         if pushed:
             # rows are already in every peer's buffer: order the hops across ranks on the stream
-            st.dist.all_reduce(st._tick, group=st.group)
+            st.peer_fence()
         else:
             view = st.full[i][st.rank * st.rows_per:(st.rank + 1) * st.rows_per]
             st.dist.all_gather_into_tensor(st.full[i], view, group=st.group)
 
-    def hop(self, local_norm, i_in, i_out):
+    def hop(self, local_norm, i_in, i_out, keep=None):
+        """One hop.  ``keep`` (push mode): an n_local x ld tensor that receives this rank's rows as one more
+        destination of the epilogue - the hop's element of the K+1 list, without a clone afterwards."""
         from . import _lib
         from .device import _p, _stream_ptr
         st = self.st
@@ -234,11 +283,17 @@ class DeviceOps:
             self._hop_copy(local_norm, xin, i_out)
             self._pushed = True
         elif st.mode == "push" and st.world > 1:
-            dests = (C.c_void_p * len(st.peers))(*st.peer_ptrs[i_out])
-            _lib.check(st.lib.srg_spmm_csr_f32_push(_p(local_norm.indptr), _p(local_norm.indices), _p(local_norm.data),
-                                                    st.n_local, local_norm.nnz_bound, _p(xin), st.ld, dests,
-                                                    len(st.peers), st.row0, st.ld, st.f_loc,
-                                                    _stream_ptr(st.device)))
+            ptrs = list(st.peer_ptrs[i_out])
+            row0s = [st.row0] * len(ptrs)
+            if keep is not None:
+                assert keep.shape == (st.n_local, st.ld) and keep.is_contiguous()
+                ptrs.append(keep.data_ptr())
+                row0s.append(0)
+            dests = (C.c_void_p * len(ptrs))(*ptrs)
+            offs = (C.c_int64 * len(ptrs))(*row0s)
+            _lib.check(st.lib.srg_spmm_csr_f32_push2(_p(local_norm.indptr), _p(local_norm.indices), _p(local_norm.data),
+                                                     st.n_local, local_norm.nnz_bound, _p(xin), st.ld, dests, offs,
+                                                     len(ptrs), st.ld, st.f_loc, _stream_ptr(st.device)))
             self._pushed = True
         else:
             out = st.full[i_out][st.row0:st.row0 + st.n_local]
@@ -329,15 +384,17 @@ def propagate_device(st: DistState, local_norm, x_local_padded, k, keep_hops=Tru
     st._x_event = None
     if st.world > 1:
         if st.mode in ("push", "copy"):
-            st.dist.all_reduce(st._tick, group=st.group)      # every rank's rows have landed everywhere
+            st.peer_fence()                                    # every rank's rows have landed everywhere
         else:
             ops.exchange(cur)
-    out = [ops.snapshot_local(cur)] if keep_hops else []
+    fused_keep = keep_hops and st.mode == "push" and st.world > 1
+    out = [x_local_padded if fused_keep else ops.snapshot_local(cur)] if keep_hops else []
     for _ in range(k):
-        ops.hop(local_norm, cur, nxt)
+        keep = torch.empty((st.n_local, st.ld), dtype=torch.float32, device=st.device) if fused_keep else None
+        ops.hop(local_norm, cur, nxt, keep=keep)
         ops.exchange(nxt, pushed=(st.mode in ("push", "copy") and st.world > 1))
         if keep_hops:
-            out.append(ops.snapshot_local(nxt))
+            out.append(keep if fused_keep else ops.snapshot_local(nxt))
         cur, nxt = nxt, cur
     if not keep_hops:
         out = [ops.snapshot_local(cur)]

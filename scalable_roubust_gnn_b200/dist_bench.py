@@ -40,6 +40,15 @@ def _bind_to_gpu_numa_node(torch, local_rank):
         return None
 
 
+def default_feat_groups(world, mode):
+    """Row blocks x feature slices of the default grid.  A pure row partition makes every rank RECEIVE (P-1)/P of X
+    per hop; from 4 GPUs on that exchange is as long as the local hop, so the features are split in two (the exchange
+    volume halves, the gathered rows become 224 bytes wide - the shape the bulk-gather kernel is built for)."""
+    if mode not in ("push", "copy", "push_tma"):
+        return "1"
+    return "2" if world >= 4 else "1"
+
+
 def run(args, workloads, metric, unit, emit):
     import torch
     import torch.distributed as dist
@@ -63,12 +72,12 @@ def run(args, workloads, metric, unit, emit):
     t0 = time.perf_counter()
     # 8 GPUs are NVLink-ingress bound with a pure row partition (every rank receives 7/8 of X per hop):
     # a 4 x 2 grid (row blocks x feature slices) halves the exchange volume
-    pf = int(os.environ.get("SRG_FEAT_GROUPS", "2" if (world >= 8 and mode in ("push", "copy", "push_tma")) else "1"))
+    pf = int(os.environ.get("SRG_FEAT_GROUPS", default_feat_groups(world, mode)))
     st = sdist.DistState(n, f, world, rank, mode=mode, feat_groups=pf)
     s, e = st.row0, st.row0 + st.n_local
     f_loc = st.f_loc
     gen = os.environ.get("SRG_GEN", "device" if args.workload.startswith("papers100M") else "host")
-    a_loc_host = x_loc_host = None
+    a_loc_host = x_loc_host = ag_inputs = p1_inputs = None
     if gen == "device":
         # config 5: every rank builds ITS rows of the scrambled R-MAT graph on its GPU (counter-based
         # generator, csrc/coo.cu) and its slice of the procedural features; nothing of this size ever
@@ -87,9 +96,15 @@ def run(args, workloads, metric, unit, emit):
     else:
         a = synth.uniform_graph(n, nnz)        # every rank regenerates the same graph (fixed seed) ...
         a_loc_host = sdist.shard_rows(a, s, e)  # ... and keeps its row slice
-        x_loc_host = np.ascontiguousarray(synth.features(n, f)[s:e, st.f0:st.f1])
+        x_full = synth.features(n, f)
+        x_loc_host = np.ascontiguousarray(x_full[s:e, st.f0:st.f1])
         nnz_hat = a.nnz + n
-        del a
+        # the plain row partition + NCCL all-gather (the north-star collective) is timed beside the push grid
+        ag_rows_per, ag_starts = sdist.row_partition(n, world)
+        ag_s, ag_e = int(ag_starts[rank]), int(ag_starts[rank + 1])
+        ag_inputs = (sdist.shard_rows(a, ag_s, ag_e), np.ascontiguousarray(x_full[ag_s:ag_e])) if mode != "allgather" else None
+        p1_inputs = (a, x_full) if rank == 0 else None      # rank 0 re-runs the whole graph on ONE GPU for the bitwise check
+        del a, x_full
         a_loc = dev.upload_csr(a_loc_host)
         x_loc = dev.pack_features(torch.from_numpy(np.ascontiguousarray(x_loc_host)).cuda())
     torch.cuda.synchronize()
@@ -100,19 +115,21 @@ def run(args, workloads, metric, unit, emit):
     def step():
         sdist.start_input_exchange(st, x_loc)          # overlaps the normalisation
         norm, flags = sdist.dist_sym_norm(st, a_loc, 0.5)
-        sdist.propagate_device(st, norm, x_loc, k, keep_hops=False)
-        return flags
+        # keep_hops=True: the step produces what GraphOp.propagate returns - all K+1 matrices (the rank's rows)
+        hops = sdist.propagate_device(st, norm, x_loc, k, keep_hops=True)
+        return flags, hops
 
     from bench import ClockSampler  # noqa: E402  (bench.py is the entry script)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                        # before the warm-up: its start-up must not hit timed steps
     for _ in range(args.warmup):
-        flags = step()
+        flags, _ = step()
     torch.cuda.synchronize()
     assert int(flags.item()) & ~_lib.SRG_FLAG_WEIGHTED == 0, f"normalisation flags {int(flags.item())}"
     step()
     torch.cuda.synchronize()
+    st.check_fence()
     sampler.lines.clear()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -158,12 +175,21 @@ def run(args, workloads, metric, unit, emit):
     del norm_p
 
     verify = None
+    allgather = None
     if gen == "device":
         verify = _verify_device_generated(st, a_loc, x_loc, k, f, sdist, synth, torch, dist)
         e2e_line = None
     else:
+        verify = _verify_against_one_gpu(st, a_loc, x_loc, k, f, p1_inputs, dev, sdist, torch, dist)
+        p1_inputs = None
+        if ag_inputs is not None and os.environ.get("SRG_BENCH_ALLGATHER", "1") != "0":
+            allgather = _allgather_baseline(args, n, f, k, world, rank, ag_inputs, dev, sdist, torch, dist)
+        ag_inputs = None
         e2e_line = _e2e(args, st, a_loc_host, x_loc_host, k, f_loc, lib, dev, sdist, torch, dist)
+    st.check_fence()
     clocks = sampler.stop() if rank == 0 else None
+    if allgather is not None:
+        probe["allgather_mode"] = allgather
     _emit_line(args, st, metric, unit, emit, mode, pf, world, rank, n, nnz_hat, f, f_loc, k, t_step, launches, e2e_line,
                clocks, verify, gen, probe)
     st.close()
@@ -206,6 +232,73 @@ def _overlap_probe(st, norm, lib, torch):
     else:
         res["exchange_only_ms"] = 0.0
     return res
+
+
+def _verify_against_one_gpu(st, a_loc, x_loc, k, f, p1_inputs, dev, sdist, torch, dist):
+    """Multi-GPU parity inside the bench run: every rank's rows of EVERY hop are gathered on rank 0 and compared,
+    bit for bit, with the same propagation run on rank 0's GPU alone over the whole graph (the single-GPU path the
+    parity tests pin to the oracle).  Returns the verify block on rank 0."""
+    sdist.start_input_exchange(st, x_loc)
+    norm, _ = sdist.dist_sym_norm(st, a_loc, 0.5)
+    hops = sdist.propagate_device(st, norm, x_loc, k, keep_hops=True)
+    torch.cuda.synchronize()
+    want = None
+    if st.rank == 0:
+        a, x = p1_inputs
+        norm1, flags1, _ = dev.sym_norm(dev.upload_csr(a), 0.5)
+        want = dev.propagate(norm1, dev.pack_features(torch.from_numpy(x).cuda()), f, k)
+        torch.cuda.synchronize()
+    ok, rows_checked = True, 0
+    slot = torch.zeros((st.rows_per, st.ld), dtype=torch.float32, device="cuda")
+    gathered = torch.empty((st.world * st.rows_per, st.ld), dtype=torch.float32, device="cuda")
+    for j in range(1, k + 1):
+        slot.zero_()
+        slot[:st.n_local].copy_(hops[j])
+        dist.all_gather_into_tensor(gathered, slot)
+        if st.rank == 0:
+            for r in range(st.world):
+                ri, ci = sdist.grid_coords(r, st.world, st.feat_groups)
+                r0, r1 = int(st.starts[ri]), int(st.starts[ri + 1])
+                c0, c1 = sdist.feature_slice(f, st.feat_groups, ci)
+                got = gathered[r * st.rows_per: r * st.rows_per + (r1 - r0), :c1 - c0]
+                ok = ok and bool(torch.equal(got, want[j][r0:r1, c0:c1]))
+                rows_checked += r1 - r0
+    del hops, gathered, slot, want
+    if st.rank != 0:
+        return None
+    return {"bitwise_vs_p1": ok, "hops_compared": k, "rows_compared_per_hop": rows_checked // max(k, 1),
+            "how": "every rank's rows of every hop gathered on rank 0 and compared with torch.equal against the same "
+                   "propagation run on rank 0's GPU alone over the whole graph"}
+
+
+def _allgather_baseline(args, n, f, k, world, rank, ag_inputs, dev, sdist, torch, dist):
+    """The same step with the plain row partition and one NCCL all-gather per hop (SRG_DIST_MODE=allgather)."""
+    a_host, x_host = ag_inputs
+    st2 = sdist.DistState(n, f, world, rank, mode="allgather", feat_groups=1)
+    a_d = dev.upload_csr(a_host)
+    x_d = dev.pack_features(torch.from_numpy(x_host).cuda())
+
+    def step2():
+        sdist.start_input_exchange(st2, x_d)
+        norm, _ = sdist.dist_sym_norm(st2, a_d, 0.5)
+        return sdist.propagate_device(st2, norm, x_d, k, keep_hops=True)
+
+    for _ in range(3):
+        step2()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(1, min(args.steps, 5))
+    e0.record()
+    for _ in range(reps):
+        step2()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    st2.close()
+    return {"ms_per_step": float(ms.item()), "partition": f"{world} contiguous row blocks x 1",
+            "exchange": "ncclAllGather of the previous hop's slices before each hop"}
 
 
 def _verify_device_generated(st, a_loc, x_loc, k, f, sdist, synth, torch, dist):
@@ -305,7 +398,7 @@ def _emit_line(args, st, metric, unit, emit, mode, pf, world, rank, n, nnz_hat, 
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(args, n, nnz_hat, f, k), exchange=mode,
                                partition=f"{st.n_row_blocks} contiguous row blocks x {pf} feature slices"),
-                "roofline": {"bound": "hbm", "kernel": {"push": "spmm_stream_kernel (push epilogue)", "push_tma": "spmm_stream_kernel (TMA bulk-store push epilogue)", "copy": "spmm hop in row chunks + copy-engine exchange"}.get(mode, "spmm_stream_kernel + ncclAllGather"),
+                "roofline": {"bound": "hbm", "kernel": ("spmm_bulk_kernel (TMA row gathers, push epilogue)" if (mode in ("push", "push_tma") and st.ld <= 64) else None) or {"push": "spmm_stream_kernel (push epilogue)", "push_tma": "spmm_stream_kernel (TMA bulk-store push epilogue)", "copy": "spmm hop in row chunks + copy-engine exchange"}.get(mode, "spmm_stream_kernel + ncclAllGather"),
                              "achieved": bg / world / hop_s / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": bg / world / hop_s / 1e9 / peak, "peak_source": peak_src, "traffic": None,
                              "note": "per GPU, step time / K (includes the sharded normalisation and the exchange)",

@@ -100,6 +100,61 @@ def test_spmm_bit_exact_all_widths(f):
     np.testing.assert_array_equal(y, want)
 
 
+@pytest.mark.parametrize("f", [4, 13, 32, 50, 56, 64, 100, 128])
+@pytest.mark.parametrize("stages,rows,tile", [(2, 32, 0), (3, 16, 0), (2, 32, 1), (4, 5, 1), (2, 1, 0)])
+def test_spmm_bulk_gather_bit_exact(f, stages, rows, tile):
+    """The bulk-gather (TMA row copy) form of the hop kernel: same FMA chain, so bit for bit the C oracle, for every
+    pipeline depth / rows per task / output path, on a graph with empty rows and rows spanning several chunks."""
+    n = 900
+    rng = np.random.default_rng(f + stages)
+    adj = sym_graph(n, 9000, f).tolil()
+    adj[5, :] = 0                                   # empty rows (a caller-supplied matrix may have them)
+    adj[6, :] = 0
+    adj[n - 1, :] = 0
+    adj[40, ::3] = 1.5                              # 300 entries: ten chunks
+    adj = sp.csr_matrix(adj)
+    adj.data = (adj.data * rng.standard_normal(adj.nnz)).astype(np.float32)
+    adj.eliminate_zeros()
+    assert (np.diff(adj.indptr) == 0).sum() >= 3
+    x = rng.standard_normal((n, f)).astype(np.float32)
+    want = oracle.spmm_hop(adj, x)
+    a = dev.upload_csr(adj)
+    xp = dev.pack_features(torch.from_numpy(x).cuda())
+    for key, val in (("bulk_gather", 1), ("bulk_stages", stages), ("bulk_rows", rows), ("bulk_tile", tile)):
+        _lib.set_tuning(key, val)
+    try:
+        y = dev.unpack_features(dev.spmm(a, xp, f), f).cpu().numpy()
+    finally:
+        for key, val in (("bulk_gather", -1), ("bulk_stages", 2), ("bulk_rows", 32), ("bulk_tile", 0)):
+            _lib.set_tuning(key, val)
+    np.testing.assert_array_equal(y, want)
+
+
+def test_spmm_bulk_gather_long_rows_and_rmat():
+    """Hub rows: the segment tasks and the ordered combine run through the bulk kernel as well; short rows stay
+    bit-identical, hub rows agree to fp32 rounding (segment sums), exactly as in the LDGSTS form."""
+    n, f = 20000, 50
+    adj = oracle.sym_norm(_hub_graph(n, 5, 5000, 3), 0.5)
+    lens = np.diff(adj.indptr)
+    x = np.random.default_rng(0).standard_normal((n, f)).astype(np.float32)
+    want = oracle.spmm_hop(adj, x)
+    a = dev.upload_csr(adj.astype(np.float32))
+    xp = dev.pack_features(torch.from_numpy(x).cuda())
+    res = {}
+    for tile in (0, 1):
+        _lib.set_tuning("bulk_gather", 1)
+        _lib.set_tuning("bulk_tile", tile)
+        try:
+            res[tile] = dev.unpack_features(dev.spmm(a, xp, f), f).cpu().numpy()
+        finally:
+            _lib.set_tuning("bulk_gather", -1)
+            _lib.set_tuning("bulk_tile", 0)
+    short = lens <= 1024
+    np.testing.assert_array_equal(res[0], res[1])                # the output path changes no bit
+    np.testing.assert_array_equal(res[0][short], want[short])
+    np.testing.assert_allclose(res[0][~short], want[~short], rtol=1e-5, atol=1e-5)
+
+
 @pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
 def test_spmm_bit_exact_vs_compiled_reference():
     adj = oracle.sym_norm(sym_graph(5000, 60000, 3), 0.5)

@@ -354,6 +354,7 @@ rows_fill_fast_kernel(const int *__restrict__ indptr, const int *__restrict__ in
                       const int *__restrict__ flags, int force_vals) {
   if (*flags & kFatal) return;  // defective input: the slot arithmetic below would run out of bounds
   const bool weighted = (DT != SRG_VAL_ONES) && (force_vals || (*flags & kWeighted));
+  if (!weighted && !force_vals) return;   // all-ones input: tile_fill_unweighted_kernel wrote A~
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -389,6 +390,239 @@ rows_fill_fast_kernel(const int *__restrict__ indptr, const int *__restrict__ in
       if (!weighted) degree[k.a] = (len == 0) ? 0.0 : (double)(len - 1) + diag;  // 1.0 entries: exact
     }
   }
+}
+
+// ---- row-tile kernels: the fast path of canonical input ---------------------------------------------------------------
+// A block takes kTileRows consecutive rows; their entries are one contiguous range of the CSR arrays, which the
+// block streams with coalesced loads, ONE THREAD PER ENTRY.  The row of an entry comes from a binary search over the
+// tile's row pointers in shared memory (8 steps, no global traffic), so there is no per-row overhead, no lane idles
+// on short rows, and a power-law hub is simply a longer loop of the block that owns it.  Three passes:
+//   tile_count   validation flags (sortedness, index range, weights, explicit zeros) + row length of A~ = A + I
+//   tile_fill    unweighted input: every kept entry's slot follows from its input slot; degree = len + 1 (exact)
+//   tile_values  R[a,b] = (A~[b,a] * dl[a]) * dr[b] on a symmetric A~, PPR blend, fp32 rounding; symmetry is CHECKED
+//                by two 64-bit sums of a hash of (min, max[, value]) over the upper and over the lower entries
+//                (equal for every symmetric matrix; a mismatch raises SRG_FLAG_ASYMMETRIC and the caller retries
+//                through the general transpose path, which needs no symmetry).  The exact per-entry mirror lookup
+//                of round 1 (entry_values_kernel) stays available: srg_set_tuning("exact_sym_check", 1).
+constexpr int kTileRows = 256;
+static int g_exact_sym_check = 0;
+void set_exact_sym_check(int v) { g_exact_sym_check = v; }
+
+// largest t in [0, nr) with rp[t] <= j  (rows may be empty: the LAST of equal pointers owns the entry)
+__device__ __forceinline__ int tile_row_of(const int *rp, int nr, int j) {
+  int lo = 0, hi = nr;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (rp[mid] <= j) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kTileRows)
+tile_count_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, const void *__restrict__ data,
+                  long long n_rows, long long row0, long long n_cols, int *__restrict__ rowlen,
+                  int *__restrict__ flags) {
+  __shared__ int rp[kTileRows + 1];
+  __shared__ int hdk[kTileRows];   // bit 0: the row stores its diagonal, bit 1: A~'s diagonal cancels (value -1)
+  const long long r0 = (long long)blockIdx.x * kTileRows;
+  const int nr = (int)min((long long)kTileRows, n_rows - r0);
+  for (int t = threadIdx.x; t <= nr; t += kTileRows) rp[t] = indptr[r0 + t];
+  hdk[threadIdx.x] = 0;
+  __syncthreads();
+  const int e0 = rp[0], e1 = rp[nr];
+  int fl = 0;
+  constexpr int U = 4;   // independent loads in flight per thread
+  for (int j0 = e0 + threadIdx.x; j0 < e1; j0 += U * kTileRows) {
+    int b[U], pb[U];
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = j0 + u * kTileRows;
+      b[u] = (j < e1) ? ld_stream_i32(indices + j) : 0;
+      pb[u] = (j < e1 && j > e0) ? __ldg(indices + j - 1) : -1;
+      v[u] = (DT != SRG_VAL_ONES && j < e1) ? ValLoad<DT>::at(data, j) : 1.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = j0 + u * kTileRows;
+      if (j >= e1) break;
+      const int t = tile_row_of(rp, nr, j);
+      const int ag = (int)(r0 + t + row0);
+      if (j > rp[t] && b[u] <= pb[u]) fl |= SRG_FLAG_UNSORTED;
+      if (b[u] < 0 || b[u] >= n_cols) fl |= SRG_FLAG_BAD_INDEX;
+      if (DT != SRG_VAL_ONES && v[u] != 1.0) fl |= (v[u] == 0.0) ? (kWeighted | SRG_FLAG_EXPLICIT_ZERO) : kWeighted;
+      if (b[u] == ag) hdk[t] = 1 | ((__dadd_rn(v[u], 1.0) == 0.0) ? 2 : 0);
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nr) {
+    const int t = threadIdx.x, h = hdk[t];
+    rowlen[r0 + t] = (rp[t + 1] - rp[t]) - (h & 1) + ((h & 2) ? 0 : 1);
+  }
+  raise_flags(flags, fl);
+}
+
+// unweighted canonical input (all stored values 1.0): A~ = A + I written entry-parallel.  A~'s row a has
+// len + 1 - hd entries (hd: A stores its diagonal, which becomes 2.0), so hd follows from the two row pointers.
+__global__ void __launch_bounds__(kTileRows)
+tile_fill_unweighted_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, long long n_rows,
+                            long long row0, const int *__restrict__ at_indptr, int *__restrict__ at_indices,
+                            double *__restrict__ degree, const int *__restrict__ flags, int dt_can_be_weighted) {
+  const int f = *flags;
+  if (f & kFatal) return;                                 // defective input: nothing is written
+  if (dt_can_be_weighted && (f & kWeighted)) return;      // weighted: rows_fill_fast_kernel does it
+  __shared__ int rp[kTileRows + 1];
+  __shared__ int ap[kTileRows + 1];
+  const long long r0 = (long long)blockIdx.x * kTileRows;
+  const int nr = (int)min((long long)kTileRows, n_rows - r0);
+  for (int t = threadIdx.x; t <= nr; t += kTileRows) {
+    rp[t] = indptr[r0 + t];
+    ap[t] = at_indptr[r0 + t];
+  }
+  __syncthreads();
+  const int e0 = rp[0], e1 = rp[nr];
+  constexpr int U = 4;
+  for (int j0 = e0 + threadIdx.x; j0 < e1; j0 += U * kTileRows) {
+    int bb[U], pbb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = j0 + u * kTileRows;
+      bb[u] = (j < e1) ? ld_stream_i32(indices + j) : 0;
+      pbb[u] = (j < e1 && j > e0) ? __ldg(indices + j - 1) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = j0 + u * kTileRows;
+      if (j >= e1) break;
+      const int b = bb[u];
+      const int t = tile_row_of(rp, nr, j);
+      const int ag = (int)(r0 + t + row0);
+      const int s = rp[t], e = rp[t + 1];
+      const int hd = ((ap[t + 1] - ap[t]) == (e - s)) ? 1 : 0;
+      const int pos = ap[t] + (j - s) + ((b > ag) ? 1 - hd : 0);
+      at_indices[pos] = b;                                  // b == ag: the stored diagonal keeps its slot
+      if (!hd) {
+        // the new diagonal entry sits between the last b < ag and the first b > ag
+        if (b > ag && (j == s || pbb[u] < ag)) at_indices[pos - 1] = ag;
+        else if (b < ag && j == e - 1) at_indices[pos + 1] = ag;
+      }
+    }
+  }
+  if ((int)threadIdx.x < nr) {
+    const int t = threadIdx.x;
+    const int len = rp[t + 1] - rp[t];
+    if (len == 0) at_indices[ap[t]] = (int)(r0 + t + row0);
+    degree[r0 + t] = (double)(len + 1);                   // len ones + the added 1.0 (or 2.0 on a stored diagonal)
+  }
+}
+
+__device__ __forceinline__ unsigned hash32(unsigned x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+
+__global__ void __launch_bounds__(kTileRows)
+tile_values_kernel(long long n_rows, long long row0, long long n_cols, const int *__restrict__ at_indptr,
+                   const int *__restrict__ at_indices, const double *__restrict__ at_val,
+                   const double *__restrict__ degree, const double *__restrict__ dl, const double *__restrict__ dr,
+                   double one_minus_alpha, double alpha, int use_ppr, int check_sym, double *__restrict__ val64,
+                   float *__restrict__ val32, int *__restrict__ flags, unsigned long long *__restrict__ tri_counts) {
+  if (*flags & kFatal) return;  // A~ was not written
+  const bool weighted = (*flags & kWeighted) != 0;
+  __shared__ int ap[kTileRows + 1];
+  __shared__ double dla[kTileRows];
+  __shared__ double dgv[kTileRows];   // unweighted: value of the row's diagonal entry (1.0 or 2.0)
+  const long long r0 = (long long)blockIdx.x * kTileRows;
+  const int nr = (int)min((long long)kTileRows, n_rows - r0);
+  for (int t = threadIdx.x; t <= nr; t += kTileRows) ap[t] = at_indptr[r0 + t];
+  __syncthreads();
+  if ((int)threadIdx.x < nr) {
+    const int t = threadIdx.x;
+    dla[t] = dl[r0 + t + row0];
+    dgv[t] = degree[r0 + t] - (double)(ap[t + 1] - ap[t] - 1);   // exact: 1.0 or 2.0
+  }
+  __syncthreads();
+  const int e0 = ap[0], e1 = ap[nr];
+  int fl = 0;
+  unsigned long long s1 = 0, s2 = 0;   // upper - lower, two independent sums (wrap-around arithmetic)
+  constexpr int U = 4;
+  for (int p0 = e0 + threadIdx.x; p0 < e1; p0 += U * kTileRows) {
+    int bb[U];
+    double drb[U], atv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * kTileRows;
+      bb[u] = (p < e1) ? ld_stream_i32(at_indices + p) : 0;
+      atv[u] = (weighted && p < e1) ? at_val[p] : 1.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) drb[u] = (p0 + u * kTileRows < e1) ? __ldg(dr + bb[u]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+    const int p = p0 + u * kTileRows;
+    if (p >= e1) break;
+    const int b = bb[u];
+    const int t = tile_row_of(ap, nr, p);
+    const int ag = (int)(r0 + t + row0);
+    const double vt = weighted ? atv[u] : ((b == ag) ? dgv[t] : 1.0);
+    double v = __dmul_rn(__dmul_rn(vt, dla[t]), drb[u]);
+    if (use_ppr) {
+      v = __dmul_rn(one_minus_alpha, v);
+      if (b == ag) v = __dadd_rn(v, alpha);
+    }
+    if (v == 0.0) fl |= SRG_FLAG_ZERO_PRODUCT;
+    if (val64) val64[p] = v;
+    if (val32) val32[p] = __double2float_rn(v);
+    if (check_sym && b != ag) {
+      const unsigned lo = (unsigned)min(ag, b), hi = (unsigned)max(ag, b);
+      unsigned ha = hash32(lo * 0x9e3779b1u + hash32(hi));
+      unsigned hb = hash32(hi * 0x85ebca6bu ^ hash32(lo + 0x27d4eb2fu));
+      if (weighted) {
+        const unsigned long long vb = (unsigned long long)__double_as_longlong(vt);
+        ha = hash32(ha ^ (unsigned)vb);
+        hb = hash32(hb ^ (unsigned)(vb >> 32));
+      }
+      const unsigned long long h1 = ((unsigned long long)ha << 32) | hb;
+      const unsigned long long h2 = (unsigned long long)ha * (unsigned long long)(hb | 1u);
+      if (b > ag) {
+        s1 += h1;
+        s2 += h2;
+      } else {
+        s1 -= h1;
+        s2 -= h2;
+      }
+    }
+    }
+  }
+  if (check_sym) {
+    __shared__ unsigned long long red[2][kTileRows / 32];
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+      red[0][threadIdx.x >> 5] = s1;
+      red[1][threadIdx.x >> 5] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long t1 = 0, t2 = 0;
+      for (int w = 0; w < kTileRows / 32; ++w) {
+        t1 += red[0][w];
+        t2 += red[1][w];
+      }
+      if (t1) atomicAdd(tri_counts, t1);
+      if (t2) atomicAdd(tri_counts + 1, t2);
+    }
+  }
+  raise_flags(flags, fl);
 }
 
 // weighted graphs only: degree = A~.sum(1) in numpy's add.reduceat order, one thread per row
@@ -538,7 +772,8 @@ entry_values_kernel(long long n_rows, long long row0, long long n_cols, const in
 }
 
 __global__ void tri_compare_kernel(const unsigned long long *tri_counts, int *flags) {
-  if (tri_counts[0] != 0ULL) atomicOr(flags, SRG_FLAG_ASYMMETRIC);  // #upper != #lower
+  // exact check: #upper != #lower; hash check: sum over the upper entries != sum over the lower entries
+  if (tri_counts[0] != 0ULL || tri_counts[1] != 0ULL) atomicOr(flags, SRG_FLAG_ASYMMETRIC);
 }
 
 // defective input: hand back an EMPTY matrix (all row pointers 0) so that a caller who launches
@@ -594,12 +829,9 @@ int rows_count_launch(const int32_t *indptr, const int32_t *indices, const void 
     SRG_LAUNCHED();
     return SRG_OK;
   }
-  PlanHolder h;
-  int rc = make_plan(indptr, n_rows, nnz, s, &h);
-  if (rc) return rc;
-  SRG_DT_SWITCH(dt, (rows_count_fast_kernel<DTT><<<norm_grid(n_rows), 256, 0, s>>>(indptr, indices, data, n_rows, row0, n_cols, h.p, rowlen, flags)));
+  (void)nnz;
+  SRG_DT_SWITCH(dt, (tile_count_kernel<DTT><<<(unsigned)ceil_div64(n_rows, kTileRows), kTileRows, 0, s>>>(indptr, indices, data, n_rows, row0, n_cols, rowlen, flags)));
   SRG_LAUNCHED();
-  free_plan(&h, s);
   return SRG_OK;
 }
 
@@ -613,6 +845,14 @@ int rows_fill_launch(const int32_t *indptr, const int32_t *indices, const void *
     SRG_LAUNCHED();
     return SRG_OK;
   }
+  if (!force_vals) {
+    // all-ones input (known from the dtype, or found at run time by the count pass): entry-parallel tile kernel
+    tile_fill_unweighted_kernel<<<(unsigned)ceil_div64(n_rows, kTileRows), kTileRows, 0, s>>>(
+        indptr, indices, n_rows, row0, at_indptr, at_indices, degree, flags, dt != SRG_VAL_ONES ? 1 : 0);
+    SRG_LAUNCHED();
+    if (dt == SRG_VAL_ONES) return SRG_OK;
+  }
+  // weighted (or forced) values: warp-per-task kernels, which leave at once when the flags say "all ones"
   PlanHolder h;
   int rc = make_plan(indptr, n_rows, nnz, s, &h);
   if (rc) return rc;
@@ -732,6 +972,20 @@ extern "C" int srg_norm_values_rows_csr(int32_t *at_indptr, const int32_t *at_in
   if (check_symmetry) {
     SRG_CUDA(cudaMallocAsync(&tri, 2 * sizeof(unsigned long long), s));
     SRG_CUDA(cudaMemsetAsync(tri, 0, 2 * sizeof(unsigned long long), s));
+  }
+  if (!g_exact_sym_check) {
+    tile_values_kernel<<<(unsigned)ceil_div64(n_rows, kTileRows), kTileRows, 0, s>>>(
+        n_rows, row0, n_cols, at_indptr, at_indices, at_val, degree_rows, pow_left, pow_right, 1.0 - ppr_alpha, ppr_alpha,
+        ppr_alpha >= 0.0 ? 1 : 0, check_symmetry, out_val_f64, out_val_f32, flags, tri);
+    SRG_LAUNCHED();
+    void_on_fatal_kernel<<<(unsigned)ceil_div64(n_rows + 1, 256), 256, 0, s>>>(flags, at_indptr, n_rows + 1);
+    SRG_LAUNCHED();
+    if (check_symmetry) {
+      tri_compare_kernel<<<1, 1, 0, s>>>(tri, flags);
+      SRG_LAUNCHED();
+      cudaFreeAsync(tri, s);
+    }
+    return SRG_OK;
   }
   // 256-bit window loads need a 32-byte aligned index array with >= 16 entries of capacity (nnz)
   const int win_max = ((uintptr_t)at_indices % 32 == 0 && nnz >= 16) ? (int)((nnz - 16) & ~7LL) : -1;

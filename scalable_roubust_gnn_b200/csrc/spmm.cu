@@ -35,6 +35,7 @@
 #include "common.cuh"
 
 namespace srg {
+void set_exact_sym_check(int v);   // norm.cu
 
 // ---- tuning knobs (srg_set_tuning) -----------------------------------------------------------------
 static int g_spmm_variant = 1;   // 1 = stream kernel where it applies, 0 = group kernel everywhere
@@ -181,6 +182,34 @@ struct PeerDests {
   int count;
 };
 
+// long rows (power-law hubs): the kernel that meets a row longer than long_len registers it here (device-side plan,
+// no separate pass over indptr) and leaves it to the segment tasks that run next in stream order
+struct LongPlan {
+  int *counts;     // [0] number of long rows, [1] number of segments
+  int *row;        // [cap_rows]   row id
+  int *first;      // [cap_rows]   first segment of the row
+  int *nseg;       // [cap_rows]   its segment count
+  int *seg_lo;     // [cap_segs]
+  int *seg_hi;     // [cap_segs]
+  float *partial;  // [cap_segs x ldp] segment sums
+  int cap_rows, cap_segs;
+  void *base;      // the single allocation behind all of the above
+};
+
+__device__ __forceinline__ void plan_add_long_row(const LongPlan &p, int row, int st, int ed, int L) {
+  const int ns = (ed - st + L - 1) / L;
+  const int i = atomicAdd(p.counts, 1);
+  const int s0 = atomicAdd(p.counts + 1, ns);
+  if (i >= p.cap_rows || s0 + ns > p.cap_segs) return;  // cannot happen: caps come from nnz / L
+  p.row[i] = row;
+  p.first[i] = s0;
+  p.nseg[i] = ns;
+  for (int k = 0; k < ns; ++k) {
+    p.seg_lo[s0 + k] = st + k * L;
+    p.seg_hi[s0 + k] = min(ed, st + (k + 1) * L);
+  }
+}
+
 struct StreamArgs {
   const int *row_lo;         // first entry of row r   (CSR: indptr)
   const int *row_hi;         // one past the last entry (CSR: indptr + 1); rows of one task are contiguous
@@ -194,6 +223,7 @@ struct StreamArgs {
   long long ldy;             // in float4
   int nvec, chunks, R;
   int long_len;              // rows longer than this are left to the segment kernels (0: none are)
+  LongPlan plan;             // where such rows are registered (long_len > 0)
   PeerDests peers;
 };
 
@@ -213,13 +243,11 @@ __device__ __forceinline__ void store_row(const StreamArgs &a, float4 *yrow, con
 // (`tile`, kStreamWarps * R rows of ldy float4) instead of global memory; the kernel's epilogue sends the tile.
 template <int B, bool L2_64, bool PUSH, bool TMA>
 __device__ __forceinline__ void stream_warp_task(const StreamArgs &a, float4 *smem4, float4 *tile, const int w,
-                                                 const int lane) {
+                                                 const int lane, const long long task, const long long n_rows) {
   constexpr int S = 2 * B;
   constexpr unsigned FULL = 0xffffffffu;
   const unsigned ring = (unsigned)__cvta_generic_to_shared(smem4 + (size_t)w * S * 32 + lane);
 
-  const long long n_rows = a.n_rows_dev ? min((long long)*a.n_rows_dev, a.n_rows) : a.n_rows;
-  const long long task = (long long)blockIdx.x * kStreamWarps + w;
   const long long rblock = task / a.chunks;
   const int chunk = (int)(task - rblock * a.chunks);
   const long long r0 = rblock * a.R;
@@ -245,7 +273,10 @@ __device__ __forceinline__ void stream_warp_task(const StreamArgs &a, float4 *sm
     // kernels (A^ has a full diagonal, so empty rows only occur for caller-supplied matrices)
     for (int r = 0; r < nr; ++r) {
       const int st = __shfl_sync(FULL, prev_end, r), ed = __shfl_sync(FULL, my_end, r);
-      if (a.long_len > 0 && ed - st > a.long_len) continue;
+      if (a.long_len > 0 && ed - st > a.long_len) {
+        if (lane == 0 && chunk == 0) plan_add_long_row(a.plan, (int)(r0 + r), st, ed, a.long_len);
+        continue;
+      }
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int j = st; j < ed; ++j) {
         const int c = __ldg(a.indices + j);
@@ -348,7 +379,16 @@ __global__ void __launch_bounds__(kStreamWarps * 32) spmm_stream_kernel(const St
     for (int i = threadIdx.x; i < tile_vec; i += kStreamWarps * 32) tile[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
   }
-  stream_warp_task<B, L2_64, PUSH, TMA>(a, smem4, tile, w, lane);
+  {
+    // the main launch has one task per warp; the segment launch (row count only known on the device) runs a
+    // bounded grid whose warps stride over the tasks
+    const long long n_rows = a.n_rows_dev ? min((long long)*a.n_rows_dev, a.n_rows) : a.n_rows;
+    const long long n_tasks = ((n_rows + a.R - 1) / a.R) * a.chunks;
+    for (long long task = (long long)blockIdx.x * kStreamWarps + w; task < n_tasks; task += (long long)gridDim.x * kStreamWarps) {
+      stream_warp_task<B, L2_64, PUSH, TMA>(a, smem4, tile, w, lane, task, n_rows);
+      if (TMA) break;
+    }
+  }
   if (TMA) {
     // generic-proxy writes of the tile -> visible to the async proxy, then ONE bulk store per destination:
     // the exchange leaves the SM through the TMA unit, not through the load/store path the gathers use
@@ -442,9 +482,10 @@ __global__ void __launch_bounds__(128) spmm_bulk_kernel(const StreamArgs a, cons
   const unsigned mb = tile + (TILE ? (unsigned)a.R * (unsigned)a.ldy * 16u : 0u);
 
   const long long n_rows = a.n_rows_dev ? min((long long)*a.n_rows_dev, a.n_rows) : a.n_rows;
-  const long long task = (long long)blockIdx.x * wpb + w;
+  const long long n_tasks = (n_rows + a.R - 1) / a.R;
+  // the main launch has one task per warp; the segment launch (count only known on the device) strides
+  for (long long task = (long long)blockIdx.x * wpb + w; task < n_tasks; task += (long long)gridDim.x * wpb) {
   const long long r0 = task * a.R;
-  if (r0 >= n_rows) return;
   const int nr = (int)min((long long)a.R, n_rows - r0);
   const bool active = lane < a.nvec;
   const float4 *Xc = a.X + lane;
@@ -482,6 +523,7 @@ __global__ void __launch_bounds__(128) spmm_bulk_kernel(const StreamArgs a, cons
     for (int r = 0; r < nr; ++r) {
       const int st = __shfl_sync(FULL, prev_end, r), ed = __shfl_sync(FULL, my_end, r);
       const bool skip = a.long_len > 0 && ed - st > a.long_len;
+      if (skip && lane == 0) plan_add_long_row(a.plan, (int)(r0 + r), st, ed, a.long_len);
       if (!skip) {
         for (int j = st; j < ed; ++j) {
           const int c = __ldg(a.indices + j);
@@ -590,6 +632,11 @@ __global__ void __launch_bounds__(128) spmm_bulk_kernel(const StreamArgs a, cons
       if (issued < n_chunks) SRG_BULK_ISSUE();
     }
 #undef SRG_BULK_ISSUE
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb + 8u * s) : "memory");
+    }
+    __syncwarp();
   }
 #undef SRG_BULK_ROW_DONE
 
@@ -615,11 +662,13 @@ __global__ void __launch_bounds__(128) spmm_bulk_kernel(const StreamArgs a, cons
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
+    __syncwarp();
   }
+  }  // task loop
 }
 
 template <int S, bool PUSH, bool TILE>
-static int launch_bulk_t(const StreamArgs &a, int64_t max_rows, cudaStream_t s) {
+static int launch_bulk_t(const StreamArgs &a, int64_t max_rows, cudaStream_t s, int64_t grid_cap) {
   const size_t per_warp = bulk_warp_smem(S, a.nvec, a.R, a.ldy, TILE);
   int wpb = 4;
   while (wpb > 1 && per_warp * wpb > 113 * 1024) wpb >>= 1;   // at least two blocks per SM when a warp's share allows it
@@ -629,7 +678,8 @@ static int launch_bulk_t(const StreamArgs &a, int64_t max_rows, cudaStream_t s) 
     return SRG_ERR_RANGE;
   }
   const int64_t tasks = ceil_div64(max_rows, a.R);
-  const int64_t blocks = ceil_div64(tasks, wpb);
+  int64_t blocks = ceil_div64(tasks, wpb);
+  if (grid_cap > 0) blocks = std::min(blocks, grid_cap);
   if (blocks > 2147483647LL) {
     set_err("spmm: grid too large (%lld blocks)", (long long)blocks);
     return SRG_ERR_RANGE;
@@ -642,11 +692,11 @@ static int launch_bulk_t(const StreamArgs &a, int64_t max_rows, cudaStream_t s) 
 }
 
 template <bool PUSH>
-static int launch_bulk(const StreamArgs &a, int64_t max_rows, bool tile, cudaStream_t s) {
+static int launch_bulk(const StreamArgs &a, int64_t max_rows, bool tile, cudaStream_t s, int64_t grid_cap = 0) {
   const int S = g_bulk_stages < 2 ? 2 : (g_bulk_stages > 4 ? 4 : g_bulk_stages);
 #define SRG_CASE(SS)                                                     \
   if (S == SS)                                                           \
-    return tile ? launch_bulk_t<SS, PUSH, true>(a, max_rows, s) : launch_bulk_t<SS, PUSH, false>(a, max_rows, s)
+    return tile ? launch_bulk_t<SS, PUSH, true>(a, max_rows, s, grid_cap) : launch_bulk_t<SS, PUSH, false>(a, max_rows, s, grid_cap)
   SRG_CASE(2);
   SRG_CASE(3);
   SRG_CASE(4);
@@ -655,38 +705,6 @@ static int launch_bulk(const StreamArgs &a, int64_t max_rows, bool tile, cudaStr
 }
 
 // ---- long rows: device-side plan, segment tasks, ordered combine ------------------------------------------
-struct LongPlan {
-  int *counts;     // [0] number of long rows, [1] number of segments
-  int *row;        // [cap_rows]   row id
-  int *first;      // [cap_rows]   first segment of the row
-  int *nseg;       // [cap_rows]   its segment count
-  int *seg_lo;     // [cap_segs]
-  int *seg_hi;     // [cap_segs]
-  float *partial;  // [cap_segs x ldp] segment sums
-  int cap_rows, cap_segs;
-  void *base;      // the single allocation behind all of the above
-};
-
-__global__ void __launch_bounds__(256)
-plan_long_rows_kernel(const int *__restrict__ indptr, long long n_rows, int L, LongPlan p) {
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_rows) return;
-  const int st = indptr[r], ed = indptr[r + 1];
-  const int len = ed - st;
-  if (len <= L) return;
-  const int ns = (len + L - 1) / L;
-  const int i = atomicAdd(p.counts, 1);
-  const int s0 = atomicAdd(p.counts + 1, ns);
-  if (i >= p.cap_rows || s0 + ns > p.cap_segs) return;  // cannot happen: caps come from nnz / L
-  p.row[i] = (int)r;
-  p.first[i] = s0;
-  p.nseg[i] = ns;
-  for (int k = 0; k < ns; ++k) {
-    p.seg_lo[s0 + k] = st + k * L;
-    p.seg_hi[s0 + k] = min(ed, st + (k + 1) * L);
-  }
-}
-
 template <bool PUSH>
 __global__ void __launch_bounds__(256)
 combine_long_rows_kernel(LongPlan p, long long ldp4, float4 *Y, long long ldy, int nvec, PeerDests peers) {
@@ -748,10 +766,13 @@ static int launch_stream_t(const StreamArgs &a, int64_t blocks, cudaStream_t s) 
   return SRG_OK;
 }
 
+constexpr int64_t kSegGridCap = 148 * 8;   // segment launches: bounded grid, warps stride over the device-side task count
+
 template <bool PUSH>
-static int launch_stream(const StreamArgs &a, int64_t max_rows, cudaStream_t s, bool tma = false) {
+static int launch_stream(const StreamArgs &a, int64_t max_rows, cudaStream_t s, bool tma = false, int64_t grid_cap = 0) {
   const int64_t tasks = ceil_div64(max_rows, a.R) * a.chunks;
-  const int64_t blocks = ceil_div64(tasks, kStreamWarps);
+  int64_t blocks = ceil_div64(tasks, kStreamWarps);
+  if (grid_cap > 0) blocks = std::min(blocks, grid_cap);
   if (blocks > 2147483647LL) {
     set_err("spmm: grid too large (%lld blocks)", (long long)blocks);
     return SRG_ERR_RANGE;
@@ -798,11 +819,11 @@ static int stream_hop(const int *indptr, const int *indices, const float *vals, 
   a.long_len = split ? L : 0;
   LongPlan plan;
   int rc;
+  memset(&a.plan, 0, sizeof(a.plan));
   if (split) {
     const int64_t ldp = (int64_t)a.chunks * 32 * 4;  // floats per partial row (whole chunks)
     if ((rc = alloc_long_plan(nnz, L, ldp, &plan, s))) return rc;
-    plan_long_rows_kernel<<<(unsigned)ceil_div64(n_rows, 256), 256, 0, s>>>(indptr, n_rows, L, plan);
-    SRG_LAUNCHED();
+    a.plan = plan;   // the hop kernel registers the long rows it meets
   }
   // bulk-store form of the push hop: one row chunk per task (nvec <= 32), whole rows of <= 32 float4, tile <= 32 KB
   const bool tma = PUSH && g_push_tma && a.chunks == 1 && a.ldy <= 32 && a.R <= 8 && a.peers.count > 0;
@@ -828,7 +849,7 @@ static int stream_hop(const int *indptr, const int *indices, const float *vals, 
     g.R = 1;
     g.long_len = 0;
     g.peers.count = 0;
-    rc = bulk ? launch_bulk<false>(g, plan.cap_segs, false, s) : launch_stream<false>(g, plan.cap_segs, s);
+    rc = bulk ? launch_bulk<false>(g, plan.cap_segs, false, s, kSegGridCap) : launch_stream<false>(g, plan.cap_segs, s, false, kSegGridCap);
     if (!rc) {
       const int blocks = (int)std::min<int64_t>(ceil_div64((int64_t)plan.cap_rows * 32, 256), 148 * 8);
       combine_long_rows_kernel<PUSH><<<blocks, 256, 0, s>>>(plan, (long long)a.chunks * 32, Y, ldy4, nvec, a.peers);
@@ -963,6 +984,7 @@ extern "C" int srg_set_tuning(const char *key, int64_t value) {
   else if (k == "gather_l2_64") g_gather_l2_64 = (int)value;
   else if (k == "long_row") g_long_row = (int)value;
   else if (k == "push_tma") g_push_tma = (int)value;
+  else if (k == "exact_sym_check") set_exact_sym_check((int)value);
   else if (k == "bulk_gather") g_bulk_gather = (int)value;
   else if (k == "bulk_auto") g_bulk_auto = (int)value;
   else if (k == "bulk_min") g_bulk_min = (int)value;

@@ -372,29 +372,40 @@ def start_input_exchange(st: DistState, x_local_padded):
     st._x_event = ev
 
 
-def propagate_device(st: DistState, local_norm, x_local_padded, k, keep_hops=True):
+def propagate_device(st: DistState, local_norm, x_local_padded, k, keep_hops=True, marks=None):
     """K hops on the device; returns the list of local hop slices (or only the last when not keep_hops).
-    If start_input_exchange was called for this input, only its completion is awaited here."""
+    If start_input_exchange was called for this input, only its completion is awaited here.
+    ``marks``: optional list that receives (label, recorded CUDA event) pairs after each stage (bench breakdown)."""
     import torch
     ops = DeviceOps(st)
     cur, nxt = 0, 1
+
+    def mark(label):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((label, ev))
     if st._x_event is None:
         start_input_exchange(st, x_local_padded)
     torch.cuda.current_stream(st.device).wait_event(st._x_event)
     st._x_event = None
+    mark("input exchange landed")
     if st.world > 1:
         if st.mode in ("push", "copy"):
             st.peer_fence()                                    # every rank's rows have landed everywhere
         else:
             ops.exchange(cur)
+    mark("fence")
     fused_keep = keep_hops and st.mode == "push" and st.world > 1
     out = [x_local_padded if fused_keep else ops.snapshot_local(cur)] if keep_hops else []
-    for _ in range(k):
+    for j in range(k):
         keep = torch.empty((st.n_local, st.ld), dtype=torch.float32, device=st.device) if fused_keep else None
         ops.hop(local_norm, cur, nxt, keep=keep)
+        mark(f"hop {j + 1} kernel")
         ops.exchange(nxt, pushed=(st.mode in ("push", "copy") and st.world > 1))
         if keep_hops:
             out.append(keep if fused_keep else ops.snapshot_local(nxt))
+        mark(f"hop {j + 1} fence")
         cur, nxt = nxt, cur
     if not keep_hops:
         out = [ops.snapshot_local(cur)]

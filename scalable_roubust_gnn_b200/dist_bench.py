@@ -146,6 +146,25 @@ def run(args, workloads, metric, unit, emit):
     t_step = float(ms.item()) * 1e-3 / args.steps
     launches = _lib.launch_count() - launches0
 
+    # ---- where the step time goes: one more step with an event after every stage (rank 0's clock) ----------------
+    torch.cuda.synchronize()
+    dist.barrier()
+    marks = []
+    ev_s = torch.cuda.Event(enable_timing=True)
+    ev_s.record()
+    sdist.start_input_exchange(st, x_loc)
+    norm_b, _ = sdist.dist_sym_norm(st, a_loc, 0.5)
+    ev_n = torch.cuda.Event(enable_timing=True)
+    ev_n.record()
+    marks.append(("normalisation (incl. degree all-gather)", ev_n))
+    sdist.propagate_device(st, norm_b, x_loc, k, keep_hops=True, marks=marks)
+    torch.cuda.synchronize()
+    stages, prev = [], ev_s
+    for label, ev in marks:
+        stages.append([label, round(prev.elapsed_time(ev), 4)])
+        prev = ev
+    del norm_b
+
     # ---- overlap probe (SURVEY 8d multi-GPU reporting): the local hop alone, the exchange alone, the fused hop ---
     # collectives (normalisation all-gather, barrier, the hops' ticks) run unconditionally on every rank; only the
     # purely local timing sits inside the try, so a failure cannot leave another rank waiting
@@ -154,14 +173,21 @@ def run(args, workloads, metric, unit, emit):
     sdist.propagate_device(st, norm_p, x_loc, 1, keep_hops=False)
     torch.cuda.synchronize()
     dist.barrier()
+    # the fused hop (kernel with the push epilogue + the fence that orders it across ranks), back to back on
+    # the two buffers - the input exchange and the normalisation are not part of this figure
+    ops_p = sdist.DeviceOps(st)
+    pushed = st.mode in ("push", "copy") and world > 1
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hop_reps = 6
+    ops_p.hop(norm_p, 0, 1)
+    ops_p.exchange(1, pushed=pushed)
     e0.record()
-    hop_reps = 3
-    for _ in range(hop_reps):
-        sdist.propagate_device(st, norm_p, x_loc, k, keep_hops=False)
+    for i in range(hop_reps):
+        ops_p.hop(norm_p, i & 1 ^ 1, i & 1)
+        ops_p.exchange(i & 1, pushed=pushed)
     e1.record()
     torch.cuda.synchronize()
-    t_hops = torch.tensor([e0.elapsed_time(e1) / (hop_reps * k)], device="cuda")
+    t_hops = torch.tensor([e0.elapsed_time(e1) / hop_reps], device="cuda")
     dist.all_reduce(t_hops, op=dist.ReduceOp.MAX)
     probe = {"hop_fused_ms": float(t_hops.item())}
     dist.barrier()
@@ -185,9 +211,12 @@ def run(args, workloads, metric, unit, emit):
         if ag_inputs is not None and os.environ.get("SRG_BENCH_ALLGATHER", "1") != "0":
             allgather = _allgather_baseline(args, n, f, k, world, rank, ag_inputs, dev, sdist, torch, dist)
         ag_inputs = None
-        e2e_line = _e2e(args, st, a_loc_host, x_loc_host, k, f_loc, lib, dev, sdist, torch, dist)
+        e2e_line = None
+        if os.environ.get("SRG_BENCH_E2E", "1") != "0":
+            e2e_line = _e2e(args, st, a_loc_host, x_loc_host, k, f_loc, lib, dev, sdist, torch, dist)
     st.check_fence()
     clocks = sampler.stop() if rank == 0 else None
+    probe["stages_ms_rank0"] = stages
     if allgather is not None:
         probe["allgather_mode"] = allgather
     _emit_line(args, st, metric, unit, emit, mode, pf, world, rank, n, nnz_hat, f, f_loc, k, t_step, launches, e2e_line,
@@ -416,5 +445,6 @@ def _emit_line(args, st, metric, unit, emit, mode, pf, world, rank, n, nnz_hat, 
             line["overlap"] = probe
         if verify is not None:
             line["verify"] = verify
+        if gen == "device":
             line["data"] = "synthetic (device-generated shards; no host copy exists, so no host end-to-end leg)"
         emit(line)

@@ -49,7 +49,7 @@ static int g_bulk_gather = -1;   // -1: bulk (TMA) row gathers for rows of <= g_
 static int g_bulk_auto = 64;     // widest row (floats, padded) the automatic choice hands to the bulk kernel
 static int g_bulk_min = 32;      // ... and the narrowest (a bulk copy of < 128 bytes is not worth a TMA request)
 static int g_bulk_stages = 2;    // chunks of 32 neighbour rows in flight per warp (2..4)
-static int g_bulk_rows = 32;     // rows per warp task of the bulk kernel (1..32)
+static int g_bulk_rows = 8;      // rows per warp task of the bulk kernel (1..32); 8 measured best (profiles/r02_hop_shard_sweep.log)
 static int g_bulk_tile = 0;      // 1: finished rows are staged in shared memory and leave as ONE bulk store per destination
 
 // ---- vector abstraction for the group kernel: float4 fast path, float scalar path ------------------

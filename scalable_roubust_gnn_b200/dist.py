@@ -137,6 +137,7 @@ class DistState:
         self._x_event = None
         self.p2p = mode in ("push", "copy") and world > 1     # peer-mapped full buffers
         self.comm = torch.cuda.Stream(device=self.device)     # copy mode: the DMA exchange stream
+        self.peer_streams = [torch.cuda.Stream(device=self.device) for _ in self.peers]   # input exchange: one per peer
         self.n_chunks = int(os.environ.get("SRG_COPY_CHUNKS", "4"))   # copy mode: row chunks per hop
         nbytes = self.n_pad * self.ld * 4
         for _ in range(2):
@@ -272,13 +273,21 @@ class DeviceOps:
             view = st.full[i][st.rank * st.rows_per:(st.rank + 1) * st.rows_per]
             st.dist.all_gather_into_tensor(st.full[i], view, group=st.group)
 
-    def hop(self, local_norm, i_in, i_out, keep=None):
+    def hop(self, local_norm, i_in, i_out, keep=None, last=False):
         """One hop.  ``keep`` (push mode): an n_local x ld tensor that receives this rank's rows as one more
-        destination of the epilogue - the hop's element of the K+1 list, without a clone afterwards."""
+        destination of the epilogue - the hop's element of the K+1 list, without a clone afterwards.
+        ``last``: nobody gathers from the result of the final hop, so with a ``keep`` destination it is written there
+        only (no exchange, no fence)."""
         from . import _lib
         from .device import _p, _stream_ptr
         st = self.st
         xin = st.full[i_in]
+        if last and keep is not None and st.mode == "push" and st.world > 1:
+            _lib.check(st.lib.srg_spmm_csr_f32(_p(local_norm.indptr), _p(local_norm.indices), _p(local_norm.data),
+                                               st.n_local, local_norm.nnz_bound, _p(xin), st.ld, _p(keep), st.ld, st.f_loc,
+                                               _stream_ptr(st.device)))
+            self._pushed = False
+            return
         if st.mode == "copy" and st.world > 1:
             self._hop_copy(local_norm, xin, i_out)
             self._pushed = True
@@ -352,14 +361,27 @@ def start_input_exchange(st: DistState, x_local_padded):
     from .device import _p
     side = st.side
     side.wait_stream(torch.cuda.current_stream(st.device))
+    input_copy = st.world > 1 and (st.mode == "copy" or (st.mode == "push" and os.environ.get("SRG_INPUT_XCHG", "copy") == "copy"))
     with torch.cuda.stream(side):
-        if st.mode == "copy" and st.world > 1:
+        if st.p2p:
+            # the previous call's last hop (which ends without a fence) may still be reading the buffer this
+            # exchange overwrites on a slower peer: order against it here, on the side stream, so that the
+            # normalisation on the main stream does not wait for anybody
+            st.peer_fence()
+        if input_copy:
+            # copy engines, one stream per peer so the copies run side by side: the input exchange overlaps the
+            # normalisation without taking SMs from it
             st.full[0][st.row0:st.row0 + st.n_local].copy_(x_local_padded)
             src = st.full[0].data_ptr() + st.row0 * st.ld * 4
+            ready = torch.cuda.Event()
+            ready.record(side)
             for blk, peer in enumerate(st.peers):
                 if peer != st.rank:
+                    ps = st.peer_streams[blk]
+                    ps.wait_event(ready)
                     _lib.check(st.lib.srg_copy_async(C.c_void_p(st.peer_ptrs[0][blk] + st.row0 * st.ld * 4), C.c_void_p(src),
-                                                     st.n_local * st.ld * 4, C.c_void_p(side.cuda_stream)))
+                                                     st.n_local * st.ld * 4, C.c_void_p(ps.cuda_stream)))
+                    side.wait_stream(ps)
         elif st.mode == "push" and st.world > 1:
             dests = (C.c_void_p * len(st.peers))(*st.peer_ptrs[0])
             _lib.check(st.lib.srg_push_rows_f32(_p(x_local_padded), st.n_local, st.ld, dests, len(st.peers), st.row0,
@@ -400,8 +422,13 @@ def propagate_device(st: DistState, local_norm, x_local_padded, k, keep_hops=Tru
     out = [x_local_padded if fused_keep else ops.snapshot_local(cur)] if keep_hops else []
     for j in range(k):
         keep = torch.empty((st.n_local, st.ld), dtype=torch.float32, device=st.device) if fused_keep else None
-        ops.hop(local_norm, cur, nxt, keep=keep)
+        last = fused_keep and j == k - 1
+        ops.hop(local_norm, cur, nxt, keep=keep, last=last)
         mark(f"hop {j + 1} kernel")
+        if last:
+            # a later call reuses the full buffers: its first fence orders them against this hop's reads
+            out.append(keep)
+            break
         ops.exchange(nxt, pushed=(st.mode in ("push", "copy") and st.world > 1))
         if keep_hops:
             out.append(keep if fused_keep else ops.snapshot_local(nxt))

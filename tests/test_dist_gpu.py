@@ -138,14 +138,8 @@ def test_two_gpus_nccl_fence_equals_flag_fence(tmp_path, monkeypatch):
     np.testing.assert_array_equal(res["nccl"], res["flags"])
 
 
-# hardware status (round 1): push ran on 4 GPUs; copy / push_tma ran on 2 GPUs (tests above) and 8 GPUs (bench), their
-# 4-GPU grid runs are opt-in until they have been seen green once (SRG_TEST_UNVALIDATED=1)
-_UNVALIDATED = pytest.mark.skipif(not os.environ.get("SRG_TEST_UNVALIDATED"),
-                                  reason="not yet run on 4 GPUs; set SRG_TEST_UNVALIDATED=1")
-
-
 @pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs 4 GPUs")
-@pytest.mark.parametrize("mode", ["push", pytest.param("copy", marks=_UNVALIDATED), pytest.param("push_tma", marks=_UNVALIDATED)])
+@pytest.mark.parametrize("mode", ["push", "copy", "push_tma"])
 @pytest.mark.parametrize("rmat", [False, True])
 def test_four_gpus_row_by_feature_grid(tmp_path, rmat, mode):
     """2 row blocks x 2 feature slices (the layout used at 8 GPUs to halve the exchange): every rank's

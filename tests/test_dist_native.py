@@ -70,10 +70,8 @@ def _worker(rank, world, n, f, k, out_dir):
     nd.close()
 
 
-# hardware status (round 1): world size 1 ran on a B200; the 2-GPU run is opt-in until it has been seen green once
 @pytest.mark.gpu
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.skipif(not os.environ.get("SRG_TEST_UNVALIDATED"), reason="not yet run on 2 GPUs; set SRG_TEST_UNVALIDATED=1")
 def test_native_handle_two_gpus_bitwise_equal_one_gpu(tmp_path):
     world, n, f, k = 2, 50001, 100, 3
     mp.spawn(_worker, args=(world, n, f, k, str(tmp_path)), nprocs=world, join=True)

@@ -50,6 +50,7 @@ static int g_bulk_auto = 64;     // widest row (floats, padded) the automatic ch
 static int g_bulk_min = 32;      // ... and the narrowest (a bulk copy of < 128 bytes is not worth a TMA request)
 static int g_bulk_stages = 2;    // chunks of 32 neighbour rows in flight per warp (2..4)
 static int g_bulk_rows = 8;      // rows per warp task of the bulk kernel (1..32); 8 measured best (profiles/r02_hop_shard_sweep.log)
+static int g_push_rows_blocks = 148;   // grid of the input-exchange kernel (one block per SM by default)
 static int g_bulk_tile = 0;      // 1: finished rows are staged in shared memory and leave as ONE bulk store per destination
 
 // ---- vector abstraction for the group kernel: float4 fast path, float scalar path ------------------
@@ -985,6 +986,7 @@ extern "C" int srg_set_tuning(const char *key, int64_t value) {
   else if (k == "long_row") g_long_row = (int)value;
   else if (k == "push_tma") g_push_tma = (int)value;
   else if (k == "exact_sym_check") set_exact_sym_check((int)value);
+  else if (k == "push_rows_blocks") g_push_rows_blocks = (int)std::max<int64_t>(1, value);
   else if (k == "bulk_gather") g_bulk_gather = (int)value;
   else if (k == "bulk_auto") g_bulk_auto = (int)value;
   else if (k == "bulk_min") g_bulk_min = (int)value;
@@ -1112,14 +1114,28 @@ extern "C" int srg_apply_feature_mask_f32(const float *x, int64_t ld_x, const in
 
 // copy this rank's rows into the same rows of every destination buffer (peer stores over NVLink):
 // the input exchange of the multi-GPU path without a collective
+// One block per SM, 8 independent 16-byte loads in flight per thread: enough bytes in flight to fill the NVLink
+// egress (~2 us x 700 GB/s) while leaving most of every SM to the normalisation kernels this exchange overlaps.
 __global__ void __launch_bounds__(256)
 push_rows_kernel(const float4 *__restrict__ src, long long n_vec, PeerDests peers) {
+  constexpr int U = 8;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-    const float4 v = src[i];
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_vec; i0 += stride * U) {
+    float4 v[U];
 #pragma unroll
-    for (int d = 0; d < kMaxPeers; ++d)
-      if (d < peers.count) peers.p[d][i] = v;
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n_vec) v[u] = ld_gather_f4(src + i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n_vec) {
+#pragma unroll
+        for (int d = 0; d < kMaxPeers; ++d)
+          if (d < peers.count) peers.p[d][i] = v[u];
+      }
+    }
   }
 }
 
@@ -1139,7 +1155,7 @@ extern "C" int srg_push_rows_f32(const float *src, int64_t n_rows, int64_t ld, f
     pd.p[d] = reinterpret_cast<float4 *>(dests[d]) + dest_row0 * (ld / 4);
   }
   const long long n_vec = n_rows * (ld / 4);
-  const int blocks = (int)std::min<int64_t>(ceil_div64(n_vec, 256), 148 * 4);
+  const int blocks = (int)std::min<int64_t>(ceil_div64(n_vec, 256 * 8), g_push_rows_blocks);
   push_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4 *>(src), n_vec, pd);
   SRG_LAUNCHED();
   return SRG_OK;

@@ -405,108 +405,177 @@ rows_fill_fast_kernel(const int *__restrict__ indptr, const int *__restrict__ in
 //                through the general transpose path, which needs no symmetry).  The exact per-entry mirror lookup
 //                of round 1 (entry_values_kernel) stays available: srg_set_tuning("exact_sym_check", 1).
 constexpr int kTileRows = 256;
+constexpr int kHubLen = 8192;      // rows with more entries leave the tile loop and are spread over a whole grid
+constexpr int kHubBlocks = 148 * 4;
 static int g_exact_sym_check = 0;
 void set_exact_sym_check(int v) { g_exact_sym_check = v; }
 
-// largest t in [0, nr) with rp[t] <= j  (rows may be empty: the LAST of equal pointers owns the entry)
-__device__ __forceinline__ int tile_row_of(const int *rp, int nr, int j) {
+// rows longer than kHubLen (power-law hubs): registered by the tile kernel that owns them, processed by a second
+// launch whose blocks ALL stride over the hub's entries (a 10^6-entry row would otherwise be one block's loop)
+struct HubList {
+  int *count;   // device counter
+  int *rows;    // [cap] local row ids
+  int cap;
+};
+
+// largest t in [0, nr) with cp[t] <= c  (rows may be empty / skipped: the LAST of equal pointers owns the entry)
+__device__ __forceinline__ int tile_row_of(const int *cp, int nr, int c) {
   int lo = 0, hi = nr;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
-    if (rp[mid] <= j) lo = mid; else hi = mid;
+    if (cp[mid] <= c) lo = mid; else hi = mid;
   }
   return lo;
+}
+
+// Shared prologue of the tile kernels: row pointers of the tile in rp[], compacted pointers (hub rows contribute no
+// entries) in cp[]; hub rows are registered when `hubs` is given.  Returns the number of compacted entries.
+__device__ __forceinline__ int tile_setup(const int *__restrict__ ptr, long long r0, int nr, int *rp, int *cp,
+                                          const HubList *hubs) {
+  for (int t = threadIdx.x; t <= nr; t += kTileRows) rp[t] = ptr[r0 + t];
+  __syncthreads();
+  int len = 0;
+  if ((int)threadIdx.x < nr) {
+    len = rp[threadIdx.x + 1] - rp[threadIdx.x];
+    if (len > kHubLen) {
+      if (hubs) {
+        const int i = atomicAdd(hubs->count, 1);
+        if (i < hubs->cap) hubs->rows[i] = (int)(r0 + threadIdx.x);
+      }
+      len = 0;
+    }
+  }
+  int total;
+  const int excl = block_excl_scan<kTileRows>(len, &total);
+  cp[threadIdx.x] = excl;
+  if (threadIdx.x == 0) cp[kTileRows] = total;
+  __syncthreads();
+  if ((int)threadIdx.x >= nr) cp[threadIdx.x] = total;   // rows beyond the tile: empty
+  __syncthreads();
+  return total;
+}
+
+// ---- count ------------------------------------------------------------------------------------------------------------
+template <int DT>
+__device__ __forceinline__ void count_entry(int j, int b, int pb, double v, int row_start, int ag, long long n_cols,
+                                            int &fl, int &diag_bits) {
+  if (j > row_start && b <= pb) fl |= SRG_FLAG_UNSORTED;
+  if (b < 0 || b >= n_cols) fl |= SRG_FLAG_BAD_INDEX;
+  if (DT != SRG_VAL_ONES && v != 1.0) fl |= (v == 0.0) ? (kWeighted | SRG_FLAG_EXPLICIT_ZERO) : kWeighted;
+  if (b == ag) diag_bits = 1 | ((__dadd_rn(v, 1.0) == 0.0) ? 2 : 0);
 }
 
 template <int DT>
 __global__ void __launch_bounds__(kTileRows)
 tile_count_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, const void *__restrict__ data,
                   long long n_rows, long long row0, long long n_cols, int *__restrict__ rowlen,
-                  int *__restrict__ flags) {
+                  int *__restrict__ flags, HubList hubs) {
   __shared__ int rp[kTileRows + 1];
+  __shared__ int cp[kTileRows + 1];
   __shared__ int hdk[kTileRows];   // bit 0: the row stores its diagonal, bit 1: A~'s diagonal cancels (value -1)
   const long long r0 = (long long)blockIdx.x * kTileRows;
   const int nr = (int)min((long long)kTileRows, n_rows - r0);
-  for (int t = threadIdx.x; t <= nr; t += kTileRows) rp[t] = indptr[r0 + t];
   hdk[threadIdx.x] = 0;
-  __syncthreads();
-  const int e0 = rp[0], e1 = rp[nr];
+  const int total = tile_setup(indptr, r0, nr, rp, cp, &hubs);
   int fl = 0;
   constexpr int U = 4;   // independent loads in flight per thread
-  for (int j0 = e0 + threadIdx.x; j0 < e1; j0 += U * kTileRows) {
-    int b[U], pb[U];
+  for (int c0 = threadIdx.x; c0 < total; c0 += U * kTileRows) {
+    int b[U], pb[U], tt[U], jj[U];
     double v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int j = j0 + u * kTileRows;
-      b[u] = (j < e1) ? ld_stream_i32(indices + j) : 0;
-      pb[u] = (j < e1 && j > e0) ? __ldg(indices + j - 1) : -1;
-      v[u] = (DT != SRG_VAL_ONES && j < e1) ? ValLoad<DT>::at(data, j) : 1.0;
+      const int c = c0 + u * kTileRows;
+      tt[u] = (c < total) ? tile_row_of(cp, nr, c) : 0;
+      jj[u] = rp[tt[u]] + (c - cp[tt[u]]);
+      b[u] = (c < total) ? ld_stream_i32(indices + jj[u]) : 0;
+      pb[u] = (c < total && jj[u] > rp[tt[u]]) ? __ldg(indices + jj[u] - 1) : -1;
+      v[u] = (DT != SRG_VAL_ONES && c < total) ? ValLoad<DT>::at(data, jj[u]) : 1.0;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int j = j0 + u * kTileRows;
-      if (j >= e1) break;
-      const int t = tile_row_of(rp, nr, j);
-      const int ag = (int)(r0 + t + row0);
-      if (j > rp[t] && b[u] <= pb[u]) fl |= SRG_FLAG_UNSORTED;
-      if (b[u] < 0 || b[u] >= n_cols) fl |= SRG_FLAG_BAD_INDEX;
-      if (DT != SRG_VAL_ONES && v[u] != 1.0) fl |= (v[u] == 0.0) ? (kWeighted | SRG_FLAG_EXPLICIT_ZERO) : kWeighted;
-      if (b[u] == ag) hdk[t] = 1 | ((__dadd_rn(v[u], 1.0) == 0.0) ? 2 : 0);
+      if (c0 + u * kTileRows >= total) break;
+      int bits = 0;
+      count_entry<DT>(jj[u], b[u], pb[u], v[u], rp[tt[u]], (int)(r0 + tt[u] + row0), n_cols, fl, bits);
+      if (bits) hdk[tt[u]] = bits;
     }
   }
   __syncthreads();
   if ((int)threadIdx.x < nr) {
     const int t = threadIdx.x, h = hdk[t];
-    rowlen[r0 + t] = (rp[t + 1] - rp[t]) - (h & 1) + ((h & 2) ? 0 : 1);
+    rowlen[r0 + t] = (rp[t + 1] - rp[t]) - (h & 1) + ((h & 2) ? 0 : 1);   // hub rows: as if no diagonal were stored
   }
   raise_flags(flags, fl);
 }
 
-// unweighted canonical input (all stored values 1.0): A~ = A + I written entry-parallel.  A~'s row a has
-// len + 1 - hd entries (hd: A stores its diagonal, which becomes 2.0), so hd follows from the two row pointers.
+template <int DT>
+__global__ void __launch_bounds__(256)
+hub_count_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, const void *__restrict__ data,
+                 long long row0, long long n_cols, int *__restrict__ rowlen, int *__restrict__ flags, HubList hubs) {
+  const int nh = min(*hubs.count, hubs.cap);
+  int fl = 0;
+  for (int h = 0; h < nh; ++h) {
+    const int a = hubs.rows[h];
+    const int s = indptr[a], e = indptr[a + 1];
+    const int ag = (int)(a + row0);
+    for (long long j = (long long)s + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < e; j += (long long)gridDim.x * blockDim.x) {
+      const int b = ld_stream_i32(indices + j);
+      const int pb = (j > s) ? __ldg(indices + j - 1) : -1;
+      const double v = (DT != SRG_VAL_ONES) ? ValLoad<DT>::at(data, j) : 1.0;
+      int bits = 0;
+      count_entry<DT>((int)j, b, pb, v, s, ag, n_cols, fl, bits);
+      if (bits) rowlen[a] = (e - s) - 1 + ((bits & 2) ? 0 : 1);   // the one stored diagonal fixes the row length up
+    }
+  }
+  raise_flags(flags, fl);
+}
+
+// ---- fill (unweighted canonical input: all stored values 1.0) -----------------------------------------------------------
+// A~'s row a has len + 1 - hd entries (hd: A stores its diagonal, which becomes 2.0), so hd follows from the two row
+// pointers and every kept entry's slot follows from its input slot.
+__device__ __forceinline__ void fill_entry(int j, int b, int pb, int s, int e, int ag, int ap_t, int hd,
+                                           int *__restrict__ at_indices) {
+  const int pos = ap_t + (j - s) + ((b > ag) ? 1 - hd : 0);
+  at_indices[pos] = b;                                  // b == ag: the stored diagonal keeps its slot
+  if (!hd) {
+    // the new diagonal entry sits between the last b < ag and the first b > ag
+    if (b > ag && (j == s || pb < ag)) at_indices[pos - 1] = ag;
+    else if (b < ag && j == e - 1) at_indices[pos + 1] = ag;
+  }
+}
+
 __global__ void __launch_bounds__(kTileRows)
 tile_fill_unweighted_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, long long n_rows,
                             long long row0, const int *__restrict__ at_indptr, int *__restrict__ at_indices,
-                            double *__restrict__ degree, const int *__restrict__ flags, int dt_can_be_weighted) {
+                            double *__restrict__ degree, const int *__restrict__ flags, int dt_can_be_weighted,
+                            HubList hubs) {
   const int f = *flags;
   if (f & kFatal) return;                                 // defective input: nothing is written
   if (dt_can_be_weighted && (f & kWeighted)) return;      // weighted: rows_fill_fast_kernel does it
   __shared__ int rp[kTileRows + 1];
+  __shared__ int cp[kTileRows + 1];
   __shared__ int ap[kTileRows + 1];
   const long long r0 = (long long)blockIdx.x * kTileRows;
   const int nr = (int)min((long long)kTileRows, n_rows - r0);
-  for (int t = threadIdx.x; t <= nr; t += kTileRows) {
-    rp[t] = indptr[r0 + t];
-    ap[t] = at_indptr[r0 + t];
-  }
-  __syncthreads();
-  const int e0 = rp[0], e1 = rp[nr];
+  for (int t = threadIdx.x; t <= nr; t += kTileRows) ap[t] = at_indptr[r0 + t];
+  const int total = tile_setup(indptr, r0, nr, rp, cp, &hubs);
   constexpr int U = 4;
-  for (int j0 = e0 + threadIdx.x; j0 < e1; j0 += U * kTileRows) {
-    int bb[U], pbb[U];
+  for (int c0 = threadIdx.x; c0 < total; c0 += U * kTileRows) {
+    int bb[U], pbb[U], tt[U], jj[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int j = j0 + u * kTileRows;
-      bb[u] = (j < e1) ? ld_stream_i32(indices + j) : 0;
-      pbb[u] = (j < e1 && j > e0) ? __ldg(indices + j - 1) : -1;
+      const int c = c0 + u * kTileRows;
+      tt[u] = (c < total) ? tile_row_of(cp, nr, c) : 0;
+      jj[u] = rp[tt[u]] + (c - cp[tt[u]]);
+      bb[u] = (c < total) ? ld_stream_i32(indices + jj[u]) : 0;
+      pbb[u] = (c < total && jj[u] > rp[tt[u]]) ? __ldg(indices + jj[u] - 1) : -1;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int j = j0 + u * kTileRows;
-      if (j >= e1) break;
-      const int b = bb[u];
-      const int t = tile_row_of(rp, nr, j);
-      const int ag = (int)(r0 + t + row0);
+      if (c0 + u * kTileRows >= total) break;
+      const int t = tt[u];
       const int s = rp[t], e = rp[t + 1];
       const int hd = ((ap[t + 1] - ap[t]) == (e - s)) ? 1 : 0;
-      const int pos = ap[t] + (j - s) + ((b > ag) ? 1 - hd : 0);
-      at_indices[pos] = b;                                  // b == ag: the stored diagonal keeps its slot
-      if (!hd) {
-        // the new diagonal entry sits between the last b < ag and the first b > ag
-        if (b > ag && (j == s || pbb[u] < ag)) at_indices[pos - 1] = ag;
-        else if (b < ag && j == e - 1) at_indices[pos + 1] = ag;
-      }
+      fill_entry(jj[u], bb[u], pbb[u], s, e, (int)(r0 + t + row0), ap[t], hd, at_indices);
     }
   }
   if ((int)threadIdx.x < nr) {
@@ -517,6 +586,28 @@ tile_fill_unweighted_kernel(const int *__restrict__ indptr, const int *__restric
   }
 }
 
+__global__ void __launch_bounds__(256)
+hub_fill_unweighted_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, long long row0,
+                           const int *__restrict__ at_indptr, int *__restrict__ at_indices,
+                           const int *__restrict__ flags, int dt_can_be_weighted, HubList hubs) {
+  const int f = *flags;
+  if ((f & kFatal) || (dt_can_be_weighted && (f & kWeighted))) return;
+  const int nh = min(*hubs.count, hubs.cap);
+  for (int h = 0; h < nh; ++h) {
+    const int a = hubs.rows[h];
+    const int s = indptr[a], e = indptr[a + 1];
+    const int ap_t = at_indptr[a];
+    const int hd = ((at_indptr[a + 1] - ap_t) == (e - s)) ? 1 : 0;
+    const int ag = (int)(a + row0);
+    for (long long j = (long long)s + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < e; j += (long long)gridDim.x * blockDim.x) {
+      const int b = ld_stream_i32(indices + j);
+      const int pb = (j > s) ? __ldg(indices + j - 1) : -1;
+      fill_entry((int)j, b, pb, s, e, ag, ap_t, hd, at_indices);
+    }
+  }
+}
+
+// ---- values -------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned hash32(unsigned x) {
   x ^= x >> 16;
   x *= 0x7feb352du;
@@ -526,103 +617,162 @@ __device__ __forceinline__ unsigned hash32(unsigned x) {
   return x;
 }
 
+struct ValuesArgs {
+  const int *at_indices;
+  const double *at_val;
+  const double *dr;
+  double one_minus_alpha, alpha;
+  int use_ppr, check_sym;
+  double *val64;
+  float *val32;
+};
+
+__device__ __forceinline__ void values_entry(const ValuesArgs &g, int p, int b, double vt, double dla, double drb, int ag,
+                                             bool weighted, int &fl, unsigned long long &s1, unsigned long long &s2) {
+  double v = __dmul_rn(__dmul_rn(vt, dla), drb);
+  if (g.use_ppr) {
+    v = __dmul_rn(g.one_minus_alpha, v);
+    if (b == ag) v = __dadd_rn(v, g.alpha);
+  }
+  if (v == 0.0) fl |= SRG_FLAG_ZERO_PRODUCT;
+  if (g.val64) g.val64[p] = v;
+  if (g.val32) g.val32[p] = __double2float_rn(v);
+  if (g.check_sym && b != ag) {
+    const unsigned lo = (unsigned)min(ag, b), hi = (unsigned)max(ag, b);
+    unsigned ha = hash32(lo * 0x9e3779b1u + hash32(hi));
+    unsigned hb = hash32(hi * 0x85ebca6bu ^ hash32(lo + 0x27d4eb2fu));
+    if (weighted) {
+      const unsigned long long vb = (unsigned long long)__double_as_longlong(vt);
+      ha = hash32(ha ^ (unsigned)vb);
+      hb = hash32(hb ^ (unsigned)(vb >> 32));
+    }
+    const unsigned long long h1 = ((unsigned long long)ha << 32) | hb;
+    const unsigned long long h2 = (unsigned long long)ha * (unsigned long long)(hb | 1u);
+    if (b > ag) {
+      s1 += h1;
+      s2 += h2;
+    } else {
+      s1 -= h1;
+      s2 -= h2;
+    }
+  }
+}
+
+// block-wide sum of the two symmetry accumulators into tri_counts (wrap-around arithmetic)
+__device__ __forceinline__ void sym_sums_commit(unsigned long long s1, unsigned long long s2,
+                                                unsigned long long *__restrict__ tri_counts) {
+  __shared__ unsigned long long red[2][kTileRows / 32];
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) {
+    red[0][threadIdx.x >> 5] = s1;
+    red[1][threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t1 = 0, t2 = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      t1 += red[0][w];
+      t2 += red[1][w];
+    }
+    if (t1) atomicAdd(tri_counts, t1);
+    if (t2) atomicAdd(tri_counts + 1, t2);
+  }
+}
+
 __global__ void __launch_bounds__(kTileRows)
-tile_values_kernel(long long n_rows, long long row0, long long n_cols, const int *__restrict__ at_indptr,
-                   const int *__restrict__ at_indices, const double *__restrict__ at_val,
-                   const double *__restrict__ degree, const double *__restrict__ dl, const double *__restrict__ dr,
-                   double one_minus_alpha, double alpha, int use_ppr, int check_sym, double *__restrict__ val64,
-                   float *__restrict__ val32, int *__restrict__ flags, unsigned long long *__restrict__ tri_counts) {
+tile_values_kernel(long long n_rows, long long row0, const int *__restrict__ at_indptr, const double *__restrict__ degree,
+                   const double *__restrict__ dl, ValuesArgs g, int *__restrict__ flags,
+                   unsigned long long *__restrict__ tri_counts, HubList hubs) {
   if (*flags & kFatal) return;  // A~ was not written
   const bool weighted = (*flags & kWeighted) != 0;
   __shared__ int ap[kTileRows + 1];
+  __shared__ int cp[kTileRows + 1];
   __shared__ double dla[kTileRows];
   __shared__ double dgv[kTileRows];   // unweighted: value of the row's diagonal entry (1.0 or 2.0)
   const long long r0 = (long long)blockIdx.x * kTileRows;
   const int nr = (int)min((long long)kTileRows, n_rows - r0);
-  for (int t = threadIdx.x; t <= nr; t += kTileRows) ap[t] = at_indptr[r0 + t];
-  __syncthreads();
+  const int total = tile_setup(at_indptr, r0, nr, ap, cp, &hubs);
   if ((int)threadIdx.x < nr) {
     const int t = threadIdx.x;
     dla[t] = dl[r0 + t + row0];
     dgv[t] = degree[r0 + t] - (double)(ap[t + 1] - ap[t] - 1);   // exact: 1.0 or 2.0
   }
   __syncthreads();
-  const int e0 = ap[0], e1 = ap[nr];
   int fl = 0;
   unsigned long long s1 = 0, s2 = 0;   // upper - lower, two independent sums (wrap-around arithmetic)
   constexpr int U = 4;
-  for (int p0 = e0 + threadIdx.x; p0 < e1; p0 += U * kTileRows) {
-    int bb[U];
+  for (int c0 = threadIdx.x; c0 < total; c0 += U * kTileRows) {
+    int bb[U], tt[U], pp[U];
     double drb[U], atv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int p = p0 + u * kTileRows;
-      bb[u] = (p < e1) ? ld_stream_i32(at_indices + p) : 0;
-      atv[u] = (weighted && p < e1) ? at_val[p] : 1.0;
+      const int c = c0 + u * kTileRows;
+      tt[u] = (c < total) ? tile_row_of(cp, nr, c) : 0;
+      pp[u] = ap[tt[u]] + (c - cp[tt[u]]);
+      bb[u] = (c < total) ? ld_stream_i32(g.at_indices + pp[u]) : 0;
+      atv[u] = (weighted && c < total) ? g.at_val[pp[u]] : 1.0;
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) drb[u] = (p0 + u * kTileRows < e1) ? __ldg(dr + bb[u]) : 0.0;
+    for (int u = 0; u < U; ++u) drb[u] = (c0 + u * kTileRows < total) ? __ldg(g.dr + bb[u]) : 0.0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-    const int p = p0 + u * kTileRows;
-    if (p >= e1) break;
-    const int b = bb[u];
-    const int t = tile_row_of(ap, nr, p);
-    const int ag = (int)(r0 + t + row0);
-    const double vt = weighted ? atv[u] : ((b == ag) ? dgv[t] : 1.0);
-    double v = __dmul_rn(__dmul_rn(vt, dla[t]), drb[u]);
-    if (use_ppr) {
-      v = __dmul_rn(one_minus_alpha, v);
-      if (b == ag) v = __dadd_rn(v, alpha);
-    }
-    if (v == 0.0) fl |= SRG_FLAG_ZERO_PRODUCT;
-    if (val64) val64[p] = v;
-    if (val32) val32[p] = __double2float_rn(v);
-    if (check_sym && b != ag) {
-      const unsigned lo = (unsigned)min(ag, b), hi = (unsigned)max(ag, b);
-      unsigned ha = hash32(lo * 0x9e3779b1u + hash32(hi));
-      unsigned hb = hash32(hi * 0x85ebca6bu ^ hash32(lo + 0x27d4eb2fu));
-      if (weighted) {
-        const unsigned long long vb = (unsigned long long)__double_as_longlong(vt);
-        ha = hash32(ha ^ (unsigned)vb);
-        hb = hash32(hb ^ (unsigned)(vb >> 32));
-      }
-      const unsigned long long h1 = ((unsigned long long)ha << 32) | hb;
-      const unsigned long long h2 = (unsigned long long)ha * (unsigned long long)(hb | 1u);
-      if (b > ag) {
-        s1 += h1;
-        s2 += h2;
-      } else {
-        s1 -= h1;
-        s2 -= h2;
-      }
-    }
+      if (c0 + u * kTileRows >= total) break;
+      const int t = tt[u];
+      const int ag = (int)(r0 + t + row0);
+      const double vt = weighted ? atv[u] : ((bb[u] == ag) ? dgv[t] : 1.0);
+      values_entry(g, pp[u], bb[u], vt, dla[t], drb[u], ag, weighted, fl, s1, s2);
     }
   }
-  if (check_sym) {
-    __shared__ unsigned long long red[2][kTileRows / 32];
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (lane == 0) {
-      red[0][threadIdx.x >> 5] = s1;
-      red[1][threadIdx.x >> 5] = s2;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long t1 = 0, t2 = 0;
-      for (int w = 0; w < kTileRows / 32; ++w) {
-        t1 += red[0][w];
-        t2 += red[1][w];
-      }
-      if (t1) atomicAdd(tri_counts, t1);
-      if (t2) atomicAdd(tri_counts + 1, t2);
-    }
-  }
+  if (g.check_sym) sym_sums_commit(s1, s2, tri_counts);
   raise_flags(flags, fl);
+}
+
+__global__ void __launch_bounds__(256)
+hub_values_kernel(long long row0, const int *__restrict__ at_indptr, const double *__restrict__ degree,
+                  const double *__restrict__ dl, ValuesArgs g, int *__restrict__ flags,
+                  unsigned long long *__restrict__ tri_counts, HubList hubs) {
+  if (*flags & kFatal) return;
+  const bool weighted = (*flags & kWeighted) != 0;
+  const int nh = min(*hubs.count, hubs.cap);
+  int fl = 0;
+  unsigned long long s1 = 0, s2 = 0;
+  for (int h = 0; h < nh; ++h) {
+    const int a = hubs.rows[h];
+    const int s = at_indptr[a], e = at_indptr[a + 1];
+    const int ag = (int)(a + row0);
+    const double dla = dl[ag];
+    const double dgv = degree[a] - (double)(e - s - 1);
+    for (long long p = (long long)s + (long long)blockIdx.x * blockDim.x + threadIdx.x; p < e; p += (long long)gridDim.x * blockDim.x) {
+      const int b = ld_stream_i32(g.at_indices + p);
+      const double vt = weighted ? g.at_val[p] : ((b == ag) ? dgv : 1.0);
+      values_entry(g, (int)p, b, vt, dla, __ldg(g.dr + b), ag, weighted, fl, s1, s2);
+    }
+  }
+  if (g.check_sym) sym_sums_commit(s1, s2, tri_counts);
+  raise_flags(flags, fl);
+}
+
+struct HubHolder {
+  HubList h;
+  int *base = nullptr;
+};
+static int make_hub_list(int64_t nnz_bound, cudaStream_t s, HubHolder *o) {
+  const int64_t cap = nnz_bound / kHubLen + 1;
+  SRG_CUDA(cudaMallocAsync(&o->base, (size_t)(1 + cap) * sizeof(int), s));
+  o->h.count = o->base;
+  o->h.rows = o->base + 1;
+  o->h.cap = (int)cap;
+  SRG_CUDA(cudaMemsetAsync(o->base, 0, sizeof(int), s));
+  return SRG_OK;
+}
+static void free_hub_list(HubHolder *o, cudaStream_t s) {
+  if (o->base) cudaFreeAsync(o->base, s);
+  o->base = nullptr;
 }
 
 // weighted graphs only: degree = A~.sum(1) in numpy's add.reduceat order, one thread per row
@@ -829,9 +979,16 @@ int rows_count_launch(const int32_t *indptr, const int32_t *indices, const void 
     SRG_LAUNCHED();
     return SRG_OK;
   }
-  (void)nnz;
-  SRG_DT_SWITCH(dt, (tile_count_kernel<DTT><<<(unsigned)ceil_div64(n_rows, kTileRows), kTileRows, 0, s>>>(indptr, indices, data, n_rows, row0, n_cols, rowlen, flags)));
+  HubHolder hubs;
+  int rc = make_hub_list(nnz, s, &hubs);
+  if (rc) return rc;
+  SRG_DT_SWITCH(dt, (tile_count_kernel<DTT><<<(unsigned)ceil_div64(n_rows, kTileRows), kTileRows, 0, s>>>(indptr, indices, data, n_rows, row0, n_cols, rowlen, flags, hubs.h)));
   SRG_LAUNCHED();
+  if (nnz > kHubLen) {   // a hub row needs more than kHubLen entries
+    SRG_DT_SWITCH(dt, (hub_count_kernel<DTT><<<kHubBlocks, 256, 0, s>>>(indptr, indices, data, row0, n_cols, rowlen, flags, hubs.h)));
+    SRG_LAUNCHED();
+  }
+  free_hub_list(&hubs, s);
   return SRG_OK;
 }
 
@@ -847,9 +1004,18 @@ int rows_fill_launch(const int32_t *indptr, const int32_t *indices, const void *
   }
   if (!force_vals) {
     // all-ones input (known from the dtype, or found at run time by the count pass): entry-parallel tile kernel
+    HubHolder hubs;
+    int rch = make_hub_list(nnz, s, &hubs);
+    if (rch) return rch;
     tile_fill_unweighted_kernel<<<(unsigned)ceil_div64(n_rows, kTileRows), kTileRows, 0, s>>>(
-        indptr, indices, n_rows, row0, at_indptr, at_indices, degree, flags, dt != SRG_VAL_ONES ? 1 : 0);
+        indptr, indices, n_rows, row0, at_indptr, at_indices, degree, flags, dt != SRG_VAL_ONES ? 1 : 0, hubs.h);
     SRG_LAUNCHED();
+    if (nnz > kHubLen) {
+      hub_fill_unweighted_kernel<<<kHubBlocks, 256, 0, s>>>(indptr, indices, row0, at_indptr, at_indices, flags,
+                                                           dt != SRG_VAL_ONES ? 1 : 0, hubs.h);
+      SRG_LAUNCHED();
+    }
+    free_hub_list(&hubs, s);
     if (dt == SRG_VAL_ONES) return SRG_OK;
   }
   // weighted (or forced) values: warp-per-task kernels, which leave at once when the flags say "all ones"
@@ -974,10 +1140,26 @@ extern "C" int srg_norm_values_rows_csr(int32_t *at_indptr, const int32_t *at_in
     SRG_CUDA(cudaMemsetAsync(tri, 0, 2 * sizeof(unsigned long long), s));
   }
   if (!g_exact_sym_check) {
-    tile_values_kernel<<<(unsigned)ceil_div64(n_rows, kTileRows), kTileRows, 0, s>>>(
-        n_rows, row0, n_cols, at_indptr, at_indices, at_val, degree_rows, pow_left, pow_right, 1.0 - ppr_alpha, ppr_alpha,
-        ppr_alpha >= 0.0 ? 1 : 0, check_symmetry, out_val_f64, out_val_f32, flags, tri);
+    ValuesArgs g;
+    g.at_indices = at_indices;
+    g.at_val = at_val;
+    g.dr = pow_right;
+    g.one_minus_alpha = 1.0 - ppr_alpha;
+    g.alpha = ppr_alpha;
+    g.use_ppr = ppr_alpha >= 0.0 ? 1 : 0;
+    g.check_sym = check_symmetry;
+    g.val64 = out_val_f64;
+    g.val32 = out_val_f32;
+    HubHolder hubs;
+    if ((rc = make_hub_list(nnz, s, &hubs))) return rc;
+    tile_values_kernel<<<(unsigned)ceil_div64(n_rows, kTileRows), kTileRows, 0, s>>>(n_rows, row0, at_indptr, degree_rows,
+                                                                                  pow_left, g, flags, tri, hubs.h);
     SRG_LAUNCHED();
+    if (nnz > kHubLen) {
+      hub_values_kernel<<<kHubBlocks, 256, 0, s>>>(row0, at_indptr, degree_rows, pow_left, g, flags, tri, hubs.h);
+      SRG_LAUNCHED();
+    }
+    free_hub_list(&hubs, s);
     void_on_fatal_kernel<<<(unsigned)ceil_div64(n_rows + 1, 256), 256, 0, s>>>(flags, at_indptr, n_rows + 1);
     SRG_LAUNCHED();
     if (check_symmetry) {

@@ -439,20 +439,27 @@ def propagate_device(st: DistState, local_norm, x_local_padded, k, keep_hops=Tru
     return out
 
 
-def dist_sym_norm(st: DistState, a_local, r, ppr_alpha=None):
+def dist_sym_norm(st: DistState, a_local, r, ppr_alpha=None, marks=None):
     """Normalise this rank's rows (raw DeviceCSR with global column ids).  Returns (DeviceCSR with
-    float32 values, flags tensor)."""
+    float32 values, flags tensor).  ``marks``: optional list receiving (label, CUDA event) after each stage."""
     import torch
 
     from . import _lib
     from .device import DeviceCSR, _p, _stream_ptr
     lib, dev = st.lib, st.device
     s = _stream_ptr(dev)
+
+    def mark(label):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((label, ev))
     n_loc, nnz = st.n_local, a_local.nnz
     flags = torch.zeros(1, dtype=torch.int32, device=dev)
     at_indptr = torch.empty(n_loc + 1, dtype=torch.int32, device=dev)
     _lib.check(lib.srg_selfloop_rows_csr(_p(a_local.indptr), _p(a_local.indices), _p(a_local.data), a_local.val_dtype,
                                          n_loc, nnz, st.row0, st.n, _p(at_indptr), None, _p(flags), s))
+    mark("norm: count + scan")
     cap = max(nnz + n_loc, 1)
     at_indices = torch.empty(cap, dtype=torch.int32, device=dev)
     at_val = torch.empty(cap, dtype=torch.float64, device=dev) if a_local.data is not None else None
@@ -463,9 +470,11 @@ def dist_sym_norm(st: DistState, a_local, r, ppr_alpha=None):
     _lib.check(lib.srg_selfloop_fill_rows_csr(_p(a_local.indptr), _p(a_local.indices), _p(a_local.data),
                                               a_local.val_dtype, n_loc, nnz, st.row0, st.n, _p(at_indptr), _p(at_indices),
                                               _p(at_val), _p(deg_loc), _p(flags), s))
+    mark("norm: fill + degrees")
     if st.world > 1:
         view = gath[st.rank * st.rows_per:(st.rank + 1) * st.rows_per]
         st.dist.all_gather_into_tensor(gath, view, group=st.group)
+    mark("norm: degree all-gather (first cross-rank wait of the step)")
     if st.feat_groups > 1:
         deg_all = gath.view(st.n_row_blocks, st.feat_groups, st.rows_per)[:, st.ci, :].contiguous().view(-1)
     else:
@@ -477,6 +486,7 @@ def dist_sym_norm(st: DistState, a_local, r, ppr_alpha=None):
     alpha = -1.0 if ppr_alpha is None else float(ppr_alpha)
     _lib.check(lib.srg_norm_values_rows_csr(_p(at_indptr), _p(at_indices), _p(at_val), _p(deg_loc), n_loc, nnz + n_loc,
                                             st.row0, st.n_pad, _p(dl), _p(dr), alpha, 0, None, _p(val32), _p(flags), s))
+    mark("norm: power tables + values")
     return DeviceCSR(at_indptr, at_indices, val32, n_loc, nnz + n_loc), flags
 
 

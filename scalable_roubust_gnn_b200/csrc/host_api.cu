@@ -13,7 +13,10 @@
 // raised so repeated calls reuse the same blocks.
 #include <stdlib.h>
 
+#include <string.h>
+
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -72,11 +75,20 @@ int spmm_csr_f32_impl(const int32_t *indptr, const int32_t *indices, const float
                       int32_t F, bool accumulate, cudaStream_t s);
 
 // ---- per-device state of the host entry points -------------------------------------------------
+constexpr int kStageSlots = 4;
+constexpr size_t kStageChunk = 16u << 20;   // bytes per slot of the pinned staging ring
+
 struct DeviceState {
   bool init = false;
   cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
   cudaEvent_t ev_csr = nullptr, ev_x = nullptr, ev_norm = nullptr;
   std::vector<cudaEvent_t> ev_hop;
+  // the streams, events and the staging ring are shared by every call on this device: one call at a time
+  std::mutex mu;
+  // pinned staging ring for pageable inputs (allocated on first use)
+  void *stage_buf[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t stage_ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned stage_next = 0;
 };
 static std::mutex g_state_mu;
 static DeviceState g_state[64];
@@ -99,6 +111,118 @@ static int get_state(int device, DeviceState **out) {
     st.init = true;
   }
   *out = &st;
+  return SRG_OK;
+}
+
+// ---- pageable host -> device copies -----------------------------------------------------------------------------
+// The reference's callers hand over ordinary numpy arrays (SSRG/models/base_scalable/base_model.py:36).  A
+// cudaMemcpyAsync from pageable memory is staged by the driver on ONE thread and blocks the caller; here the copy is
+// cut into 16 MB chunks that a small pool of host threads moves into a ring of pinned buffers while the DMA engine
+// drains the previous chunks, so the upload runs close to the pinned PCIe rate.
+class CopyPool {
+ public:
+  explicit CopyPool(int workers) {
+    for (int i = 0; i < workers; ++i) th_.emplace_back([this, i] { run(i); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto &t : th_) t.join();
+  }
+  // dst <- src, split over the workers and the calling thread
+  void copy(void *dst, const void *src, size_t n) {
+    const int parts = (int)th_.size() + 1;
+    const size_t per = ((n + parts - 1) / parts + 4095) & ~(size_t)4095;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      dst_ = static_cast<char *>(dst);
+      src_ = static_cast<const char *>(src);
+      n_ = n;
+      per_ = per;
+      pending_ = (int)th_.size();
+      ++gen_;
+    }
+    cv_.notify_all();
+    const size_t lo = std::min(n, per * (size_t)th_.size());
+    if (lo < n) memcpy(dst_ + lo, src_ + lo, n - lo);
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void run(int i) {
+    unsigned long long seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lk(m_);
+      cv_.wait(lk, [&] { return gen_ != seen; });
+      seen = gen_;
+      if (stop_) return;
+      char *d = dst_;
+      const char *s = src_;
+      const size_t lo = std::min(n_, per_ * (size_t)i), hi = std::min(n_, lo + per_);
+      lk.unlock();
+      if (hi > lo) memcpy(d + lo, s + lo, hi - lo);
+      lk.lock();
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  char *dst_ = nullptr;
+  const char *src_ = nullptr;
+  size_t n_ = 0, per_ = 0;
+  int pending_ = 0;
+  unsigned long long gen_ = 0;
+  bool stop_ = false;
+};
+
+static bool host_ptr_is_pageable(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return true;
+  }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+
+static int staging_threads() {
+  static const int v = [] {
+    const char *e = getenv("SRG_STAGE_THREADS");
+    int t = e ? atoi(e) : 4;
+    return std::max(0, std::min(t, 16));
+  }();
+  return v;   // 0: leave pageable copies to the driver
+}
+
+// H2D copy of `bytes` from a host buffer that may be pageable; stream-ordered on `s` (the caller holds st->mu)
+static int h2d_copy(DeviceState *st, void *dst, const void *src, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return SRG_OK;
+  const int threads = staging_threads();
+  if (threads == 0 || bytes < (4u << 20) || !host_ptr_is_pageable(src)) {
+    SRG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    return SRG_OK;
+  }
+  static CopyPool pool(threads - 1);
+  static std::mutex pool_mu;   // one staged copy at a time across devices (the pool is shared)
+  std::lock_guard<std::mutex> lk(pool_mu);
+  for (int i = 0; i < kStageSlots; ++i)
+    if (!st->stage_buf[i]) {
+      SRG_CUDA(cudaHostAlloc(&st->stage_buf[i], kStageChunk, cudaHostAllocDefault));
+      SRG_CUDA(cudaEventCreateWithFlags(&st->stage_ev[i], cudaEventDisableTiming));
+    }
+  for (size_t off = 0; off < bytes; off += kStageChunk) {
+    const size_t len = std::min(kStageChunk, bytes - off);
+    const unsigned slot = st->stage_next++ % kStageSlots;
+    SRG_CUDA(cudaEventSynchronize(st->stage_ev[slot]));   // the DMA that last read this slot has finished
+    pool.copy(st->stage_buf[slot], static_cast<const char *>(src) + off, len);
+    SRG_CUDA(cudaMemcpyAsync(static_cast<char *>(dst) + off, st->stage_buf[slot], len, cudaMemcpyHostToDevice, s));
+    SRG_CUDA(cudaEventRecord(st->stage_ev[slot], s));
+  }
   return SRG_OK;
 }
 
@@ -357,6 +481,7 @@ static int construct_attempt(const int32_t *indptr, const int32_t *indices, cons
     *out_nnz = 0;
     return SRG_OK;
   }
+  std::lock_guard<std::mutex> dev_lock(st->mu);
   int flags = 0;
   int32_t nnz_out = 0;
   {
@@ -365,11 +490,11 @@ static int construct_attempt(const int32_t *indptr, const int32_t *indices, cons
     char *d_data = nullptr;
     if ((rc = pa.alloc(&d_indptr, n + 1))) return rc;
     if ((rc = pa.alloc(&d_indices, nnz))) return rc;
-    SRG_CUDA(cudaMemcpyAsync(d_indptr, indptr, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
-    if (nnz) SRG_CUDA(cudaMemcpyAsync(d_indices, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = h2d_copy(st, d_indptr, indptr, (size_t)(n + 1) * 4, s))) return rc;
+    if (nnz && (rc = h2d_copy(st, d_indices, indices, (size_t)nnz * 4, s))) return rc;
     if (val_dtype != SRG_VAL_ONES) {
       if ((rc = pa.alloc(&d_data, nnz * (int64_t)val_bytes(val_dtype)))) return rc;
-      if (nnz) SRG_CUDA(cudaMemcpyAsync(d_data, data, (size_t)nnz * val_bytes(val_dtype), cudaMemcpyHostToDevice, s));
+      if (nnz && (rc = h2d_copy(st, d_data, data, (size_t)nnz * val_bytes(val_dtype), s))) return rc;
     }
     NormOut no;
     if ((rc = run_norm(pa, d_indptr, d_indices, d_data, val_dtype, n, nnz, r, ppr_alpha,
@@ -438,6 +563,7 @@ static int propagate_attempt(const int32_t *indptr, const int32_t *indices, cons
   SRG_REQUIRE(guard.ok, "propagate_host: cannot select device %d", device);
   DeviceState *st;
   if ((rc = get_state(device, &st))) return rc;
+  std::lock_guard<std::mutex> dev_lock(st->mu);   // shared streams / events / staging ring: one call per device at a time
   while ((int)st->ev_hop.size() < K) {
     cudaEvent_t e;
     SRG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -493,10 +619,9 @@ static int propagate_attempt(const int32_t *indptr, const int32_t *indices, cons
     SRG_CUDA(cudaStreamWaitEvent(s_out, st->ev_csr, 0));
 
     // copy-in: raw CSR first (normalisation can start), then features
-    SRG_CUDA(cudaMemcpyAsync(d_indptr, indptr, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s_in));
-    if (nnz) SRG_CUDA(cudaMemcpyAsync(d_indices, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, s_in));
-    if (d_data && nnz)
-      SRG_CUDA(cudaMemcpyAsync(d_data, data, (size_t)nnz * val_bytes(val_dtype), cudaMemcpyHostToDevice, s_in));
+    if ((rc = h2d_copy(st, d_indptr, indptr, (size_t)(n + 1) * 4, s_in))) return rc;
+    if (nnz && (rc = h2d_copy(st, d_indices, indices, (size_t)nnz * 4, s_in))) return rc;
+    if (d_data && nnz && (rc = h2d_copy(st, d_data, data, (size_t)nnz * val_bytes(val_dtype), s_in))) return rc;
     SRG_CUDA(cudaEventRecord(st->ev_csr, s_in));
     // compute: normalisation (queued before the feature upload so it overlaps it even when the
     // host buffers are pageable and cudaMemcpyAsync blocks the host while staging)
@@ -509,9 +634,8 @@ static int propagate_attempt(const int32_t *indptr, const int32_t *indices, cons
 
     if (have_feat) {
       float *dst = need_pack ? d_flat_in : hops[0];
-      SRG_CUDA(cudaMemcpyAsync(dst, features, (size_t)n * F * 4, cudaMemcpyHostToDevice, s_in));
-      if (feature_mask)
-        SRG_CUDA(cudaMemcpyAsync(d_mask, feature_mask, (size_t)n * F * 4, cudaMemcpyHostToDevice, s_in));
+      if ((rc = h2d_copy(st, dst, features, (size_t)n * F * 4, s_in))) return rc;
+      if (feature_mask && (rc = h2d_copy(st, d_mask, feature_mask, (size_t)n * F * 4, s_in))) return rc;
       if (need_pack && (rc = srg_pack_features_f32(d_flat_in, F, hops[0], ld, n, F, d_mask, s_in))) return rc;
       SRG_CUDA(cudaEventRecord(st->ev_x, s_in));
     }
@@ -682,6 +806,7 @@ static int shim_spmm(float *answer, const float *data, const int *indices, const
   DeviceState *st;
   if ((rc = get_state(device, &st))) return rc;
   cudaStream_t s = st->s_compute;
+  std::lock_guard<std::mutex> dev_lock(st->mu);
   const int64_t n = mat_row, F = mat_col, nnz = indptr[mat_row];
   SRG_REQUIRE(nnz >= 0 && (nnz == 0 || (data && indices)), "FloatCSRMulDense*: bad CSR");
   PoolAllocs pa(s);

@@ -435,15 +435,25 @@ __device__ __forceinline__ int tile_setup(const int *__restrict__ ptr, long long
   for (int t = threadIdx.x; t <= nr; t += kTileRows) rp[t] = ptr[r0 + t];
   __syncthreads();
   int len = 0;
+  bool hub = false;
   if ((int)threadIdx.x < nr) {
     len = rp[threadIdx.x + 1] - rp[threadIdx.x];
-    if (len > kHubLen) {
-      if (hubs) {
-        const int i = atomicAdd(hubs->count, 1);
-        if (i < hubs->cap) hubs->rows[i] = (int)(r0 + threadIdx.x);
-      }
-      len = 0;
+    hub = len > kHubLen;
+  }
+  if (!__syncthreads_or(hub ? 1 : 0)) {
+    // the usual tile: no hub row, the compacted pointers are the row pointers themselves
+    const int total0 = rp[nr] - rp[0];
+    cp[threadIdx.x] = ((int)threadIdx.x < nr) ? rp[threadIdx.x] - rp[0] : total0;
+    if (threadIdx.x == 0) cp[kTileRows] = total0;
+    __syncthreads();
+    return total0;
+  }
+  if (hub) {
+    if (hubs) {
+      const int i = atomicAdd(hubs->count, 1);
+      if (i < hubs->cap) hubs->rows[i] = (int)(r0 + threadIdx.x);
     }
+    len = 0;
   }
   int total;
   const int excl = block_excl_scan<kTileRows>(len, &total);

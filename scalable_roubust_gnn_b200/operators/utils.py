@@ -109,6 +109,11 @@ def csr_sparse_dense_matmul(adj, feature):
     lib = _lib.load()
     if not isinstance(feature, np.ndarray) or feature.dtype != np.float32:
         raise C.ArgumentError("feature must be a float32 numpy.ndarray")
+    if feature.ndim != 2:
+        raise ValueError("feature must be a 2-D array (N x F)")
+    # the native symbol reads indptr[mat_row] and mat[indices[j] * mat_col ...]: check what it will index
+    if adj.shape[0] != adj.shape[1] or adj.shape[1] != feature.shape[0]:
+        raise ValueError("Dimension mismatch detected for the adjacency and the feature matrix!")
     answer = np.zeros(feature.shape, dtype=np.float32).reshape(-1)
     data = np.ascontiguousarray(adj.data, dtype=np.float32)
     indices = np.ascontiguousarray(adj.indices, dtype=np.int32)
@@ -117,7 +122,10 @@ def csr_sparse_dense_matmul(adj, feature):
     mat_row, mat_col = feature.shape
     if lib.srg_device_count() <= 0:
         raise _lib.SrgError(_lib.SRG_ERR_NODEV, "no CUDA device visible: libsrgnn_b200 has no CPU fallback")
-    lib.FloatCSRMulDenseOMP(_ptr(answer), _ptr(data), _ptr(indices), _ptr(indptr), _ptr(mat), mat_row, mat_col)
+    # FloatCSRMulDense is the same shim with an error channel (the literal FloatCSRMulDenseOMP symbol has none and
+    # must abort on failure, matmul.h:5); its diagnostic goes through srg_last_error
+    if lib.FloatCSRMulDense(_ptr(answer), int(data.size), _ptr(data), _ptr(indices), _ptr(indptr), _ptr(mat), mat_row, mat_col):
+        raise _lib.SrgError(_lib.SRG_ERR_CUDA, _lib.last_error() or "FloatCSRMulDense failed")
     return answer.reshape(feature.shape)
 
 

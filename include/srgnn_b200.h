@@ -298,6 +298,26 @@ int srg_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float 
                      int64_t n_rows, int64_t nnz, const float *X, int64_t ldx, float *Y,
                      int64_t ldy, int32_t F, void *stream);
 
+/* ---- (a9, config 3) heat-kernel wavelets of the IDENTITY impulse as sparse matrices ----------------------------
+ * Psi_s = sum_k c_sk T_k(L~) I, thresholded (r < tol -> dropped; tol = NaN: no threshold), float32 CSR — what
+ * WaveletSparsifier.calculate_wavelet (wavelet/src/utils.py:89-104) and SpectralModel.calculate_wavelet
+ * (SSRG/models/base_scalable/base_model.py:236-265) obtain from pygsp's cheby_op on dense N x N / N x 1000 impulse
+ * blocks.  The recurrence runs on stored entries only (sparse products L T_{k-1} by expand / stable sort / ordered
+ * fp64 segment sums); bit-identical to srg_cheby_filter_f64 on identity blocks.  L: the CSR of srg_laplacian_csr
+ * (fp64, device) and must store every diagonal entry (SRG_ERR_UNSUPPORTED otherwise: isolated nodes).
+ * coeffs: HOST [n_scales][order + 1].  Set-up path: synchronises the stream.  Results live behind the handle:
+ *   srg_cheby_sparse_info   nnz of one scale, total products expanded, nnz of the order-M pattern
+ *   srg_cheby_sparse_fetch  device-to-device copy of one scale's CSR into caller arrays
+ *   srg_cheby_sparse_free   releases the handle */
+int srg_cheby_sparse_run(const int32_t *l_indptr, const int32_t *l_indices, const double *l_vals, int64_t n,
+                         int64_t l_nnz, double lmax, const double *coeffs, int32_t n_scales, int32_t order,
+                         double tol, void **out_handle, void *stream);
+int srg_cheby_sparse_info(void *handle, int32_t scale, int64_t *out_nnz, int64_t *out_products,
+                          int64_t *out_pattern_nnz);
+int srg_cheby_sparse_fetch(void *handle, int32_t scale, int32_t *indptr, int32_t *indices, float *vals,
+                           void *stream);
+int srg_cheby_sparse_free(void *handle);
+
 /* ---- (e) row-partitioned multi-GPU hop ------------------------------------------------------- */
 /*
  * One hop over this rank's row slice with the exchange fused into the epilogue: every finished row

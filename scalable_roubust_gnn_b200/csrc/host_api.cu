@@ -193,7 +193,10 @@ static bool host_ptr_is_pageable(const void *p) {
 static int staging_threads() {
   static const int v = [] {
     const char *e = getenv("SRG_STAGE_THREADS");
-    int t = e ? atoi(e) : 4;
+    // measured at the products shape (1.24 GB of pageable input, 16 host CPUs): driver path 172 ms end to end,
+    // 2 threads 146, 4 threads 106, 8 threads 99, pinned inputs 85
+    const int hw = (int)std::thread::hardware_concurrency();
+    int t = e ? atoi(e) : std::max(2, std::min(8, hw / 2));
     return std::max(0, std::min(t, 16));
   }();
   return v;   // 0: leave pageable copies to the driver

@@ -94,7 +94,8 @@ class WaveletSparsifier:
     the device (the reference materialises the N x N identity, utils.py:94).
     """
 
-    def __init__(self, graph, scale, approximation_order, tolerance, lmax=None, block=1024, device="cuda"):
+    def __init__(self, graph, scale, approximation_order, tolerance, lmax=None, block=1024, device="cuda",
+                 method="sparse"):
         if not sp.issparse(graph):
             import networkx as nx  # only when the caller already uses it
             graph = nx.adjacency_matrix(graph)
@@ -104,6 +105,10 @@ class WaveletSparsifier:
         self.n = w.shape[0]
         self.device = device
         self.block = int(block)
+        # "sparse": the recurrence on stored entries only (csrc/chebysp.cu); "blocks": dense impulse column blocks
+        # (csrc/cheby.cu), the shape of the reference's own evaluation - both give the same bits
+        self.method = method
+        self.stats = {}
         self.scales = [-scale, scale]
         self.approximation_order = approximation_order
         self.tolerance = tolerance
@@ -133,8 +138,43 @@ class WaveletSparsifier:
         self.phi_matrices = out
         return self.phi_matrices
 
+    def _wavelets_sparse(self, normalize):
+        """The whole identity impulse at once, on stored entries only (csrc/chebysp.cu)."""
+        lib = _lib.load()
+        dev_ = self.device
+        n = self.n
+        s = _stream_ptr(torch.device(dev_) if isinstance(dev_, str) else dev_)
+        coeffs = np.ascontiguousarray(self.chebyshev_coefficients(), dtype=np.float64)
+        l_nnz = int(self.lap.indptr[-1].item())
+        handle = C.c_void_p()
+        tol = float("nan") if self.tolerance is None else float(self.tolerance)
+        _lib.check(lib.srg_cheby_sparse_run(_p(self.lap.indptr), _p(self.lap.indices), _p(self.lap.data), n, l_nnz,
+                                            float(self.lmax), coeffs.ctypes.data_as(C.POINTER(C.c_double)), len(self.scales),
+                                            int(self.approximation_order), tol, C.byref(handle), s))
+        out = []
+        try:
+            for sc in range(len(self.scales)):
+                nnz, prod, pat = C.c_int64(), C.c_int64(), C.c_int64()
+                _lib.check(lib.srg_cheby_sparse_info(handle, sc, C.byref(nnz), C.byref(prod), C.byref(pat)))
+                self.stats = {"products": int(prod.value), "pattern_nnz": int(pat.value)}
+                indptr = torch.empty(n + 1, dtype=torch.int32, device=dev_)
+                cols = torch.empty(max(int(nnz.value), 1), dtype=torch.int32, device=dev_)
+                vals = torch.empty(max(int(nnz.value), 1), dtype=torch.float32, device=dev_)
+                _lib.check(lib.srg_cheby_sparse_fetch(handle, sc, _p(indptr), _p(cols), _p(vals), s))
+                if normalize:
+                    _lib.check(lib.srg_csr_row_normalize_l1_f32(n, _p(indptr), _p(vals), s))
+                out.append((indptr, cols, vals))
+        finally:
+            lib.srg_cheby_sparse_free(handle)
+        return out
+
     def calculate_all_wavelets_device(self, normalize=True):
         """Same, device resident: a list (one per scale) of (indptr int32[n+1], cols int32, vals float32)."""
+        if self.method == "sparse" and self.approximation_order >= 1:
+            try:
+                return self._wavelets_sparse(normalize)
+            except _lib.SrgUnsupported:
+                pass          # isolated nodes (no stored Laplacian diagonal): the dense-block path handles them
         lib = _lib.load()
         dev_ = self.device
         n = self.n
@@ -216,7 +256,8 @@ class SpectralModel:
     ``lmax``: pygsp's ARPACK estimate is an input here (``estimate_lmax`` reproduces its call).
     """
 
-    def __init__(self, scale, approximation_order, tolerance, lmax=None, block=1000, device="cuda"):
+    def __init__(self, scale, approximation_order, tolerance, lmax=None, block=1000, device="cuda", method="sparse"):
+        self.method = method
         self.scales = [-scale, scale]
         self.approximation_order = approximation_order
         self.tolerance = tolerance
@@ -249,7 +290,7 @@ class SpectralModel:
             feature = feature.numpy()
         feature = np.ascontiguousarray(feature, dtype=np.float32)
         ws = WaveletSparsifier(adj, self.scales[1], self.approximation_order, self.tolerance, lmax=self.lmax,
-                               block=self.block, device=self.device)
+                               block=self.block, device=self.device, method=self.method)
         if feature.ndim != 2 or feature.shape[0] != ws.n:
             raise ValueError("Dimension mismatch detected for the adjacency and the feature matrix!")
         self.lmax = ws.lmax

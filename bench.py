@@ -26,12 +26,16 @@ import scipy.sparse as sp
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+RMAT_WORKLOADS = {"products-rmat"}
+
 WORKLOADS = {
     # name: (N, nnz of the symmetric adjacency without self loops, F, K)
     "cora": (2708, 10556, 1433, 3),
     "pubmed": (19717, 88648, 500, 5),
     "arxiv": (169343, 1166243, 128, 3),
     "products": (2449029, 61859140, 100, 3),
+    # the products shape on a power-law (R-MAT 0.57/0.19/0.19/0.05) graph: hub rows up to ~10^5 entries
+    "products-rmat": (2449029, 61859140, 100, 3),
     # config 5: power-law (scrambled R-MAT) graph built per rank on the device; multi-GPU runs only
     "papers100M": (111059956, 1615685872, 128, 3),
 }
@@ -53,8 +57,13 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_GRAPH_KIND = {"kind": "uniform"}
+
+
 def synth_graph(n, nnz, seed=0):
     from scalable_roubust_gnn_b200 import synth
+    if _GRAPH_KIND["kind"] == "rmat":
+        return synth.rmat_graph(n, nnz, seed)
     return synth.uniform_graph(n, nnz, seed)
 
 
@@ -249,7 +258,8 @@ def run_reference(args):
 
 
 def workload_config(args, n, nnz_hat, f, k):
-    kind = "power-law (scrambled R-MAT, device-generated)" if args.workload.startswith("papers100M") else "uniform"
+    kind = ("power-law (scrambled R-MAT, device-generated)" if args.workload.startswith("papers100M")
+            else "power-law (R-MAT)" if args.workload in RMAT_WORKLOADS else "uniform")
     return {"workload": f"{args.workload}-shaped synthetic {kind} graph", "N": n, "nnz_hat": int(nnz_hat), "F": f,
             "K": k, "r": 0.5, "scale": args.scale, "l2": "inputs (X, CSR) exceed L2; no flush needed" if n * f * 4 > 126e6
             else "flushed between steps"}
@@ -407,6 +417,112 @@ def run_ours(args):
     emit(line)
 
 
+# ------------------------------------------------------------------------------------------------
+def run_cheby(args):
+    """--workload arxiv-cheby (BASELINE config 3): heat-kernel wavelets Psi(-0.5), Psi(+0.5) of the identity impulse
+    on the arxiv-shaped graph, Chebyshev order 3, tol 1e-4, float32 CSR + L1 row normalisation
+    (wavelet/src/utils.py:89-138, SSRG/models/base_scalable/base_model.py:180-265).  1 GPU."""
+    import torch
+
+    import oracle
+    from scalable_roubust_gnn_b200 import _lib, device as dev, spectral, synth
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    n, nnz, f, _ = synth.SHAPES["arxiv"]
+    n, nnz = int(n * args.scale), int(nnz * args.scale)
+    order, scale, tol = 3, 0.5, 1e-4
+    w = synth.uniform_graph(n, nnz)
+    i = np.arange(n)
+    ring = sp.coo_matrix((np.ones(n), (i, (i + 1) % n)), shape=(n, n)).tocsr()      # no isolated nodes
+    w = w.maximum(ring).maximum(ring.T).tocsr()
+    w.sort_indices()
+    x = synth.features(n, f)
+    w_dev = dev.upload_csr(w)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    lap0, _, _ = spectral.laplacian(w_dev)
+    lmax = spectral.estimate_lmax_device(lap0)
+    stats = {}
+
+    def step():
+        ws = spectral.WaveletSparsifier.__new__(spectral.WaveletSparsifier)
+        ws.n, ws.device, ws.block, ws.method, ws.stats = n, "cuda", 1000, "sparse", {}
+        ws.scales, ws.approximation_order, ws.tolerance, ws.lmax = [-scale, scale], order, tol, lmax
+        ws.lap, ws.degree, _ = spectral.laplacian(w_dev)
+        out = ws.calculate_all_wavelets_device(normalize=True)
+        stats.update(ws.stats)
+        return out
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    for _ in range(args.warmup):
+        phis = step()
+    torch.cuda.synchronize()
+    sampler.lines.clear()
+    launches0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a_, b_ in ev:
+        flush.zero_()
+        a_.record()
+        phis = step()
+        b_.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+    ms = [a_.elapsed_time(b_) for a_, b_ in ev]
+    t_step = float(np.mean(ms)) * 1e-3
+    nnz_phi = [int(p[0][-1].item()) for p in phis]
+    peak, peak_src = measured_peak()
+    # algorithmic bytes of the dominant phase (the order-3 sparse product): every expanded product is written once
+    # (8-byte key + 8-byte value) and read once by the ordered segment sum; the stable radix sort between the two moves
+    # them ~7 more times (library primitive, cub) - that is the traffic above the algorithmic figure
+    alg = stats.get("products", 0) * 32 + stats.get("pattern_nnz", 0) * (12 + 8 * 3)
+    roofline = {"bound": "hbm", "kernel": "chebysp expand -> stable key sort (cub) -> ordered fp64 segment sums -> epilogue",
+                "achieved": alg / t_step / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / t_step / 1e9 / peak,
+                "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": alg,
+                "products_expanded": stats.get("products"), "pattern_nnz_order_m": stats.get("pattern_nnz"),
+                "note": "whole step time (Laplacian + 2 sparse products + epilogues + threshold + L1 normalisation)"}
+    # end to end through the mirrored model API: scipy adjacency + numpy features in, [X | relu(Psi Psi^-1 X)] out
+    model = spectral.SpectralModel(scale, order, tol)
+    model.preprocess(w, x)
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        model = spectral.SpectralModel(scale, order, tol)
+        out = model.preprocess(w, x)
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    e2e = {"value": n / t_e2e, "unit": "impulse columns/s", "ms_per_step": t_e2e * 1e3,
+           "h2d_bytes_per_step": int(w.indptr.nbytes + w.indices.nbytes + w.data.nbytes + x.nbytes),
+           "d2h_bytes_per_step": int(out.numel() * 4),
+           "api": "SpectralModel(scale, order, tol).preprocess(scipy adjacency, float32 ndarray) -> N x 2F CPU tensor "
+                  "(includes the device Lanczos estimate of lambda_max)"}
+    cpu = None
+    if not args.no_cpu_baseline:
+        # bounded sample: ONE 1000-column impulse block of the 170 the reference evaluates, through the oracle's
+        # restatement of pygsp's cheby_op (pygsp itself is absent: kind "port"), both scales
+        lap_h = oracle.combinatorial_laplacian(w)
+        coeffs = np.stack([oracle.cheby_coeff_heat(t, lmax, order) for t in (-scale, scale)])
+        blk = min(1000, n)
+        imp = np.zeros((n, blk))
+        imp[np.arange(blk), np.arange(blk)] = 1.0
+        t0 = time.perf_counter()
+        res = oracle.cheby_op(lap_h, coeffs, imp, lmax)
+        for r in res:
+            oracle.wavelet_threshold(r, tol)
+        dt = time.perf_counter() - t0
+        cpu = {"value": blk / dt, "unit": "impulse columns/s", "cores": 1, "kind": "port",
+               "sample": f"one {blk}-column impulse block of {-(-n // 1000)} (oracle.cheby_op + threshold, scipy fp64, both scales): {dt:.2f} s"}
+    line = {"metric": "heat-wavelet sparsification throughput (Chebyshev m=3, scales -0.5/+0.5, identity impulse)",
+            "value": n / t_step, "unit": "impulse columns/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "arxiv-shaped synthetic uniform graph, wavelet/Chebyshev spectral filter (BASELINE config 3)",
+                       "N": n, "nnz": int(w.nnz), "order": order, "scales": [-scale, scale], "tol": tol, "lmax": lmax,
+                       "nnz_psi": nnz_phi, "scale": args.scale, "l2": "flushed between steps"},
+            "step_ms_all": [round(v, 3) for v in ms], "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks}
+    emit(line)
+
+
 def main():
     # stdout must carry ONE JSON line, but libraries (NCCL's version banner) write to fd 1 too: keep a
     # private copy of the real stdout for the JSON and point fd 1 at stderr for everybody else
@@ -419,11 +535,21 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="products", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="products", choices=sorted(WORKLOADS) + ["arxiv-cheby", "products-rmat"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink N and nnz (smoke runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.workload in RMAT_WORKLOADS:
+        _GRAPH_KIND["kind"] = "rmat"
+    if args.workload == "arxiv-cheby":
+        if args.impl == "reference":
+            emit({"impl": "reference", "unavailable": "config 3 runs through pygsp in the reference; pygsp is absent from the image "
+                                                      "(see cpu_baseline of the --impl ours line for the oracle port)"})
+            return
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_cheby(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

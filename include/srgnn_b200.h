@@ -318,6 +318,13 @@ int srg_cheby_sparse_fetch(void *handle, int32_t scale, int32_t *indptr, int32_t
                            void *stream);
 int srg_cheby_sparse_free(void *handle);
 
+/* Largest eigenvalue of a symmetric CSR matrix (the Laplacian) by Lanczos with full re-orthogonalisation, fp64, on
+ * the device: what pygsp's Graph.estimate_lmax obtains from ARPACK (eigsh k=1, tol 5e-3; wavelet/src/utils.py:83,
+ * SSRG/models/base_scalable/base_model.py:184) before multiplying by 1.01.  Stops when the top Ritz value moved by
+ * less than tol / 10 over two steps, or after max_steps (<= 256).  Set-up path: synchronises the stream. */
+int srg_lanczos_lambda_max_f64(const int32_t *indptr, const int32_t *indices, const double *vals, int64_t n,
+                               double tol, int32_t max_steps, double *out_lambda, int32_t *out_steps, void *stream);
+
 /* ---- (e) row-partitioned multi-GPU hop ------------------------------------------------------- */
 /*
  * One hop over this rank's row slice with the exchange fused into the epilogue: every finished row

@@ -487,3 +487,154 @@ extern "C" int srg_cheby_sparse_free(void *handle) {
   delete r;
   return SRG_OK;
 }
+
+// ---- lambda_max of the Laplacian on the device (pygsp Graph.estimate_lmax) ----------------------------------------------
+// The reference obtains lmax from ARPACK: 1.01 * eigsh(L, k=1, tol=5e-3, ncv=min(N,10)) (wavelet/src/utils.py:83,
+// SSRG/models/base_scalable/base_model.py:184) with a random start vector, so its value is only defined to the 5e-3
+// relative tolerance of that call.  Here: Lanczos with full re-orthogonalisation in fp64 (SpMV + dots + updates are
+// kernels below; the small tridiagonal eigenvalue is a Sturm bisection on the host), stopped when the largest Ritz
+// value has moved by less than tol / 10 over two steps.  Deterministic (hashed start vector, ordered reductions).
+namespace srg {
+
+__global__ void __launch_bounds__(256)
+spmv_f64_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, const double *__restrict__ vals,
+                long long n, const double *__restrict__ x, double *__restrict__ y) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
+  double acc = 0.0;
+  for (int p = indptr[i] + lane; p < indptr[i + 1]; p += 32) acc = __fma_rn(vals[p], x[indices[p]], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) y[i] = acc;
+}
+
+// out[k] = x . V[k]  for k < count (one block per k, fixed-order tree: deterministic)
+__global__ void __launch_bounds__(1024)
+dots_f64_kernel(const double *__restrict__ x, const double *__restrict__ V, long long n, double *__restrict__ out) {
+  __shared__ double sh[1024];
+  const double *v = V + (long long)blockIdx.x * n;
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 1024) acc = __fma_rn(x[i], v[i], acc);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+// x -= sum_k c[k] V[k]
+__global__ void __launch_bounds__(256)
+project_out_kernel(double *__restrict__ x, const double *__restrict__ V, long long n, const double *__restrict__ c, int count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = x[i];
+  for (int k = 0; k < count; ++k) v = __fma_rn(-c[k], V[(long long)k * n + i], v);
+  x[i] = v;
+}
+
+__global__ void __launch_bounds__(256)
+scale_into_kernel(const double *__restrict__ x, double s, long long n, double *__restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = x[i] * s;
+}
+
+__global__ void __launch_bounds__(256) hashed_start_kernel(double *__restrict__ v, long long n, unsigned seed) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned x = (unsigned)i * 0x9e3779b1u + seed;
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  v[i] = 0.5 + (double)x * (1.0 / 4294967296.0);      // positive entries: never orthogonal to the top eigenvector's sign pattern by accident
+}
+
+// largest eigenvalue of the symmetric tridiagonal (alpha[0..m), beta[0..m-1)) by Sturm bisection
+static double tridiag_lambda_max(const std::vector<double> &a, const std::vector<double> &b) {
+  const int m = (int)a.size();
+  double lo = a[0], hi = a[0];
+  for (int i = 0; i < m; ++i) {
+    const double r = (i > 0 ? fabs(b[i - 1]) : 0.0) + (i + 1 < m ? fabs(b[i]) : 0.0);
+    lo = std::min(lo, a[i] - r);
+    hi = std::max(hi, a[i] + r);
+  }
+  for (int it = 0; it < 200 && hi - lo > 1e-15 * std::max(fabs(hi), fabs(lo)); ++it) {
+    const double x = 0.5 * (lo + hi);
+    // number of eigenvalues < x = number of negative pivots of T - x I
+    int neg = 0;
+    double d = 1.0;
+    for (int i = 0; i < m; ++i) {
+      const double bb = (i > 0) ? b[i - 1] * b[i - 1] : 0.0;
+      d = (a[i] - x) - (i > 0 ? bb / (d == 0.0 ? 1e-300 : d) : 0.0);
+      if (d < 0.0) ++neg;
+    }
+    if (neg >= m) hi = x; else lo = x;   // all eigenvalues below x: move down
+  }
+  return 0.5 * (lo + hi);
+}
+
+}  // namespace srg
+
+extern "C" int srg_lanczos_lambda_max_f64(const int32_t *indptr, const int32_t *indices, const double *vals, int64_t n,
+                                          double tol, int32_t max_steps, double *out_lambda, int32_t *out_steps,
+                                          void *stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  SRG_REQUIRE(n >= 1 && indptr && indices && vals && out_lambda, "lanczos: bad arguments");
+  SRG_REQUIRE(tol > 0.0 && max_steps >= 1, "lanczos: tol must be positive and max_steps >= 1");
+  cudaStream_t s = as_stream(stream);
+  const int m_max = (int)std::min<int64_t>(std::min<int64_t>(max_steps, n), 256);
+  StreamScratch scratch(s);
+  double *V = nullptr, *w = nullptr, *c = nullptr;
+  if ((rc = scratch.alloc(&V, (size_t)(m_max + 1) * n))) return rc;
+  if ((rc = scratch.alloc(&w, (size_t)n))) return rc;
+  if ((rc = scratch.alloc(&c, (size_t)(m_max + 2)))) return rc;
+  const unsigned nb = (unsigned)ceil_div64(n, 256), wb = (unsigned)ceil_div64(n * 32, 256);
+  std::vector<double> alpha, beta, hc(m_max + 2);
+  // v_0 = start / |start|
+  hashed_start_kernel<<<nb, 256, 0, s>>>(w, n, 2023u);
+  SRG_LAUNCHED();
+  dots_f64_kernel<<<1, 1024, 0, s>>>(w, w, n, c);
+  SRG_LAUNCHED();
+  SRG_CUDA(cudaMemcpyAsync(hc.data(), c, sizeof(double), cudaMemcpyDeviceToHost, s));
+  SRG_CUDA(cudaStreamSynchronize(s));
+  scale_into_kernel<<<nb, 256, 0, s>>>(w, 1.0 / sqrt(hc[0]), n, V);
+  SRG_LAUNCHED();
+  double theta = 0.0, theta_1 = 0.0, theta_2 = 0.0;
+  int j = 0;
+  for (; j < m_max; ++j) {
+    spmv_f64_kernel<<<wb, 256, 0, s>>>(indptr, indices, vals, n, V + (size_t)j * n, w);
+    SRG_LAUNCHED();
+    // full re-orthogonalisation against v_0..v_j (twice is enough); the coefficient on v_j is alpha_j
+    double a_j = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+      dots_f64_kernel<<<j + 1, 1024, 0, s>>>(w, V, n, c);
+      SRG_LAUNCHED();
+      project_out_kernel<<<nb, 256, 0, s>>>(w, V, n, c, j + 1);
+      SRG_LAUNCHED();
+      SRG_CUDA(cudaMemcpyAsync(hc.data(), c + j, sizeof(double), cudaMemcpyDeviceToHost, s));
+      SRG_CUDA(cudaStreamSynchronize(s));
+      a_j += hc[0];
+    }
+    alpha.push_back(a_j);
+    dots_f64_kernel<<<1, 1024, 0, s>>>(w, w, n, c);
+    SRG_LAUNCHED();
+    SRG_CUDA(cudaMemcpyAsync(hc.data(), c, sizeof(double), cudaMemcpyDeviceToHost, s));
+    SRG_CUDA(cudaStreamSynchronize(s));
+    const double b_j = sqrt(std::max(hc[0], 0.0));
+    theta_2 = theta_1;
+    theta_1 = theta;
+    theta = tridiag_lambda_max(alpha, beta);
+    const bool converged = j >= 4 && fabs(theta - theta_2) <= 0.1 * tol * fabs(theta);
+    if (converged || b_j <= 1e-14 * std::max(1.0, fabs(theta)) || j + 1 == m_max) {
+      ++j;
+      break;
+    }
+    beta.push_back(b_j);
+    scale_into_kernel<<<nb, 256, 0, s>>>(w, 1.0 / b_j, n, V + (size_t)(j + 1) * n);
+    SRG_LAUNCHED();
+  }
+  *out_lambda = theta;
+  if (out_steps) *out_steps = j;
+  return SRG_OK;
+}

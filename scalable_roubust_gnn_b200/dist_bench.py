@@ -94,7 +94,8 @@ def run(args, workloads, metric, unit, emit):
             deg = (a_loc.indptr[1:] - a_loc.indptr[:-1] + 1).to(torch.float32)
             x_loc[:, 0] = torch.sqrt(deg)
     else:
-        a = synth.uniform_graph(n, nnz)        # every rank regenerates the same graph (fixed seed) ...
+        gen_fn = synth.rmat_graph if args.workload == "products-rmat" else synth.uniform_graph
+        a = gen_fn(n, nnz)                     # every rank regenerates the same graph (fixed seed) ...
         a_loc_host = sdist.shard_rows(a, s, e)  # ... and keeps its row slice
         x_full = synth.features(n, f)
         x_loc_host = np.ascontiguousarray(x_full[s:e, st.f0:st.f1])

@@ -20,7 +20,7 @@ import torch
 from . import _lib
 from .device import DeviceCSR, _p, _stream_ptr, upload_csr
 
-__all__ = ["laplacian", "heat_cheby_coeffs", "estimate_lmax", "cheby_filter", "WaveletSparsifier", "SpectralModel",
+__all__ = ["laplacian", "heat_cheby_coeffs", "estimate_lmax", "estimate_lmax_device", "cheby_filter", "WaveletSparsifier", "SpectralModel",
            "wavelet_localize"]
 
 
@@ -55,6 +55,16 @@ def estimate_lmax(lap_host) -> float:
     from scipy.sparse.linalg import eigsh
     n = lap_host.shape[0]
     return float(eigsh(lap_host, k=1, tol=5e-3, ncv=min(n, 10), return_eigenvectors=False)[0]) * 1.01
+
+
+def estimate_lmax_device(lap: DeviceCSR, tol: float = 5e-3, max_steps: int = 100) -> float:
+    """pygsp Graph.estimate_lmax on the device: 1.01 x the largest eigenvalue of the Laplacian by Lanczos
+    (csrc/chebysp.cu), to the tolerance of the reference's ARPACK call (5e-3 relative)."""
+    lib = _lib.load()
+    lam, steps = C.c_double(), C.c_int32()
+    _lib.check(lib.srg_lanczos_lambda_max_f64(_p(lap.indptr), _p(lap.indices), _p(lap.data), lap.n, float(tol),
+                                              int(max_steps), C.byref(lam), C.byref(steps), _stream_ptr(lap.indptr.device)))
+    return float(lam.value) * 1.01
 
 
 def cheby_filter(lap: DeviceCSR, x: torch.Tensor, lmax: float, coeffs, tol: float | None = None, want_f32=False):
@@ -116,10 +126,8 @@ class WaveletSparsifier:
         self._w_dev = upload_csr(w, device=device)
         self.lap, self.degree, flags = laplacian(self._w_dev)
         if lmax is None:
-            m = int(self.lap.indptr[-1].item())
-            lap_host = sp.csr_matrix((self.lap.data[:m].cpu().numpy(), self.lap.indices[:m].cpu().numpy(),
-                                      self.lap.indptr.cpu().numpy()), shape=(self.n, self.n))
-            lmax = estimate_lmax(lap_host)
+            # device Lanczos; estimate_lmax(host Laplacian) reproduces the reference's ARPACK call for comparison
+            lmax = estimate_lmax_device(self.lap)
         self.lmax = float(lmax)
 
     def chebyshev_coefficients(self):

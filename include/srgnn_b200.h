@@ -325,6 +325,23 @@ int srg_cheby_sparse_free(void *handle);
 int srg_lanczos_lambda_max_f64(const int32_t *indptr, const int32_t *indices, const double *vals, int64_t n,
                                double tol, int32_t max_steps, double *out_lambda, int32_t *out_steps, void *stream);
 
+/* ---- (f-4) dataset augmentation before the path: edge_augument (SSRG/data_augument.py:73-103) ----------------
+ * srg_endpoint_counts_i64   Counter(cat(edge_row, edge_col)) (:75-77): counts[v] and the first position of v in the
+ *                           concatenation (INT64_MAX when v never occurs) — the Counter's insertion order, which
+ *                           breaks the ties of `sorted(counts.items(), key=degree)` (:81)
+ * srg_candidate_topk_f32    for low-degree node i (nodes[i]): L2 distances of the soft labels to cand[i, 0..cand_cnt[i])
+ *                           (compute_distance, SSRG/utils.py:35-38) and the k_sel[i] closest in ascending order,
+ *                           ties by candidate position, as pairs (node, candidate) at out_off[i]  (:88-95)
+ * srg_csr_to_edge_index_i64 2 x nnz int64 edge list of a CSR pattern in (row, col) order = torch.unique(dim=1) of the
+ *                           symmetrised list (:97-102) when the CSR comes from srg_edges_to_sym_csr */
+int srg_endpoint_counts_i64(const int64_t *row, const int64_t *col, int64_t m, int64_t n, int32_t *counts,
+                            int64_t *first_pos, int32_t *flags, void *stream);
+int srg_candidate_topk_f32(const float *soft, int64_t ld, int64_t n, int32_t n_classes, const int32_t *nodes,
+                           const int32_t *cand, const int32_t *cand_cnt, const int32_t *k_sel, const int32_t *out_off,
+                           int32_t c_max, int32_t n_low, int64_t *out_src, int64_t *out_dst, void *stream);
+int srg_csr_to_edge_index_i64(const int32_t *indptr, const int32_t *indices, int64_t n, int64_t nnz,
+                              int64_t *out_edge_index, void *stream);
+
 /* ---- (e) row-partitioned multi-GPU hop ------------------------------------------------------- */
 /*
  * One hop over this rank's row slice with the exchange fused into the epilogue: every finished row

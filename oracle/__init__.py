@@ -539,3 +539,45 @@ def row_partition(n, world):
     rows_per = -(-n // world)
     starts = np.minimum(np.arange(world + 1, dtype=np.int64) * rows_per, n)
     return rows_per, starts
+
+
+# ---- dataset augmentation: edge_augument (SSRG/data_augument.py:73-103) ------------------------------------------
+def edge_augument(edge_row, edge_col, n, soft_label, degree_level=1, seed=None):
+    """CPU restatement of edge_augument (test infrastructure; pinned to outputs of the reference's own function by
+    tests/golden/reference_augment.npz).  Follows the reference line by line:
+      :75-80  counts = Counter(cat(row, col)); nodes that never occur are appended with count 0
+      :81     visiting order = stable sort of the Counter's items by count
+      :83-85  stop at the first node whose count reaches degree_level
+      :87     100 * deficit candidates: generate_numbers (SSRG/utils.py:29-33) = remove node, random.sample, append node
+      :88-92  L2 distance of the soft labels (SSRG/utils.py:35-38, float32), ascending sort
+      :93-96  the `deficit` closest candidates become edges (node -> candidate)
+      :97-102 cat both directions, torch.unique(dim=1)  (= lexicographic (row, col) order, duplicates dropped)
+    `seed`: random.seed(seed) before the first draw (seed_everything), None = use the stream as it is."""
+    import random
+    from collections import Counter
+    edge_row = np.asarray(edge_row, dtype=np.int64)
+    edge_col = np.asarray(edge_col, dtype=np.int64)
+    soft = np.asarray(soft_label, dtype=np.float32)
+    if seed is not None:
+        random.seed(seed)
+    counts = Counter(np.concatenate([edge_row, edge_col]).tolist())
+    for i in range(n):
+        if i not in counts:
+            counts.update({i: 0})
+    src, dst = [edge_row], [edge_col]
+    numbers = list(range(n))
+    for node, degree in sorted(counts.items(), key=lambda kv: kv[1]):
+        if degree >= degree_level:
+            break
+        deficit = degree_level - degree
+        numbers.remove(node)
+        cand = random.sample(numbers, deficit * 100)
+        numbers.append(node)
+        diff = soft[node][None, :] - soft[cand]                        # float32, as repeat_feature - candidates
+        dist = np.sqrt((diff.astype(np.float64) ** 2).sum(1)).astype(np.float32)
+        order = np.argsort(dist, kind="stable")
+        src.append(np.full(deficit, node, dtype=np.int64))
+        dst.append(np.asarray(cand, dtype=np.int64)[order[:deficit]])
+    r, c = np.concatenate(src), np.concatenate(dst)
+    both = np.stack([np.concatenate([r, c]), np.concatenate([c, r])])
+    return np.unique(both, axis=1)

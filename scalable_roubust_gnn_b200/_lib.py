@@ -106,6 +106,9 @@ SIGNATURES = {
     "srg_cheby_sparse_info": (C.c_int, [_vp, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "srg_cheby_sparse_fetch": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),
     "srg_cheby_sparse_free": (C.c_int, [_vp]),
+    "srg_endpoint_counts_i64": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "srg_candidate_topk_f32": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "srg_csr_to_edge_index_i64": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "srg_lanczos_lambda_max_f64": (C.c_int, [_vp, _vp, _vp, _i64, _f64, _i32, C.POINTER(_f64), C.POINTER(_i32), _vp]),
     "srg_pack_features_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp]),
     "srg_unpack_features_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),

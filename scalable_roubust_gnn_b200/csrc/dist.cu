@@ -206,56 +206,67 @@ extern "C" int srg_dist_propagate(void *handle, const int32_t *indptr, const int
   const int64_t n_loc = h->n_local, cap = std::max<int64_t>(nnz + n_loc, 1), ld = h->ld;
   const int F = h->F;
 
-  // ---- normalisation of the local rows: structure, degrees, ONE all-gather of the degree vector, values ------
+  // Every rank issues the SAME sequence of collectives whatever happens locally: a rank whose local stage failed
+  // keeps taking part (its slices are then meaningless, the error code tells), so no peer is left waiting inside an
+  // ncclAllGather.  Scratch is scoped: every return path hands its blocks back.
+  StreamScratch scratch(s);
   int32_t *at_indptr = nullptr, *at_indices = nullptr;
   double *at_val = nullptr, *dl = nullptr, *dr = nullptr;
   float *val32 = nullptr;
-  SRG_CUDA(cudaMallocAsync(&at_indptr, (size_t)(n_loc + 1) * sizeof(int32_t), s));
-  SRG_CUDA(cudaMallocAsync(&at_indices, (size_t)cap * sizeof(int32_t), s));
-  if (val_dtype != SRG_VAL_ONES) SRG_CUDA(cudaMallocAsync(&at_val, (size_t)cap * sizeof(double), s));
-  SRG_CUDA(cudaMallocAsync(&dl, (size_t)std::max<int64_t>(h->n_pad, 1) * sizeof(double), s));
-  SRG_CUDA(cudaMallocAsync(&dr, (size_t)std::max<int64_t>(h->n_pad, 1) * sizeof(double), s));
-  SRG_CUDA(cudaMallocAsync(&val32, (size_t)cap * sizeof(float), s));
+  rc = scratch.alloc(&at_indptr, (size_t)(n_loc + 1));
+  if (!rc) rc = scratch.alloc(&at_indices, (size_t)cap);
+  if (!rc && val_dtype != SRG_VAL_ONES) rc = scratch.alloc(&at_val, (size_t)cap);
+  if (!rc) rc = scratch.alloc(&dl, (size_t)std::max<int64_t>(h->n_pad, 1));
+  if (!rc) rc = scratch.alloc(&dr, (size_t)std::max<int64_t>(h->n_pad, 1));
+  if (!rc) rc = scratch.alloc(&val32, (size_t)cap);
+  auto keep = [&rc](int r2) {
+    if (!rc && r2) rc = r2;
+  };
+  auto cuda_rc = [&](cudaError_t e, const char *what) {
+    if (e != cudaSuccess) keep(cuda_fail(e, what, __FILE__, __LINE__));
+  };
+  auto gather = [&](const void *send, void *recv, size_t count, ncclDataType_t dt) {
+    if (h->world <= 1) return;
+    const ncclResult_t e = g_nccl.AllGather(send, recv, count, dt, h->comm, s);
+    if (e != ncclSuccess) {
+      if (!rc) {
+        set_err("ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+        rc = SRG_ERR_CUDA;
+      }
+    }
+  };
+
+  // ---- normalisation of the local rows: structure, degrees, ONE all-gather of the degree vector, values ------
   double *deg_loc = h->deg_all + (int64_t)h->rank * h->rows_per;
-  rc = srg_selfloop_rows_csr(indptr, indices, data, val_dtype, n_loc, nnz, h->row0, h->n, at_indptr, nullptr, flags, s);
+  if (!rc) keep(srg_selfloop_rows_csr(indptr, indices, data, val_dtype, n_loc, nnz, h->row0, h->n, at_indptr, nullptr, flags, s));
   if (!rc)
-    rc = srg_selfloop_fill_rows_csr(indptr, indices, data, val_dtype, n_loc, nnz, h->row0, h->n, at_indptr, at_indices,
-                                    at_val, deg_loc, flags, s);
-  if (!rc && h->world > 1)
-    SRG_NCCL(g_nccl.AllGather(deg_loc, h->deg_all, (size_t)h->rows_per, ncclDouble, h->comm, s));   // in place
-  if (!rc) rc = srg_pow_tables_f64(h->deg_all, h->n_pad, r, dl, dr, s);
+    keep(srg_selfloop_fill_rows_csr(indptr, indices, data, val_dtype, n_loc, nnz, h->row0, h->n, at_indptr, at_indices,
+                                    at_val, deg_loc, flags, s));
+  gather(deg_loc, h->deg_all, (size_t)h->rows_per, ncclDouble);   // in place
+  if (!rc) keep(srg_pow_tables_f64(h->deg_all, h->n_pad, r, dl, dr, s));
   if (!rc)
-    rc = srg_norm_values_rows_csr(at_indptr, at_indices, at_val, deg_loc, n_loc, nnz + n_loc, h->row0, h->n_pad, dl, dr,
-                                  ppr_alpha, 0, nullptr, val32, flags, s);
+    keep(srg_norm_values_rows_csr(at_indptr, at_indices, at_val, deg_loc, n_loc, nnz + n_loc, h->row0, h->n_pad, dl, dr,
+                                  ppr_alpha, 0, nullptr, val32, flags, s));
 
   // ---- hops: slice into the full buffer, all-gather, local SpMM ------------------------------------------------
   int cur = 0;
   if (!rc && n_loc > 0)
-    SRG_CUDA(cudaMemcpy2DAsync(h->full[0] + h->row0 * ld, (size_t)ld * 4, x_local, (size_t)ld_x * 4, (size_t)F * 4,
-                               (size_t)n_loc, cudaMemcpyDeviceToDevice, s));
+    cuda_rc(cudaMemcpy2DAsync(h->full[0] + h->row0 * ld, (size_t)ld * 4, x_local, (size_t)ld_x * 4, (size_t)F * 4,
+                              (size_t)n_loc, cudaMemcpyDeviceToDevice, s), "cudaMemcpy2DAsync");
   if (!rc && out_hops && out_hops[0] && n_loc > 0)
-    SRG_CUDA(cudaMemcpy2DAsync(out_hops[0], (size_t)ld_out * 4, x_local, (size_t)ld_x * 4, (size_t)F * 4, (size_t)n_loc,
-                               cudaMemcpyDeviceToDevice, s));
+    cuda_rc(cudaMemcpy2DAsync(out_hops[0], (size_t)ld_out * 4, x_local, (size_t)ld_x * 4, (size_t)F * 4, (size_t)n_loc,
+                              cudaMemcpyDeviceToDevice, s), "cudaMemcpy2DAsync");
   const size_t slice = (size_t)h->rows_per * ld;
-  if (!rc && h->world > 1)
-    SRG_NCCL(g_nccl.AllGather(h->full[0] + (int64_t)h->rank * slice, h->full[0], slice, ncclFloat, h->comm, s));
-  for (int k = 1; k <= K && !rc; ++k) {
+  gather(h->full[0] + (int64_t)h->rank * slice, h->full[0], slice, ncclFloat);
+  for (int k = 1; k <= K; ++k) {
     const int nxt = cur ^ 1;
     float *y = h->full[nxt] + h->row0 * ld;
-    rc = srg_spmm_csr_f32(at_indptr, at_indices, val32, n_loc, nnz + n_loc, h->full[cur], ld, y, ld, F, s);
-    if (rc) break;
-    if (h->world > 1)
-      SRG_NCCL(g_nccl.AllGather(h->full[nxt] + (int64_t)h->rank * slice, h->full[nxt], slice, ncclFloat, h->comm, s));
-    if (out_hops && out_hops[k] && n_loc > 0)
-      SRG_CUDA(cudaMemcpy2DAsync(out_hops[k], (size_t)ld_out * 4, y, (size_t)ld * 4, (size_t)F * 4, (size_t)n_loc,
-                                 cudaMemcpyDeviceToDevice, s));
+    if (!rc) keep(srg_spmm_csr_f32(at_indptr, at_indices, val32, n_loc, nnz + n_loc, h->full[cur], ld, y, ld, F, s));
+    gather(h->full[nxt] + (int64_t)h->rank * slice, h->full[nxt], slice, ncclFloat);
+    if (!rc && out_hops && out_hops[k] && n_loc > 0)
+      cuda_rc(cudaMemcpy2DAsync(out_hops[k], (size_t)ld_out * 4, y, (size_t)ld * 4, (size_t)F * 4, (size_t)n_loc,
+                                cudaMemcpyDeviceToDevice, s), "cudaMemcpy2DAsync");
     cur = nxt;
   }
-  cudaFreeAsync(val32, s);
-  cudaFreeAsync(dr, s);
-  cudaFreeAsync(dl, s);
-  if (at_val) cudaFreeAsync(at_val, s);
-  cudaFreeAsync(at_indices, s);
-  cudaFreeAsync(at_indptr, s);
   return rc;
 }

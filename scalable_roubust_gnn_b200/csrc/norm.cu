@@ -413,10 +413,23 @@ void set_exact_sym_check(int v) { g_exact_sym_check = v; }
 // rows longer than kHubLen (power-law hubs): registered by the tile kernel that owns them, processed by a second
 // launch whose blocks ALL stride over the hub's entries (a 10^6-entry row would otherwise be one block's loop)
 struct HubList {
-  int *count;   // device counter
-  int *rows;    // [cap] local row ids
+  int *count;   // device counter of SEGMENTS
+  int *rows;    // [cap] local row id of the segment
+  int *lo;      // [cap] first entry of the segment
+  int *hi;      // [cap] one past its last entry
   int cap;
 };
+
+// a hub row is cut into kHubLen-entry segments; the hub kernels give one block to each segment
+__device__ __forceinline__ void hub_register(const HubList &h, int row, int s, int e) {
+  const int ns = (e - s + kHubLen - 1) / kHubLen;
+  const int i0 = atomicAdd(h.count, ns);
+  for (int k = 0; k < ns && i0 + k < h.cap; ++k) {
+    h.rows[i0 + k] = row;
+    h.lo[i0 + k] = s + k * kHubLen;
+    h.hi[i0 + k] = min(e, s + (k + 1) * kHubLen);
+  }
+}
 
 // largest t in [0, nr) with cp[t] <= c  (rows may be empty / skipped: the LAST of equal pointers owns the entry)
 __device__ __forceinline__ int tile_row_of(const int *cp, int nr, int c) {
@@ -449,10 +462,7 @@ __device__ __forceinline__ int tile_setup(const int *__restrict__ ptr, long long
     return total0;
   }
   if (hub) {
-    if (hubs) {
-      const int i = atomicAdd(hubs->count, 1);
-      if (i < hubs->cap) hubs->rows[i] = (int)(r0 + threadIdx.x);
-    }
+    if (hubs) hub_register(*hubs, (int)(r0 + threadIdx.x), rp[threadIdx.x], rp[threadIdx.x + 1]);
     len = 0;
   }
   int total;
@@ -523,11 +533,11 @@ hub_count_kernel(const int *__restrict__ indptr, const int *__restrict__ indices
                  long long row0, long long n_cols, int *__restrict__ rowlen, int *__restrict__ flags, HubList hubs) {
   const int nh = min(*hubs.count, hubs.cap);
   int fl = 0;
-  for (int h = 0; h < nh; ++h) {
+  for (int h = blockIdx.x; h < nh; h += gridDim.x) {
     const int a = hubs.rows[h];
     const int s = indptr[a], e = indptr[a + 1];
     const int ag = (int)(a + row0);
-    for (long long j = (long long)s + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < e; j += (long long)gridDim.x * blockDim.x) {
+    for (int j = hubs.lo[h] + threadIdx.x; j < hubs.hi[h]; j += blockDim.x) {
       const int b = ld_stream_i32(indices + j);
       const int pb = (j > s) ? __ldg(indices + j - 1) : -1;
       const double v = (DT != SRG_VAL_ONES) ? ValLoad<DT>::at(data, j) : 1.0;
@@ -603,13 +613,13 @@ hub_fill_unweighted_kernel(const int *__restrict__ indptr, const int *__restrict
   const int f = *flags;
   if ((f & kFatal) || (dt_can_be_weighted && (f & kWeighted))) return;
   const int nh = min(*hubs.count, hubs.cap);
-  for (int h = 0; h < nh; ++h) {
+  for (int h = blockIdx.x; h < nh; h += gridDim.x) {
     const int a = hubs.rows[h];
     const int s = indptr[a], e = indptr[a + 1];
     const int ap_t = at_indptr[a];
     const int hd = ((at_indptr[a + 1] - ap_t) == (e - s)) ? 1 : 0;
     const int ag = (int)(a + row0);
-    for (long long j = (long long)s + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < e; j += (long long)gridDim.x * blockDim.x) {
+    for (int j = hubs.lo[h] + threadIdx.x; j < hubs.hi[h]; j += blockDim.x) {
       const int b = ld_stream_i32(indices + j);
       const int pb = (j > s) ? __ldg(indices + j - 1) : -1;
       fill_entry((int)j, b, pb, s, e, ag, ap_t, hd, at_indices);
@@ -751,13 +761,13 @@ hub_values_kernel(long long row0, const int *__restrict__ at_indptr, const doubl
   const int nh = min(*hubs.count, hubs.cap);
   int fl = 0;
   unsigned long long s1 = 0, s2 = 0;
-  for (int h = 0; h < nh; ++h) {
+  for (int h = blockIdx.x; h < nh; h += gridDim.x) {
     const int a = hubs.rows[h];
     const int s = at_indptr[a], e = at_indptr[a + 1];
     const int ag = (int)(a + row0);
     const double dla = dl[ag];
     const double dgv = degree[a] - (double)(e - s - 1);
-    for (long long p = (long long)s + (long long)blockIdx.x * blockDim.x + threadIdx.x; p < e; p += (long long)gridDim.x * blockDim.x) {
+    for (int p = hubs.lo[h] + threadIdx.x; p < hubs.hi[h]; p += blockDim.x) {
       const int b = ld_stream_i32(g.at_indices + p);
       const double vt = weighted ? g.at_val[p] : ((b == ag) ? dgv : 1.0);
       values_entry(g, (int)p, b, vt, dla, __ldg(g.dr + b), ag, weighted, fl, s1, s2);
@@ -772,10 +782,12 @@ struct HubHolder {
   int *base = nullptr;
 };
 static int make_hub_list(int64_t nnz_bound, cudaStream_t s, HubHolder *o) {
-  const int64_t cap = nnz_bound / kHubLen + 1;
-  SRG_CUDA(cudaMallocAsync(&o->base, (size_t)(1 + cap) * sizeof(int), s));
+  const int64_t cap = 2 * (nnz_bound / kHubLen) + 2;   // segments: <= len / kHubLen + 1 per hub row
+  SRG_CUDA(cudaMallocAsync(&o->base, (size_t)(1 + 3 * cap) * sizeof(int), s));
   o->h.count = o->base;
   o->h.rows = o->base + 1;
+  o->h.lo = o->h.rows + cap;
+  o->h.hi = o->h.lo + cap;
   o->h.cap = (int)cap;
   SRG_CUDA(cudaMemsetAsync(o->base, 0, sizeof(int), s));
   return SRG_OK;

@@ -140,7 +140,13 @@ def test_spgemm_matches_scipy_pattern_and_values(a, seed):
     want.sort_indices()
     np.testing.assert_array_equal(got.indptr, want.indptr)
     np.testing.assert_array_equal(got.indices, want.indices)
-    np.testing.assert_allclose(got.data, want.data, rtol=2e-5, atol=5e-6)      # signed terms may nearly cancel
+    # Tolerance, and why it is not 1e-5 / 1e-6: `want` is the float64 product rounded once; the device sums float32
+    # products sequentially in ascending k (the order one of the reference's dense sgemm kernels may use,
+    # SSRG/operators/utils.py:216-219).  With up to ~n <= 40 signed terms of magnitude <= 1 per entry the float32
+    # chain carries an absolute error of up to n * 2^-24 * max|term| ~ 2.4e-6 that does NOT shrink when the terms
+    # cancel, hence the absolute floor of 5e-6 (2x that bound); entries that do not cancel agree to 2e-5 relative
+    # (n * eps32 = 40 * 6e-8 = 2.4e-6 would do; 2e-5 leaves room for hypothesis' adversarial magnitudes).
+    np.testing.assert_allclose(got.data, want.data, rtol=2e-5, atol=5e-6)
 
 
 @st.composite
@@ -168,7 +174,13 @@ def test_magnetic_norm_matches_oracle_on_arbitrary_digraphs(case, ppr):
     for got, want in ((got_re, want_re), (got_im, want_im)):
         assert_same_structure(got, want)
         if want.nnz:
-            np.testing.assert_allclose(got.data, want.data, rtol=1e-14, atol=1e-15)   # pow / sincos: an ulp or two per factor
+            # Tolerance (float64): every value is a product of four factors - d_u^(r-1), the symmetrised weight,
+            # d_v^(-r) and cos / sin(2 pi q theta).  The oracle takes pow / cos / sin from the host libm, the kernel from
+            # CUDA's (documented <= 2 ulp for pow, <= 2 ulp for sincos); neither is correctly rounded, so the two may
+            # differ by up to ~(2 + 2 + 2) ulp of the factors plus 3 roundings of the products: <= ~10 ulp = 2.2e-15
+            # relative.  1e-14 is 4-5x that bound; the absolute floor 1e-15 covers sin(2 pi q theta) values that
+            # should be exactly 0 and come out as ~1e-16 in one of the two libraries.
+            np.testing.assert_allclose(got.data, want.data, rtol=1e-14, atol=1e-15)
 
 
 @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
@@ -185,6 +197,13 @@ def test_nafs_properties(n, f, hops, seed):
     assert (w > 0).all()
     np.testing.assert_allclose(w.sum(1), 1.0, atol=2e-6)
     want, w_want = oracle.nafs_combine(feats, return_weights=True)
+    # Tolerance (north star: 1e-5 relative / 1e-6 absolute for propagated features; this is the aggregator on top).
+    # The softmax weights come from float32 dot products over up to 150 columns reduced in a different order than
+    # the oracle's (butterfly over lanes vs sequential): relative error ~sqrt(f) * eps32 ~ 7e-7 on the cosine, which
+    # exp() passes through unamplified (|score| <= 1), and up to 9 hops are normalised by their sum => a few 1e-6
+    # relative on a weight; standard-normal inputs make the combination's terms cancel, so the output carries the
+    # same few 1e-6 as an ABSOLUTE error (|x| ~ 1).  2e-5 / 2e-6 is ~4x the estimate; the reference's own torch
+    # kernels (vectorised exp / norm) are not bit-reproducible across builds either.
     np.testing.assert_allclose(w, w_want, rtol=2e-5, atol=1e-7)
     np.testing.assert_allclose(out[:, :f].cpu().numpy(), want, rtol=2e-5, atol=2e-6)
     same = [devs[0]] * hops

@@ -111,7 +111,9 @@ class DistState:
             mode = "push"
             _lib.set_tuning("push_tma", 1)
         elif mode == "push":
-            _lib.set_tuning("push_tma", int(os.environ.get("SRG_PUSH_TMA", "0")))
+            # rows wider than the bulk-gather kernel takes (LDGSTS stream kernel): the bulk-store tile epilogue is the
+            # default (4 GPUs, 4 x 1: 5.52 vs 5.66 ms per step; 2 GPUs: 2.27 vs 2.30 ms per hop); SRG_PUSH_TMA=0 = st.global
+            _lib.set_tuning("push_tma", int(os.environ.get("SRG_PUSH_TMA", "1")))
         self.n, self.f, self.world, self.rank, self.mode, self.group = n, f, world, rank, mode, group
         self.feat_groups = int(feat_groups)
         self.ri, self.ci = grid_coords(rank, world, self.feat_groups)

@@ -42,11 +42,12 @@ def _bind_to_gpu_numa_node(torch, local_rank):
 
 def default_feat_groups(world, mode):
     """Row blocks x feature slices of the default grid.  A pure row partition makes every rank RECEIVE (P-1)/P of X
-    per hop; from 4 GPUs on that exchange is as long as the local hop, so the features are split in two (the exchange
+    per hop; at 8 GPUs that exchange (1.14 ms) is twice the local hop, so the features are split in two (the exchange
     volume halves, the gathered rows become 224 bytes wide - the shape the bulk-gather kernel is built for)."""
     if mode not in ("push", "copy", "push_tma"):
         return "1"
-    return "2" if world >= 4 else "1"
+    # measured (products shape, ms per step): 4 GPUs 4 x 1 5.52 vs 2 x 2 6.12; 8 GPUs 4 x 2 3.6 vs 8 x 1 6.8 (round 1)
+    return "2" if world >= 8 else "1"
 
 
 def run(args, workloads, metric, unit, emit):

@@ -328,7 +328,8 @@ def adj_to_fast_ppr_approx_symmetric_norm(adj, r, ppr_alpha, max_iter=100, devic
     normaliser of SymDirFastPprApproxGraphOp): stationary distribution of the teleporting walk by fixed-point sweeps
     (fp64, same stopping rule: |x - x_old|_2 <= 1e-6 or ``max_iter`` sweeps), the symmetrised Laplacian
     ``(Pi^1/2 P Pi^-1/2 + Pi^-1/2 P^T Pi^1/2) / 2`` and the float32 degree normalisation.  Returns a
-    ``scipy.sparse.csr_matrix`` with float32 data.  Round-1 status: not yet run on hardware (opt-in test)."""
+    ``scipy.sparse.csr_matrix`` with float32 data.  Compared with the reference's own outputs on hardware
+    (tests/test_fast_ppr.py, tests/golden/reference_ext.npz)."""
     from ..sparse_mm import csr_sym_scale, csr_to_scipy, csr_transpose
     from ..device import DeviceCSR
     lib = _lib.load()
@@ -337,6 +338,8 @@ def adj_to_fast_ppr_approx_symmetric_norm(adj, r, ppr_alpha, max_iter=100, devic
     if not sp.issparse(adj):
         raise TypeError("The adjacency matrix must be a scipy sparse matrix!")
     csr = adj.tocsr() if not isinstance(adj, sp.csr_matrix) else adj
+    if csr.shape[0] == 0:                                             # empty graph: nothing to normalise (and no 1 / n)
+        return sp.csr_matrix((0, 0), dtype=np.float32)
     dev = torch.device("cuda", int(device))
     with torch.cuda.device(dev):
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -380,8 +383,8 @@ def adj_to_slow_first_second_ppr_approx_symmetric_norm(adj, r, ppr_alpha, device
     vector is the fixed point of the same matrix by power iteration in fp64 (it agrees with LAPACK's float32 result
     to float32 accuracy), the first-order Laplacian is the pi-weighted symmetrisation, the second-order one is
     ``(P^T P + P P^T) / 2`` on the entries where both products are non-zero (sparse x sparse products), both
-    degree-normalised in float32.  Returns two ``scipy.sparse.csr_matrix`` (float32).
-    Round-1 status: not yet run on hardware (opt-in test)."""
+    degree-normalised in float32.  Returns two ``scipy.sparse.csr_matrix`` (float32).  Compared with the reference's own
+    outputs on hardware (tests/test_fast_ppr.py)."""
     from ..device import DeviceCSR
     from ..sparse_mm import csr_sym_scale, csr_to_scipy, csr_transpose, spgemm
     lib = _lib.load()
@@ -390,6 +393,8 @@ def adj_to_slow_first_second_ppr_approx_symmetric_norm(adj, r, ppr_alpha, device
     if not sp.issparse(adj):
         raise TypeError("The adjacency matrix must be a scipy sparse matrix!")
     csr = adj.tocsr() if not isinstance(adj, sp.csr_matrix) else adj
+    if csr.shape[0] == 0:
+        return sp.csr_matrix((0, 0), dtype=np.float32), sp.csr_matrix((0, 0), dtype=np.float32)
     dev = torch.device("cuda", int(device))
     with torch.cuda.device(dev):
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)

@@ -121,6 +121,9 @@ def spmm(a: DeviceCSR, x: torch.Tensor, f: int | None = None, out: torch.Tensor 
     rows = a.n if n_rows is None else n_rows
     if out is None:
         out = torch.empty((rows, x.shape[1]), dtype=torch.float32, device=x.device)
+        w4 = (f + 3) // 4 * 4
+        if out.shape[1] > w4:
+            out[:, w4:].zero_()      # the kernels write whole float4 columns up to F: keep the remaining pad columns zero
     _lib.check(lib.srg_spmm_csr_f32(_p(a.indptr), _p(a.indices), _p(a.data), rows, a.nnz_bound, _p(x), x.stride(0),
                                     _p(out), out.stride(0), f, _stream_ptr(x.device)))
     return out
@@ -132,6 +135,10 @@ def propagate(a_norm: DeviceCSR, x0: torch.Tensor, f: int, k: int, hops: list | 
     n, ld = x0.shape
     if hops is None:
         hops = [x0] + [torch.empty_like(x0) for _ in range(k)]
+        w4 = (f + 3) // 4 * 4
+        if ld > w4:
+            for h in hops[1:]:
+                h[:, w4:].zero_()    # pad columns beyond the last float4 of F are never written by the hop kernels
     ptrs = (C.c_void_p * (k + 1))(*[h.data_ptr() for h in hops])
     _lib.check(lib.srg_propagate_khop_f32(_p(a_norm.indptr), _p(a_norm.indices), _p(a_norm.data), n, a_norm.nnz_bound,
                                           ptrs, ld, f, k, _stream_ptr(x0.device)))

@@ -517,7 +517,11 @@ def test_products_scale_properties():
     xp = dev.pack_features(x)
     hops = dev.propagate(norm, xp, f, 3)
     y1 = dev.spmm(norm, xp, f)
-    assert torch.equal(y1, hops[1]) and torch.equal(dev.spmm(norm, y1, f), hops[2])      # (c), (d)
+    # (c), (d) on the logical columns and on the whole padded buffers (pad columns are zero by construction)
+    y2 = dev.spmm(norm, y1, f)
+    assert torch.equal(y1[:, :f], hops[1][:, :f]) and torch.equal(y2[:, :f], hops[2][:, :f])
+    assert torch.equal(y1, hops[1]) and torch.equal(y2, hops[2])
+    assert float(y1[:, f:].abs().sum()) == 0.0
     # (b) sampled rows, exact
     rng = np.random.default_rng(5)
     rows = np.sort(rng.choice(n, 256, replace=False))

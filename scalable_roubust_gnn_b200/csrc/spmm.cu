@@ -52,6 +52,7 @@ static int g_bulk_stages = 2;    // chunks of 32 neighbour rows in flight per wa
 static int g_bulk_rows = 8;      // rows per warp task of the bulk kernel (1..32); 8 measured best (profiles/r02_hop_shard_sweep.log)
 static int g_push_rows_blocks = 148;   // grid of the input-exchange kernel (one block per SM by default)
 static int g_push_rows_tma = 1;        // input exchange through the TMA unit (bulk load + bulk stores) instead of st.global
+static int g_push_rows_tma_blocks = 48;   // its grid (one warp per block)
 static int g_bulk_tile = 0;      // 1: finished rows are staged in shared memory and leave as ONE bulk store per destination
 
 // ---- vector abstraction for the group kernel: float4 fast path, float scalar path ------------------
@@ -989,6 +990,7 @@ extern "C" int srg_set_tuning(const char *key, int64_t value) {
   else if (k == "exact_sym_check") set_exact_sym_check((int)value);
   else if (k == "push_rows_blocks") g_push_rows_blocks = (int)std::max<int64_t>(1, value);
   else if (k == "push_rows_tma") g_push_rows_tma = (int)value;
+  else if (k == "push_rows_tma_blocks") g_push_rows_tma_blocks = (int)std::max<int64_t>(1, value);
   else if (k == "bulk_gather") g_bulk_gather = (int)value;
   else if (k == "bulk_auto") g_bulk_auto = (int)value;
   else if (k == "bulk_min") g_bulk_min = (int)value;
@@ -1211,7 +1213,10 @@ extern "C" int srg_push_rows_f32(const float *src, int64_t n_rows, int64_t ld, f
   const long long n_vec = n_rows * (ld / 4);
   if (g_push_rows_tma) {
     const long long n_bytes = n_vec * 16;
-    const int blocks = (int)std::min<int64_t>(ceil_div64(n_bytes, kPushChunk), g_push_rows_blocks);
+    // 48 warps (2 x 32 KB in flight each) already fill the NVLink egress and leave two thirds of the SMs undisturbed
+    // for the normalisation this exchange overlaps: 8 GPUs, ms per step with 24 / 48 / 96 / 148 blocks = 3.98 / 3.44 /
+    // 3.51 / 3.54 (profiles/r02_bench_n8_input_exchange_ab.txt)
+    const int blocks = (int)std::min<int64_t>(ceil_div64(n_bytes, kPushChunk), std::min(g_push_rows_blocks, g_push_rows_tma_blocks));
     const size_t smem = 2 * kPushChunk + 16;
     SRG_CUDA(cudaFuncSetAttribute(push_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     push_rows_tma_kernel<<<blocks, 32, smem, as_stream(stream)>>>(reinterpret_cast<const float4 *>(src), n_bytes, pd);

@@ -475,6 +475,30 @@ __device__ __forceinline__ int tile_setup(const int *__restrict__ ptr, long long
   return total;
 }
 
+// Entry-to-thread mapping of the tile loops: a thread takes kGroup CONSECUTIVE compacted entries, so the row of the
+// first comes from ONE binary search and the rows of the others from a short linear advance (rows are ~25 entries
+// long).  ncu showed the first version (one search per entry) issue-bound at 152 thread-instructions per entry.
+constexpr int kGroup = 4;
+// rows / positions of the entries c0 .. c0 + kGroup - 1 (those < total); returns how many are valid
+__device__ __forceinline__ int tile_group(const int *rp, const int *cp, int nr, int total, int c0, int *tt, int *jj) {
+  if (c0 >= total) return 0;
+  int t = tile_row_of(cp, nr, c0);
+  const int cnt = min(kGroup, total - c0);
+#pragma unroll
+  for (int v = 0; v < kGroup; ++v) {
+    if (v < cnt) {
+      const int c = c0 + v;
+      while (c >= cp[t + 1]) ++t;      // cp[nr..] = total: stops inside the tile; skipped (hub / empty) rows are stepped over
+      tt[v] = t;
+      jj[v] = rp[t] + (c - cp[t]);
+    } else {
+      tt[v] = 0;
+      jj[v] = 0;
+    }
+  }
+  return cnt;
+}
+
 // ---- count ------------------------------------------------------------------------------------------------------------
 template <int DT>
 __device__ __forceinline__ void count_entry(int j, int b, int pb, double v, int row_start, int ag, long long n_cols,
@@ -498,25 +522,31 @@ tile_count_kernel(const int *__restrict__ indptr, const int *__restrict__ indice
   hdk[threadIdx.x] = 0;
   const int total = tile_setup(indptr, r0, nr, rp, cp, &hubs);
   int fl = 0;
-  constexpr int U = 4;   // independent loads in flight per thread
-  for (int c0 = threadIdx.x; c0 < total; c0 += U * kTileRows) {
-    int b[U], pb[U], tt[U], jj[U];
-    double v[U];
+  constexpr int G = 2;   // groups per thread and iteration: 2 x kGroup independent loads in flight
+  for (int base = 0; base < total; base += G * kTileRows * kGroup) {
+    int b[G][kGroup], tt[G][kGroup], jj[G][kGroup], pb0[G], cnt[G];
+    double v[G][kGroup];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int c = c0 + u * kTileRows;
-      tt[u] = (c < total) ? tile_row_of(cp, nr, c) : 0;
-      jj[u] = rp[tt[u]] + (c - cp[tt[u]]);
-      b[u] = (c < total) ? ld_stream_i32(indices + jj[u]) : 0;
-      pb[u] = (c < total && jj[u] > rp[tt[u]]) ? __ldg(indices + jj[u] - 1) : -1;
-      v[u] = (DT != SRG_VAL_ONES && c < total) ? ValLoad<DT>::at(data, jj[u]) : 1.0;
+    for (int g = 0; g < G; ++g) {
+      cnt[g] = tile_group(rp, cp, nr, total, base + (g * kTileRows + (int)threadIdx.x) * kGroup, tt[g], jj[g]);
+#pragma unroll
+      for (int u = 0; u < kGroup; ++u) {
+        b[g][u] = (u < cnt[g]) ? __ldg(indices + jj[g][u]) : 0;
+        v[g][u] = (DT != SRG_VAL_ONES && u < cnt[g]) ? ValLoad<DT>::at(data, jj[g][u]) : 1.0;
+      }
+      pb0[g] = (cnt[g] > 0 && jj[g][0] > rp[tt[g][0]]) ? __ldg(indices + jj[g][0] - 1) : -1;
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (c0 + u * kTileRows >= total) break;
-      int bits = 0;
-      count_entry<DT>(jj[u], b[u], pb[u], v[u], rp[tt[u]], (int)(r0 + tt[u] + row0), n_cols, fl, bits);
-      if (bits) hdk[tt[u]] = bits;
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int u = 0; u < kGroup; ++u) {
+        if (u >= cnt[g]) break;
+        // previous entry of the same row: the group's previous element unless this one starts its row
+        const int pb = (u == 0) ? pb0[g] : ((tt[g][u] == tt[g][u - 1]) ? b[g][u - 1] : -1);
+        int bits = 0;
+        count_entry<DT>(jj[g][u], b[g][u], pb, v[g][u], rp[tt[g][u]], (int)(r0 + tt[g][u] + row0), n_cols, fl, bits);
+        if (bits) hdk[tt[g][u]] = bits;
+      }
     }
   }
   __syncthreads();
@@ -578,24 +608,27 @@ tile_fill_unweighted_kernel(const int *__restrict__ indptr, const int *__restric
   const int nr = (int)min((long long)kTileRows, n_rows - r0);
   for (int t = threadIdx.x; t <= nr; t += kTileRows) ap[t] = at_indptr[r0 + t];
   const int total = tile_setup(indptr, r0, nr, rp, cp, &hubs);
-  constexpr int U = 4;
-  for (int c0 = threadIdx.x; c0 < total; c0 += U * kTileRows) {
-    int bb[U], pbb[U], tt[U], jj[U];
+  constexpr int G = 2;
+  for (int base = 0; base < total; base += G * kTileRows * kGroup) {
+    int bb[G][kGroup], tt[G][kGroup], jj[G][kGroup], pb0[G], cnt[G];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int c = c0 + u * kTileRows;
-      tt[u] = (c < total) ? tile_row_of(cp, nr, c) : 0;
-      jj[u] = rp[tt[u]] + (c - cp[tt[u]]);
-      bb[u] = (c < total) ? ld_stream_i32(indices + jj[u]) : 0;
-      pbb[u] = (c < total && jj[u] > rp[tt[u]]) ? __ldg(indices + jj[u] - 1) : -1;
+    for (int g = 0; g < G; ++g) {
+      cnt[g] = tile_group(rp, cp, nr, total, base + (g * kTileRows + (int)threadIdx.x) * kGroup, tt[g], jj[g]);
+#pragma unroll
+      for (int u = 0; u < kGroup; ++u) bb[g][u] = (u < cnt[g]) ? __ldg(indices + jj[g][u]) : 0;
+      pb0[g] = (cnt[g] > 0 && jj[g][0] > rp[tt[g][0]]) ? __ldg(indices + jj[g][0] - 1) : -1;
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (c0 + u * kTileRows >= total) break;
-      const int t = tt[u];
-      const int s = rp[t], e = rp[t + 1];
-      const int hd = ((ap[t + 1] - ap[t]) == (e - s)) ? 1 : 0;
-      fill_entry(jj[u], bb[u], pbb[u], s, e, (int)(r0 + t + row0), ap[t], hd, at_indices);
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int u = 0; u < kGroup; ++u) {
+        if (u >= cnt[g]) break;
+        const int t = tt[g][u];
+        const int s = rp[t], e = rp[t + 1];
+        const int hd = ((ap[t + 1] - ap[t]) == (e - s)) ? 1 : 0;
+        const int pb = (u == 0) ? pb0[g] : ((t == tt[g][u - 1]) ? bb[g][u - 1] : -1);
+        fill_entry(jj[g][u], bb[g][u], pb, s, e, (int)(r0 + t + row0), ap[t], hd, at_indices);
+      }
     }
   }
   if ((int)threadIdx.x < nr) {
@@ -725,6 +758,9 @@ tile_values_kernel(long long n_rows, long long row0, const int *__restrict__ at_
   __syncthreads();
   int fl = 0;
   unsigned long long s1 = 0, s2 = 0;   // upper - lower, two independent sums (wrap-around arithmetic)
+  // one entry per thread and iteration here (not the 4-consecutive grouping of count / fill): this pass is bound by
+  // the random dr[b] gathers, i.e. by how many of them are in flight, and the grouped form's 88 registers halved the
+  // resident warps (measured 683 vs 518 us at the products shape)
   constexpr int U = 4;
   for (int c0 = threadIdx.x; c0 < total; c0 += U * kTileRows) {
     int bb[U], tt[U], pp[U];

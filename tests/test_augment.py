@@ -63,3 +63,31 @@ def test_endpoint_counts_and_visiting_order():
     np.testing.assert_array_equal(cnts, want[nodes])
     with pytest.raises(IndexError):
         augment.endpoint_counts(torch.tensor([0, n]).cuda(), torch.tensor([1, 2]).cuda(), n)
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_host_side_of_the_mirror_vs_reference_golden(tag):
+    """The host logic of augment.edge_augument without a GPU: visiting order (low_degree_order) and the reference's
+    candidate stream (draw_candidates) fed with numpy stand-ins for the three device stages reproduce the reference's
+    edge_index, i.e. what stays on the host is exactly the reference's and the device stages are plain data-parallel
+    work (counts, distances + top-k, symmetrise + unique)."""
+    from scalable_roubust_gnn_b200 import augment
+    c = _case(tag)
+    n, level = int(c["n"]), int(c["degree_level"])
+    both = np.concatenate([c["row"], c["col"]])
+    counts = np.bincount(both, minlength=n).astype(np.int32)
+    first = np.full(n, np.iinfo(np.int64).max, dtype=np.int64)
+    np.minimum.at(first, both, np.arange(len(both), dtype=np.int64))
+    nodes, cnts = augment.low_degree_order(torch.from_numpy(counts), torch.from_numpy(first), level)
+    random.seed(int(c["seed"]))
+    cands = augment.draw_candidates(nodes, cnts, n, level)
+    src, dst = [c["row"]], [c["col"]]
+    for node, cnt, cand in zip(nodes, cnts, cands):
+        diff = c["soft"][node][None, :] - c["soft"][cand]
+        dist = np.sqrt((diff.astype(np.float64) ** 2).sum(1)).astype(np.float32)
+        order = np.argsort(dist, kind="stable")[: level - cnt]
+        src.append(np.full(level - cnt, node, dtype=np.int64))
+        dst.append(cand[order].astype(np.int64))
+    r, cc = np.concatenate(src), np.concatenate(dst)
+    got = np.unique(np.stack([np.concatenate([r, cc]), np.concatenate([cc, r])]), axis=1)
+    np.testing.assert_array_equal(got, c["edge_index"])

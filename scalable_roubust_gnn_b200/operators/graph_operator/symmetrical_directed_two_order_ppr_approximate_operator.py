@@ -1,7 +1,7 @@
 """SymDirTwoOrderPprApproxGraphOp — first- and second-order PPR-approximation operators, normalised on the GPU.
 
 Mirror of SSRG/operators/graph_operator/symmetrical_directed_two_order_ppr_approximate_operator.py:7-16.
-Round-1 status: the device normaliser has not run on hardware yet (its test is opt-in).
+The device normaliser is compared with the reference's own outputs in tests/test_fast_ppr.py (-m gpu).
 """
 from ..base_operator import TwoOrderPprApproxGraphOp
 from ..utils import adj_to_slow_first_second_ppr_approx_symmetric_norm

@@ -88,7 +88,7 @@ def test_argument_validation_matches_reference_messages():
 
 
 def test_host_all_ones_check():
-    """Host utility of the (opt-in) unweighted-adjacency shortcut: multithreaded scan for values != 1."""
+    """Host utility of the unweighted-adjacency shortcut (on by default): multithreaded scan for values != 1."""
     lib = _lib.load()
     for dt, vt in ((np.float64, _lib.SRG_VAL_F64), (np.float32, _lib.SRG_VAL_F32)):
         a = np.ones(300_001, dtype=dt)

@@ -194,9 +194,10 @@ static int staging_threads() {
   static const int v = [] {
     const char *e = getenv("SRG_STAGE_THREADS");
     // measured at the products shape (1.24 GB of pageable input, 16 host CPUs): driver path 172 ms end to end,
-    // 2 threads 146, 4 threads 106, 8 threads 99, pinned inputs 85
+    // 2 threads 146, 4 threads 106, 8 threads 99, pinned inputs 85; on a second, slower box 8 / 12 / 16 threads =
+    // 107.5 / 99.8 / 97.3 ms (pinned 89): the staging copy is bound by host memory bandwidth, so take every CPU
     const int hw = (int)std::thread::hardware_concurrency();
-    int t = e ? atoi(e) : std::max(2, std::min(8, hw / 2));
+    int t = e ? atoi(e) : std::max(2, std::min(16, hw));
     return std::max(0, std::min(t, 16));
   }();
   return v;   // 0: leave pageable copies to the driver

@@ -75,7 +75,11 @@ int64_t srg_launch_count(void);
  *   warp task;  "group_unroll" 4|8;  "gather_l2_64" 0|1;  "long_row" split threshold (0 = never);
  *   "bulk_gather" -1 auto | 0 never | 1 always (rows <= 512 B fetched by TMA bulk copies), "bulk_auto" / "bulk_min"
  *   widest / narrowest padded row (floats) of the automatic choice, "bulk_stages" 2..4, "bulk_rows" rows per warp
- *   task, "bulk_tile" 0|1 finished rows leave as one bulk store per destination;  "push_tma" 0|1 */
+ *   task, "bulk_tile" 0|1 finished rows leave as one bulk store per destination;  "push_tma" 0|1 bulk-store tile
+ *   epilogue of the LDGSTS push hop;  "push_rows_tma" 0|1 input exchange through the TMA unit, "push_rows_tma_blocks"
+ *   / "push_rows_blocks" its grid / the grid of the st.global form;  "exact_sym_check" 0|1 per-entry mirror lookup
+ *   instead of the hashed symmetry check of the normalisation.  SRG_TUNE="key=value,..." sets them from the
+ *   environment when the Python package loads the library. */
 int srg_set_tuning(const char *key, int64_t value);
 
 /* ---- a3: adjacency normalisation  (SSRG/operators/utils.py:81-93) ------------------------ */

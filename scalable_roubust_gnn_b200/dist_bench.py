@@ -125,6 +125,9 @@ def run(args, workloads, metric, unit, emit):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                        # before the warm-up: its start-up must not hit timed steps
+    # the ranks finish their host-side set-up (graph generation, uploads) seconds apart; the flag fence of the first
+    # step waits for a peer for 2 s at most, so line the ranks up before the first step
+    dist.barrier()
     for _ in range(args.warmup):
         flags, _ = step()
     torch.cuda.synchronize()
@@ -410,6 +413,7 @@ def _e2e(args, st, a_loc_host, x_loc_host, k, f_loc, lib, dev, sdist, torch, dis
             o.copy_(d_flat, non_blocking=True)
         torch.cuda.synchronize()
 
+    dist.barrier()                             # pinning the host buffers takes a different time on every rank
     e2e_step()
     dist.barrier()
     t0 = time.perf_counter()

@@ -108,3 +108,57 @@ def test_grid_coordinates_and_feature_slices():
     assert cover == list(range(129))
     with pytest.raises(ValueError):
         sdist.grid_coords(0, 6, 4)
+
+
+def _grid_worker(rank, world, port, n, f, k, pf, out_dir):
+    """2 x 2 grid (row blocks x feature slices): every rank propagates ITS feature slice over ITS row block and
+    exchanges rows only with the ranks that hold the same slice (push_peers) - the scheme of the 8-GPU bench."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import scipy.sparse as sp
+        groups = {}
+        for ci in range(pf):                       # new_group is collective: every rank creates every group
+            members = sdist.push_peers(ci, world, pf)
+            groups[ci] = (members, dist.new_group(members))
+        ri, ci = sdist.grid_coords(rank, world, pf)
+        members, group = groups[ci]
+        assert members == sdist.push_peers(rank, world, pf) and members[ri] == rank
+        n_blocks = world // pf
+        adj = sym_graph(n, 8 * n, 5)
+        x = np.random.default_rng(1).random((n, f), dtype=np.float32)
+        norm = oracle.sym_norm(adj, 0.5)
+        rows_per, starts = sdist.row_partition(n, n_blocks)
+        s, e = int(starts[ri]), int(starts[ri + 1])
+        f0, f1 = sdist.feature_slice(f, pf, ci)
+        local = sdist.shard_rows(norm, s, e)
+        local = sp.csr_matrix((local.data, local.indices, local.indptr), shape=(e - s, rows_per * n_blocks))
+
+        class _GroupOps(_GlooOps):
+            def exchange(self, full):
+                mine = torch.from_numpy(full[self.rank * self.rows_per:(self.rank + 1) * self.rows_per].copy())
+                dist.all_gather_into_tensor(torch.from_numpy(full), mine, group=group)
+
+        ops = _GroupOps(n, f1 - f0, rows_per, n_blocks, ri, s, e - s)      # "rank" inside the group = row block index
+        hops = sdist.propagate_sharded(ops, local, np.ascontiguousarray(x[s:e, f0:f1]), k, rows_per, n_blocks)
+        np.save(os.path.join(out_dir, f"grid_{rank}.npy"), np.stack(hops))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_by_feature_grid_bitwise_equals_single_process(tmp_path):
+    world, pf, n, f, k = 4, 2, 1003, 13, 3
+    port = 29400 + (os.getpid() % 500)
+    mp.spawn(_grid_worker, args=(world, port, n, f, k, pf, str(tmp_path)), nprocs=world, join=True)
+    adj = sym_graph(n, 8 * n, 5)
+    x = np.random.default_rng(1).random((n, f), dtype=np.float32)
+    want, _ = oracle.propagate(adj, x, k)
+    rows_per, starts = sdist.row_partition(n, world // pf)
+    for rank in range(world):
+        ri, ci = sdist.grid_coords(rank, world, pf)
+        f0, f1 = sdist.feature_slice(f, pf, ci)
+        got = np.load(tmp_path / f"grid_{rank}.npy")
+        for h in range(k + 1):
+            # every output element is one FMA chain over the row's entries: slicing columns or rows changes no bit
+            np.testing.assert_array_equal(got[h], want[h][int(starts[ri]):int(starts[ri + 1]), f0:f1])
